@@ -1,0 +1,119 @@
+/*
+ * nkprecond.h -- C ABI of the B200 sparse direct solver for the Newton-Krylov ocean
+ * tracer-Jacobian preconditioner.
+ *
+ * This is the drop-in boundary for the ONE hot path of the reference
+ * (klindsay28/NK_ocn_tracer_jacobian_precond): the external SuperLU_DIST calls
+ *
+ *     pdgssvx_ABglobal(..., nrhs=0, ...)   src/solve_ABglobal.c:353   (factor)
+ *     pdgssvx_ABglobal(..., nrhs=1, ...)   src/solve_ABglobal.c:395   (solve + refine)
+ *     pdgssvx(..., nrhs=0, ...)            src/solve_ABdist.c:518     (factor)
+ *     pdgssvx(..., nrhs=1, ...)            src/solve_ABdist.c:571     (solve + refine)
+ *
+ * operating on the CRS operand of src/matrix.h:64-68 (flat_len, nnz, nzval_row_wise,
+ * colind, rowptr) and the flattened tracer right-hand side of src/solve_ABglobal.c:184-191.
+ * include/compat/superlu_ddefs.h maps those SuperLU names onto the calls below so the
+ * reference's main()s build unchanged; new callers use this header directly.
+ *
+ * Plain C: pointers and sizes only.  All functions return 0 on success, a negative
+ * NKP_E* code on failure; nothing here ever falls back to a CPU solver -- if CUDA or a
+ * GPU is unavailable the call fails with NKP_ECUDA.
+ */
+#ifndef NKPRECOND_H
+#define NKPRECOND_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NKP_OK 0
+#define NKP_EINVAL (-1)
+#define NKP_EANALYSIS (-2)
+#define NKP_ECUDA (-3)
+#define NKP_ENOMEM (-4)
+#define NKP_ESTATE (-5)
+
+typedef struct nkp_solver nkp_solver;
+
+/* Options; zero-initialise then call nkp_default_options. */
+typedef struct nkp_options {
+    int nb;              /* pivot block width (<= 64)                                    */
+    int leaf;            /* nested dissection stops below this many unknowns             */
+    int equil;           /* 1: row/column equilibration (SuperLU Equil=YES)              */
+    int refine_max;      /* max refinement steps (SuperLU IterRefine=SLU_DOUBLE, ITMAX)  */
+    int device;          /* CUDA device ordinal                                          */
+    int verbose;         /* 0 silent, 1 phase summary on stderr                          */
+    int reserved[10];
+} nkp_options;
+
+/* Statistics in the spirit of PStatPrint (src/solve_ABglobal.c:351-360). */
+typedef struct nkp_stats {
+    int n;
+    int64_t nnz;
+    int n_fronts;
+    int n_levels;
+    int max_front;
+    int64_t nnz_lu;          /* stored entries of L + U (incl. diagonal)          */
+    double factor_flops;     /* algorithmic flops of the numeric factorisation    */
+    double heap_bytes;       /* device bytes: factors + update-matrix pools       */
+    double t_analysis;       /* host seconds: ordering + symbolic + plan          */
+    double t_factor;         /* device seconds of the last numeric factorisation  */
+    double t_scatter;        /* ... of which zero-fill + CRS->front scatter       */
+    double t_solve;          /* device seconds of the last solve (all rhs, incl. refinement) */
+    int refine_steps;        /* refinement steps taken by the last solve          */
+    int tiny_pivots;         /* pivots replaced in the last factorisation         */
+    int64_t kernel_launches; /* kernels launched by this handle so far            */
+    double solve_bytes;      /* algorithmic bytes of one forward+backward sweep   */
+    double reserved[8];
+} nkp_stats;
+
+void nkp_default_options(nkp_options* opt);
+
+/* Analysis (ordering, symbolic factorisation, memory plan, task lists) for the pattern
+ * (n, rowptr, colind), 0-based CRS as in src/matrix.c:84-88.  coord_i/j/k are optional
+ * per-unknown grid coordinates (tracer_state_ind_to_{i,j,k}, src/matrix.c:322-329; repeat
+ * them per coupled tracer); pass NULL to order from the graph alone.  Replaces the
+ * ordering/symbolic half of the first pdgssvx* call.  The handle is reusable for any
+ * number of nkp_factor calls with new values on the same pattern. */
+int nkp_create(nkp_solver** out, int n, const int* rowptr, const int* colind,
+               const int* coord_i, const int* coord_j, const int* coord_k,
+               const nkp_options* opt);
+
+/* Numeric factorisation from HOST values (nzval_row_wise, src/matrix.c:84), includes the
+ * host->device copy.  Replaces pdgssvx*(nrhs = 0). */
+int nkp_factor(nkp_solver* s, const double* nzval);
+/* Same with the values already resident in device memory. */
+int nkp_factor_device(nkp_solver* s, const double* d_nzval);
+
+/* Solve A X = B in place, B column-major n x nrhs with leading dimension ldb, HOST
+ * memory; iterative refinement included; berr[nrhs] (may be NULL) receives the
+ * componentwise backward errors.  Replaces pdgssvx*(Fact = FACTORED, nrhs >= 1). */
+int nkp_solve(nkp_solver* s, double* B, int ldb, int nrhs, double* berr);
+/* Same with B in device memory (berr stays a host pointer). */
+int nkp_solve_device(nkp_solver* s, double* d_B, int ldb, int nrhs, double* berr);
+
+/* Residual r = b - A x for the currently loaded values (device pointers, column-major
+ * with leading dimension n); the refinement SpMV exposed for testing and measurement. */
+int nkp_residual_device(nkp_solver* s, const double* d_x, const double* d_b, double* d_r, int nrhs);
+
+/* One forward+backward sweep pair without refinement (device pointers): d_B is
+ * overwritten by the solution of the factored (equilibrated, permuted) system. */
+int nkp_sweeps_device(nkp_solver* s, double* d_B, int ldb, int nrhs);
+
+/* The fill-reducing permutation: perm[old] = new (n entries). */
+int nkp_get_perm(const nkp_solver* s, int* perm);
+int nkp_get_stats(const nkp_solver* s, nkp_stats* st);
+/* Block until all device work of this handle has finished. */
+int nkp_sync(nkp_solver* s);
+void nkp_destroy(nkp_solver* s);
+
+const char* nkp_last_error(void);
+const char* nkp_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,692 @@
+// analysis.cpp -- host analysis phase of the B200 tracer-Jacobian solver.
+//
+// Replaces what SuperLU_DIST does inside the first pdgssvx* call of the reference
+// drivers before numeric factorisation (src/SuperLU_brief_tree.txt:4-9: column
+// ordering, symbfact, ddistribute; options at src/solve_ABglobal.c:332-334):
+//
+//   1. structure of A + A^T
+//   2. fill-reducing nested-dissection ordering.  Every unknown of the reference's
+//      operand is an ocean cell with integer coordinates (i,j,k) stored in the matrix
+//      file (src/matrix.c:322-329), so the dissection is geometric: median cuts along
+//      the coordinate direction that yields the smallest *actual* vertex separator
+//      (the boundary of one half towards the other, computed from the graph, which
+//      handles the periodic i direction of src/matrix.c:795-798 and the +-2 reach of
+//      upwind3 without special cases).  Without coordinates a BFS level-structure
+//      dissection is used.
+//   3. assembly tree = dissection tree (separators/leaves are the supernodes),
+//      postorder numbering, symbolic front structures
+//   4. memory plan (factor arena + two ping-pong pools of update matrices)
+//   5. static task lists for every kernel launch of the numeric phase and solves
+//
+// The result depends only on the sparsity pattern and is reused across numeric
+// refactorisations (BASELINE.json config 5).
+#include "nkp_internal.hpp"
+
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+
+namespace nkp {
+
+namespace {
+
+double now_s() {
+    using namespace std::chrono;
+    return duration<double>(steady_clock::now().time_since_epoch()).count();
+}
+
+struct Graph {
+    int n = 0;
+    std::vector<int64_t> xadj;
+    std::vector<int> adj;
+};
+
+// symmetric structure of A + A^T without the diagonal
+void build_graph(int n, const int* rowptr, const int* colind, Graph& g) {
+    g.n = n;
+    std::vector<int64_t> cnt(n + 1, 0);
+    for (int i = 0; i < n; i++)
+        for (int p = rowptr[i]; p < rowptr[i + 1]; p++) {
+            int j = colind[p];
+            if (j == i) continue;
+            cnt[i + 1]++;
+            cnt[j + 1]++;
+        }
+    for (int i = 0; i < n; i++) cnt[i + 1] += cnt[i];
+    std::vector<int> tmp(cnt[n]);
+    std::vector<int64_t> pos(cnt.begin(), cnt.end() - 1);
+    for (int i = 0; i < n; i++)
+        for (int p = rowptr[i]; p < rowptr[i + 1]; p++) {
+            int j = colind[p];
+            if (j == i) continue;
+            tmp[pos[i]++] = j;
+            tmp[pos[j]++] = i;
+        }
+    // sort + unique each list
+    g.xadj.assign(n + 1, 0);
+    g.adj.resize(cnt[n]);
+    int64_t w = 0;
+    for (int i = 0; i < n; i++) {
+        int64_t b = cnt[i], e = cnt[i + 1];
+        std::sort(tmp.begin() + b, tmp.begin() + e);
+        g.xadj[i] = w;
+        int last = -1;
+        for (int64_t p = b; p < e; p++)
+            if (tmp[p] != last) {
+                g.adj[w++] = tmp[p];
+                last = tmp[p];
+            }
+    }
+    g.xadj[n] = w;
+    g.adj.resize(w);
+}
+
+struct TreeNode {
+    std::vector<int> verts;     // original vertex ids, ascending
+    std::vector<int> children;
+    int parent = -1;
+};
+
+struct Dissector {
+    const Graph& g;
+    const int* const* coords;   // may be null
+    Options opt;
+    std::vector<int> order;     // vertex list, partitioned in place
+    std::vector<int> regid;     // region id per vertex
+    std::vector<signed char> side;
+    std::vector<int> scratch;
+    std::vector<TreeNode> nodes;
+    int next_rid = 1;
+
+    Dissector(const Graph& g_, const int* const* c, const Options& o) : g(g_), coords(c), opt(o) {
+        order.resize(g.n);
+        std::iota(order.begin(), order.end(), 0);
+        regid.assign(g.n, 0);
+        side.assign(g.n, 0);
+    }
+
+    int make_node(int begin, int end, const std::vector<int>& children) {
+        TreeNode nd;
+        nd.verts.assign(order.begin() + begin, order.begin() + end);
+        std::sort(nd.verts.begin(), nd.verts.end());
+        nd.children = children;
+        int id = (int)nodes.size();
+        nodes.push_back(std::move(nd));
+        for (int c : children) nodes[c].parent = id;
+        return id;
+    }
+
+    // Evaluate the split "side[v] in {0,1}" of region rid: count the one-sided separators.
+    // Returns sizes of S_a (side-0 vertices touching side 1) and S_b.
+    void count_sep(int begin, int end, int rid, int& sa, int& sb) const {
+        sa = sb = 0;
+        for (int p = begin; p < end; p++) {
+            int v = order[p];
+            int sv = side[v];
+            bool touch = false;
+            for (int64_t q = g.xadj[v]; q < g.xadj[v + 1]; q++) {
+                int u = g.adj[q];
+                if (regid[u] == rid && side[u] != sv) {
+                    touch = true;
+                    break;
+                }
+            }
+            if (touch) (sv == 0 ? sa : sb)++;
+        }
+    }
+
+    struct Cand {
+        double score = 1e300;
+        int dim = -1;
+        int cut = 0;       // side 0: coord < cut
+        int take = 0;      // 0: separator from side 0, 1: from side 1
+        int sep = 0;
+    };
+
+    void try_dim(int begin, int end, int rid, int d, Cand& best) {
+        const int* x = coords[d];
+        int nv = end - begin;
+        scratch.resize(nv);
+        for (int p = 0; p < nv; p++) scratch[p] = x[order[begin + p]];
+        std::nth_element(scratch.begin(), scratch.begin() + nv / 2, scratch.end());
+        int med = scratch[nv / 2];
+        int lo = *std::min_element(scratch.begin(), scratch.end());
+        int hi = *std::max_element(scratch.begin(), scratch.end());
+        if (lo == hi) return;
+        int cut = med;
+        if (cut == lo) cut = lo + 1;  // side 0 must be non-empty
+        int n0 = 0;
+        for (int p = begin; p < end; p++) {
+            int v = order[p];
+            side[v] = (x[v] < cut) ? 0 : 1;
+            n0 += (side[v] == 0);
+        }
+        int n1 = nv - n0;
+        if (n0 == 0 || n1 == 0) return;
+        int sa, sb;
+        count_sep(begin, end, rid, sa, sb);
+        for (int take = 0; take < 2; take++) {
+            int sep = take == 0 ? sa : sb;
+            int r0 = n0 - (take == 0 ? sa : 0);
+            int r1 = n1 - (take == 1 ? sb : 0);
+            double minfrac = (double)std::min(r0, r1) / nv;
+            double score = (double)sep * (1.0 + 4.0 * std::max(0.0, 0.30 - minfrac)) + 1e-3 * std::abs(r0 - r1);
+            if (score < best.score) {
+                best.score = score;
+                best.dim = d;
+                best.cut = cut;
+                best.take = take;
+                best.sep = sep;
+            }
+        }
+    }
+
+    // BFS level-structure split when no coordinates are available
+    bool bfs_split(int begin, int end, int rid) {
+        int nv = end - begin;
+        std::vector<int>& lvl = scratch;
+        lvl.assign(nv, 0);
+        // local index map through side[] is not possible (n large) -> use a per-call map in regid-tagged array
+        // we reuse `dist` stored in a member vector sized n lazily
+        if (dist.size() != (size_t)g.n) dist.assign(g.n, -1);
+        auto bfs = [&](int src, std::vector<int>& out) {
+            out.clear();
+            out.push_back(src);
+            dist[src] = 0;
+            for (size_t h = 0; h < out.size(); h++) {
+                int v = out[h];
+                for (int64_t q = g.xadj[v]; q < g.xadj[v + 1]; q++) {
+                    int u = g.adj[q];
+                    if (regid[u] == rid && dist[u] < 0) {
+                        dist[u] = dist[v] + 1;
+                        out.push_back(u);
+                    }
+                }
+            }
+        };
+        std::vector<int> reach, reach2;
+        bfs(order[begin], reach);
+        int far = reach.back();
+        for (int v : reach) dist[v] = -1;
+        if ((int)reach.size() < nv) {
+            // disconnected: reached component vs the rest, empty separator
+            for (int p = begin; p < end; p++) side[order[p]] = 1;
+            for (int v : reach) side[v] = 0;
+            return true;
+        }
+        bfs(far, reach2);
+        int maxd = dist[reach2.back()];
+        if (maxd < 2) {
+            for (int v : reach2) dist[v] = -1;
+            return false;
+        }
+        std::vector<int> cntl(maxd + 1, 0);
+        for (int v : reach2) cntl[dist[v]]++;
+        // choose the smallest level whose cumulative position lies in the middle 40 %
+        int best = -1;
+        int cum = 0;
+        for (int l = 0; l <= maxd; l++) {
+            int before = cum;
+            cum += cntl[l];
+            if (l == 0 || l == maxd) continue;
+            double fb = (double)before / nv, fa = (double)(nv - cum) / nv;
+            if (fb < 0.25 || fa < 0.25) continue;
+            if (best < 0 || cntl[l] < cntl[best]) best = l;
+        }
+        if (best < 0) best = maxd / 2 == 0 ? 1 : maxd / 2;
+        for (int v : reach2) {
+            side[v] = dist[v] < best ? 0 : (dist[v] > best ? 1 : 2);
+            dist[v] = -1;
+        }
+        return true;
+    }
+    std::vector<int> dist;
+
+    void build(int begin, int end, std::vector<int>& roots_out) {
+        int nv = end - begin;
+        if (nv == 0) return;
+        if (nv <= opt.leaf) {
+            roots_out.push_back(make_node(begin, end, {}));
+            return;
+        }
+        int rid = next_rid++;
+        for (int p = begin; p < end; p++) regid[order[p]] = rid;
+
+        bool ok = false;
+        if (coords) {
+            Cand best;
+            for (int d = 0; d < 3; d++)
+                if (coords[d]) try_dim(begin, end, rid, d, best);
+            if (best.dim >= 0) {
+                const int* x = coords[best.dim];
+                for (int p = begin; p < end; p++) {
+                    int v = order[p];
+                    side[v] = (x[v] < best.cut) ? 0 : 1;
+                }
+                // mark the separator (one-sided boundary)
+                std::vector<int> sepv;
+                for (int p = begin; p < end; p++) {
+                    int v = order[p];
+                    if (side[v] != best.take) continue;
+                    for (int64_t q = g.xadj[v]; q < g.xadj[v + 1]; q++) {
+                        int u = g.adj[q];
+                        if (regid[u] == rid && side[u] == 1 - best.take) {
+                            sepv.push_back(v);
+                            break;
+                        }
+                    }
+                }
+                for (int v : sepv) side[v] = 2;
+                ok = true;
+            }
+        }
+        if (!ok) ok = bfs_split(begin, end, rid);
+        if (!ok) {
+            roots_out.push_back(make_node(begin, end, {}));
+            return;
+        }
+        // partition order[begin:end) into [side0 | side1 | sep]
+        int n0 = 0, n1 = 0, n2 = 0;
+        for (int p = begin; p < end; p++) {
+            int sv = side[order[p]];
+            n0 += sv == 0;
+            n1 += sv == 1;
+            n2 += sv == 2;
+        }
+        if ((n0 == 0 && n2 == 0) || (n1 == 0 && n2 == 0) || n2 == nv) {
+            roots_out.push_back(make_node(begin, end, {}));
+            return;
+        }
+        {
+            std::vector<int> tmp(order.begin() + begin, order.begin() + end);
+            int p0 = begin, p1 = begin + n0, p2 = begin + n0 + n1;
+            for (int v : tmp) {
+                int sv = side[v];
+                if (sv == 0) order[p0++] = v;
+                else if (sv == 1) order[p1++] = v;
+                else order[p2++] = v;
+            }
+        }
+        std::vector<int> child_roots;
+        build(begin, begin + n0, child_roots);
+        build(begin + n0, begin + n0 + n1, child_roots);
+        if (n2 == 0) {
+            roots_out.insert(roots_out.end(), child_roots.begin(), child_roots.end());
+            return;
+        }
+        roots_out.push_back(make_node(begin + n0 + n1, end, child_roots));
+    }
+};
+
+}  // namespace
+
+int analyse(int n, const int* rowptr, const int* colind, const int* const coords[3],
+            const Options& opt, Plan& plan) {
+    plan = Plan();
+    plan.n = n;
+    plan.nnz = rowptr[n];
+    plan.opt = opt;
+    const int nb = opt.nb;
+    if (opt.tn > nb || nb % opt.tn != 0) return -2;
+
+    double t0 = now_s();
+    Graph g;
+    build_graph(n, rowptr, colind, g);
+
+    bool have_coords = coords && (coords[0] || coords[1] || coords[2]);
+    Dissector ds(g, have_coords ? coords : nullptr, opt);
+    std::vector<int> roots;
+    ds.build(0, n, roots);
+    std::vector<TreeNode>& nodes = ds.nodes;
+    int nf = (int)nodes.size();
+
+    // nodes were created in postorder (children before parents)
+    plan.fronts.assign(nf, Front());
+    plan.perm.assign(n, -1);
+    plan.iperm.assign(n, -1);
+    {
+        int next = 0;
+        for (int t = 0; t < nf; t++) {
+            Front& f = plan.fronts[t];
+            f.first = next;
+            f.s = (int)nodes[t].verts.size();
+            f.parent = nodes[t].parent;
+            f.nchild = (int)nodes[t].children.size();
+            for (size_t c = 0; c < nodes[t].children.size(); c++) plan.fronts[nodes[t].children[c]].child_rank = (int)c;
+            for (int v : nodes[t].verts) {
+                plan.perm[v] = next;
+                plan.iperm[next] = v;
+                next++;
+            }
+        }
+        if (next != n) return -3;
+    }
+    plan.roots = roots;
+    plan.t_order = now_s() - t0;
+
+    // ---- symbolic: boundary index sets --------------------------------------------------
+    t0 = now_s();
+    std::vector<int64_t> boff(nf + 1, 0);
+    {
+        std::vector<int> mark(n, -1);
+        std::vector<int> cand;
+        plan.bidx.clear();
+        for (int t = 0; t < nf; t++) {
+            Front& f = plan.fronts[t];
+            int last = f.first + f.s - 1;
+            cand.clear();
+            for (int v : nodes[t].verts)
+                for (int64_t q = g.xadj[v]; q < g.xadj[v + 1]; q++) {
+                    int pu = plan.perm[g.adj[q]];
+                    if (pu > last && mark[pu] != t) {
+                        mark[pu] = t;
+                        cand.push_back(pu);
+                    }
+                }
+            for (int c : nodes[t].children) {
+                const Front& fc = plan.fronts[c];
+                for (int64_t q = 0; q < fc.r; q++) {
+                    int pu = plan.bidx[fc.bidx_off + q];
+                    if (pu > last && mark[pu] != t) {
+                        mark[pu] = t;
+                        cand.push_back(pu);
+                    }
+                }
+            }
+            std::sort(cand.begin(), cand.end());
+            f.r = (int)cand.size();
+            f.m = f.s + f.r;
+            f.bidx_off = (int64_t)plan.bidx.size();
+            plan.bidx.insert(plan.bidx.end(), cand.begin(), cand.end());
+            boff[t + 1] = (int64_t)plan.bidx.size();
+            plan.max_front = std::max(plan.max_front, f.m);
+        }
+    }
+    // roots must have empty boundaries
+    for (int t : roots)
+        if (plan.fronts[t].r != 0) return -4;
+
+    // levels (depth from root); fronts are in postorder so parents come later
+    for (int t = nf - 1; t >= 0; t--) {
+        Front& f = plan.fronts[t];
+        f.level = f.parent < 0 ? 0 : plan.fronts[f.parent].level + 1;
+        plan.nlevels = std::max(plan.nlevels, f.level + 1);
+    }
+
+    // parent-local indices
+    plan.rel.assign(plan.bidx.size(), -1);
+    for (int t = 0; t < nf; t++) {
+        Front& f = plan.fronts[t];
+        f.rel_off = f.bidx_off;
+        if (f.parent < 0) continue;
+        const Front& p = plan.fronts[f.parent];
+        const int* pb = plan.bidx.data() + p.bidx_off;
+        int64_t q = 0;  // merge pointer into the parent's boundary
+        for (int a = 0; a < f.r; a++) {
+            int x = plan.bidx[f.bidx_off + a];
+            int loc;
+            if (x < p.first + p.s) {
+                if (x < p.first) return -5;
+                loc = x - p.first;
+            } else {
+                while (q < p.r && pb[q] < x) q++;
+                if (q >= p.r || pb[q] != x) return -6;
+                loc = p.s + (int)q;
+            }
+            plan.rel[f.rel_off + a] = loc;
+        }
+    }
+    plan.t_symbolic = now_s() - t0;
+
+    // ---- memory plan ------------------------------------------------------------------------
+    t0 = now_s();
+    const int64_t AL = 16;  // 128-byte alignment in doubles
+    int64_t off = 0;
+    double flops = 0;
+    int64_t nnz_lu = 0;
+    for (int t = 0; t < nf; t++) {
+        Front& f = plan.fronts[t];
+        f.Loff = off;
+        off = align_up(off + (int64_t)f.m * f.s, AL);
+        f.UToff = off;
+        off = align_up(off + (int64_t)f.m * f.s, AL);
+        double s = f.s, r = f.r;
+        flops += 2.0 / 3.0 * s * s * s + 2.0 * s * s * r + 2.0 * s * r * r;
+        nnz_lu += (int64_t)f.s * f.s + 2 * (int64_t)f.s * f.r;
+    }
+    plan.factor_len = off;
+    plan.flops = flops;
+    plan.nnz_lu = nnz_lu;
+
+    plan.levels.assign(plan.nlevels, LevelPlan());
+    for (int l = 0; l < plan.nlevels; l++) plan.levels[l].level = l;
+    for (int t = 0; t < nf; t++) plan.levels[plan.fronts[t].level].fronts.push_back(t);
+    // update-matrix pools: level l uses pool l & 1
+    {
+        int64_t len[2] = {0, 0};
+        for (int l = 0; l < plan.nlevels; l++) {
+            int64_t o = 0;
+            for (int t : plan.levels[l].fronts) {
+                Front& f = plan.fronts[t];
+                f.F22off = o;  // relative to the pool start, fixed up below
+                o = align_up(o + (int64_t)f.r * f.r, AL);
+            }
+            plan.levels[l].f22_zero_len = o;
+            len[l & 1] = std::max(len[l & 1], o);
+        }
+        plan.pool_len[0] = len[0];
+        plan.pool_len[1] = len[1];
+        plan.pool_off[0] = plan.factor_len;
+        plan.pool_off[1] = plan.factor_len + len[0];
+        plan.heap_len = plan.factor_len + len[0] + len[1];
+        for (int l = 0; l < plan.nlevels; l++) {
+            plan.levels[l].f22_zero_off = plan.pool_off[l & 1];
+            for (int t : plan.levels[l].fronts) plan.fronts[t].F22off += plan.pool_off[l & 1];
+        }
+    }
+    // solve work vectors
+    {
+        int64_t o = 0;
+        for (int t = 0; t < nf; t++) {
+            plan.fronts[t].woff = o;
+            o += plan.fronts[t].m;
+        }
+        plan.solve_pool_len = o;
+    }
+
+    // ---- scatter map: CRS entry -> heap offset ---------------------------------------------
+    {
+        // front of each permuted index
+        std::vector<int> front_of(n);
+        for (int t = 0; t < nf; t++)
+            for (int a = 0; a < plan.fronts[t].s; a++) front_of[plan.fronts[t].first + a] = t;
+        plan.scatter.resize(plan.nnz);
+        for (int i = 0; i < n; i++) {
+            int pi = plan.perm[i];
+            for (int p = rowptr[i]; p < rowptr[i + 1]; p++) {
+                int pj = plan.perm[colind[p]];
+                int t = front_of[std::min(pi, pj)];
+                const Front& f = plan.fronts[t];
+                auto local = [&](int x) -> int {
+                    if (x < f.first + f.s) return x - f.first;
+                    const int* b = plan.bidx.data() + f.bidx_off;
+                    const int* e = b + f.r;
+                    const int* it = std::lower_bound(b, e, x);
+                    if (it == e || *it != x) return -1;
+                    return f.s + (int)(it - b);
+                };
+                int a = local(pi), b = local(pj);
+                if (a < 0 || b < 0) return -7;
+                plan.scatter[p] = front_entry(a, b, f.s, f.m, nb, f.Loff, f.UToff, f.F22off);
+            }
+        }
+    }
+
+    // ---- task lists ------------------------------------------------------------------------------
+    for (int l = plan.nlevels - 1; l >= 0; l--) {
+        LevelPlan& L = plan.levels[l];
+        int maxs = 0;
+        for (int t : L.fronts) maxs = std::max(maxs, plan.fronts[t].s);
+        L.nsteps = (maxs + nb - 1) / nb;
+
+        // extend-add passes: children (level l+1) grouped by child_rank
+        int npass = 0;
+        for (int t : L.fronts) npass = std::max(npass, plan.fronts[t].nchild);
+        L.add_begin.assign(npass + 1, 0);
+        L.add_tiles.assign(npass, 0);
+        if (l + 1 < plan.nlevels) {
+            for (int pass = 0; pass < npass; pass++) {
+                L.add_begin[pass] = (int)plan.add_tasks.size();
+                int tile0 = 0;
+                for (int c : plan.levels[l + 1].fronts) {
+                    const Front& fc = plan.fronts[c];
+                    if (fc.child_rank != pass || fc.r == 0) continue;
+                    const Front& fp = plan.fronts[fc.parent];
+                    AddTask a;
+                    a.Coff = fc.F22off;
+                    a.rel_off = fc.rel_off;
+                    a.Loff = fp.Loff;
+                    a.UToff = fp.UToff;
+                    a.F22off = fp.F22off;
+                    a.rc = fc.r;
+                    a.sp = fp.s;
+                    a.mp = fp.m;
+                    a.tile0 = tile0;
+                    a.tiles_m = (fc.r + opt.add_tile - 1) / opt.add_tile;
+                    a.pad = 0;
+                    tile0 += a.tiles_m * a.tiles_m;
+                    plan.add_tasks.push_back(a);
+                }
+                L.add_tiles[pass] = tile0;
+            }
+        }
+        L.add_begin[npass] = (int)plan.add_tasks.size();
+
+        L.diag_begin.assign(L.nsteps + 1, 0);
+        L.trsm_begin.assign(L.nsteps + 1, 0);
+        L.gemm_begin.assign(L.nsteps + 1, 0);
+        L.trsm_ctas.assign(L.nsteps, 0);
+        L.gemm_tiles.assign(L.nsteps, 0);
+        for (int step = 0; step < L.nsteps; step++) {
+            L.diag_begin[step] = (int)plan.diag_tasks.size();
+            L.trsm_begin[step] = (int)plan.trsm_tasks.size();
+            L.gemm_begin[step] = (int)plan.gemm_tasks.size();
+            int cta0 = 0, tile0 = 0;
+            int k0 = step * nb;
+            for (int t : L.fronts) {
+                const Front& f = plan.fronts[t];
+                if (k0 >= f.s) continue;
+                int kb = std::min(nb, f.s - k0);
+                int k1 = k0 + kb;
+                int64_t Dblk = f.Loff + k0 + (int64_t)k0 * f.m;
+                DiagTask d;
+                d.Doff = Dblk;
+                d.UTDoff = f.UToff + k0 + (int64_t)k0 * f.m;
+                d.ld = f.m;
+                d.kb = kb;
+                plan.diag_tasks.push_back(d);
+                int below = f.m - k1;
+                if (below > 0) {
+                    for (int which = 0; which < 2; which++) {
+                        TrsmTask tt;
+                        tt.Xoff = (which == 0 ? f.Loff : f.UToff) + k1 + (int64_t)k0 * f.m;
+                        tt.Toff = Dblk;
+                        tt.ld = f.m;
+                        tt.nrows = below;
+                        tt.kb = kb;
+                        tt.unit = which;
+                        tt.cta0 = cta0;
+                        tt.pad = 0;
+                        cta0 += (below + opt.trsm_rows - 1) / opt.trsm_rows;
+                        plan.trsm_tasks.push_back(tt);
+                    }
+                    int trail_s = f.s - k1;  // remaining pivot columns
+                    auto push_gemm = [&](int64_t A, int64_t B, int64_t C, int M, int N, int lda, int ldb, int ldc, int skip) {
+                        if (M <= 0 || N <= 0) return;
+                        GemmTask gt;
+                        gt.Aoff = A;
+                        gt.Boff = B;
+                        gt.Coff = C;
+                        gt.M = M;
+                        gt.N = N;
+                        gt.K = kb;
+                        gt.lda = lda;
+                        gt.ldb = ldb;
+                        gt.ldc = ldc;
+                        gt.skip = skip;
+                        gt.tile0 = tile0;
+                        gt.tiles_m = (M + opt.tm - 1) / opt.tm;
+                        gt.pad = 0;
+                        tile0 += gt.tiles_m * ((N + opt.tn - 1) / opt.tn);
+                        plan.gemm_tasks.push_back(gt);
+                    };
+                    int64_t Lpan = f.Loff + k1 + (int64_t)k0 * f.m;    // L[k1.., k0:k1]
+                    int64_t UTpan = f.UToff + k1 + (int64_t)k0 * f.m;  // U^T[k1.., k0:k1]
+                    if (trail_s > 0) {
+                        // block-lower targets in Larr: rows k1..m, cols k1..s
+                        push_gemm(Lpan, UTpan, f.Loff + k1 + (int64_t)k1 * f.m, below, trail_s, f.m, f.m, f.m, 1);
+                        // strictly block-upper targets in UTarr: rows (front cols) k1..m, cols (front rows) k1..s
+                        push_gemm(UTpan, Lpan, f.UToff + k1 + (int64_t)k1 * f.m, below, trail_s, f.m, f.m, f.m, 2);
+                    }
+                    if (f.r > 0) {
+                        int64_t Lb = f.Loff + f.s + (int64_t)k0 * f.m;
+                        int64_t UTb = f.UToff + f.s + (int64_t)k0 * f.m;
+                        push_gemm(Lb, UTb, f.F22off, f.r, f.r, f.m, f.m, f.r, 0);
+                    }
+                }
+            }
+            L.trsm_ctas[step] = cta0;
+            L.gemm_tiles[step] = tile0;
+        }
+        L.diag_begin[L.nsteps] = (int)plan.diag_tasks.size();
+        L.trsm_begin[L.nsteps] = (int)plan.trsm_tasks.size();
+        L.gemm_begin[L.nsteps] = (int)plan.gemm_tasks.size();
+    }
+
+    // solve tasks grouped by level, deepest first
+    for (int l = plan.nlevels - 1; l >= 0; l--) {
+        LevelPlan& L = plan.levels[l];
+        L.solve_begin = (int)plan.solve_tasks.size();
+        for (int t : L.fronts) {
+            const Front& f = plan.fronts[t];
+            SolveTask st;
+            st.Loff = f.Loff;
+            st.UToff = f.UToff;
+            st.bidx_off = f.bidx_off;
+            st.rel_off = f.rel_off;
+            st.woff = f.woff;
+            st.child_list = (int64_t)plan.solve_children.size();
+            st.first = f.first;
+            st.s = f.s;
+            st.r = f.r;
+            st.m = f.m;
+            st.nchild = f.nchild;
+            st.pad = 0;
+            for (int c : nodes[t].children) {
+                const Front& fc = plan.fronts[c];
+                SolveChild sc;
+                sc.woff = fc.woff;
+                sc.rel_off = fc.rel_off;
+                sc.s = fc.s;
+                sc.r = fc.r;
+                plan.solve_children.push_back(sc);
+            }
+            plan.solve_tasks.push_back(st);
+        }
+        L.solve_end = (int)plan.solve_tasks.size();
+    }
+    plan.t_plan = now_s() - t0;
+
+    if (opt.verbose) {
+        fprintf(stderr,
+                "[nkp] analysis: n=%d nnz=%lld fronts=%d levels=%d max_front=%d nnz(LU)=%lld (%.2f GB) "
+                "heap=%.2f GB flops=%.3e  t(order,symb,plan)=%.2f,%.2f,%.2f s\n",
+                n, (long long)plan.nnz, nf, plan.nlevels, plan.max_front, (long long)plan.nnz_lu,
+                plan.nnz_lu * 8e-9, plan.heap_len * 8e-9, plan.flops, plan.t_order, plan.t_symbolic, plan.t_plan);
+    }
+    return 0;
+}
+
+}  // namespace nkp

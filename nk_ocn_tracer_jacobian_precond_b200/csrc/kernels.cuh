@@ -1,0 +1,582 @@
+// kernels.cuh -- sm_100a kernels of the multifrontal numeric phase and the solves.
+//
+// Replaces the inside of SuperLU_DIST's pdgstrf / pdgstrs / pdgsrfs as called by the
+// reference (src/SuperLU_brief_tree.txt:11-24).  Every kernel is driven by a static task
+// list built by the host analysis (nkp_internal.hpp); a launch covers ALL fronts of one
+// assembly-tree level, so the launch count does not depend on the number of fronts.
+//
+//   k_scatter        CRS (scaled) -> front storage                       HBM bound
+//   k_extend_add     child update matrix -> parent front                 HBM bound
+//   k_diag           nb x nb diagonal-block LU, static pivoting          latency bound
+//   k_trsm           tall panel  X * T = B  (L panel and U^T panel)      FP64 FMA
+//   k_gemm           Schur update C -= A * B^T, FP64 tensor cores (DMMA) FP64 tensor
+//   k_fwd / k_bwd    level-scheduled triangular sweeps, multi-RHS        HBM bound
+//   k_residual       r = b - A x and |A||x|+|b| (refinement, berr)       HBM bound
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "nkp_internal.hpp"
+
+namespace nkp {
+
+// ------------------------------------------------------------------------------------------
+// helpers
+// ------------------------------------------------------------------------------------------
+
+// largest t in [0,n) with key(t) <= idx, keys ascending, key(0) == 0
+template <class T, class F>
+__device__ __forceinline__ int find_task(const T* tasks, int n, int idx, F key) {
+    int lo = 0, hi = n - 1;
+    while (lo < hi) {
+        int mid = (lo + hi + 1) >> 1;
+        if (key(tasks[mid]) <= idx) lo = mid;
+        else hi = mid - 1;
+    }
+    return lo;
+}
+
+__device__ __forceinline__ int64_t d_front_entry(int a, int b, int s, int m, int nb,
+                                                 int64_t Loff, int64_t UToff, int64_t F22off) {
+    if (b < s) {
+        if (a >= s || a / nb >= b / nb) return Loff + a + (int64_t)b * m;
+        return UToff + b + (int64_t)a * m;
+    }
+    if (a < s) return UToff + b + (int64_t)a * m;
+    return F22off + (a - s) + (int64_t)(b - s) * (m - s);
+}
+
+__device__ __forceinline__ void atomic_max_pos_double(double* addr, double v) {
+    // valid for non-negative doubles: their bit patterns order like unsigned integers
+    atomicMax(reinterpret_cast<unsigned long long*>(addr), (unsigned long long)__double_as_longlong(v));
+}
+
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem, bool pred) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    int sz = pred ? 8 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(s), "l"(gmem), "r"(sz));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::); }
+
+// D(8x8) += A(8x4) * B(4x8), FP64 tensor core
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+// ------------------------------------------------------------------------------------------
+// equilibration (dgsequ-style row / column scalings, rounded to powers of two)
+// ------------------------------------------------------------------------------------------
+
+__global__ void k_row_scale(int n, const int* __restrict__ rowptr, const double* __restrict__ val,
+                            double* __restrict__ R) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double mx = 0;
+    for (int p = rowptr[i]; p < rowptr[i + 1]; p++) mx = fmax(mx, fabs(val[p]));
+    double r = 1.0;
+    if (mx > 0) {
+        int e;
+        frexp(mx, &e);           // mx = f * 2^e, f in [0.5,1)
+        r = ldexp(1.0, 1 - e);   // r * mx in [1,2)
+    }
+    R[i] = r;
+}
+
+__global__ void k_col_max(int64_t nnz, const int* __restrict__ rowidx, const int* __restrict__ colind,
+                          const double* __restrict__ val, const double* __restrict__ R,
+                          double* __restrict__ cmax) {
+    int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= nnz) return;
+    double v = fabs(val[p]) * R[rowidx[p]];
+    atomic_max_pos_double(&cmax[colind[p]], v);
+}
+
+__global__ void k_col_scale(int n, double* __restrict__ C) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double mx = C[i];
+    double c = 1.0;
+    if (mx > 0) {
+        int e;
+        frexp(mx, &e);
+        c = ldexp(1.0, 1 - e);
+    }
+    C[i] = c;
+}
+
+__global__ void k_fill(double* p, int64_t n, double v) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+// ------------------------------------------------------------------------------------------
+// CRS -> front scatter
+// ------------------------------------------------------------------------------------------
+
+__global__ void k_scatter(int64_t nnz, const double* __restrict__ val, const int64_t* __restrict__ dst,
+                          const int* __restrict__ rowidx, const int* __restrict__ colind,
+                          const double* __restrict__ R, const double* __restrict__ C,
+                          double* __restrict__ heap) {
+    int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= nnz) return;
+    double v = val[p] * R[rowidx[p]] * C[colind[p]];
+    atomicAdd(&heap[dst[p]], v);   // duplicates in the CRS (if any) are summed, as sum_dup_vals would
+}
+
+// ------------------------------------------------------------------------------------------
+// extend-add
+// ------------------------------------------------------------------------------------------
+
+constexpr int ADD_TILE = 32;
+
+__global__ void __launch_bounds__(256) k_extend_add(const AddTask* __restrict__ tasks, int ntasks,
+                                                    const int* __restrict__ rel, double* __restrict__ heap,
+                                                    int nb) {
+    int t = find_task(tasks, ntasks, (int)blockIdx.x, [](const AddTask& x) { return x.tile0; });
+    const AddTask tk = tasks[t];
+    int local = blockIdx.x - tk.tile0;
+    int ti = local % tk.tiles_m, tj = local / tk.tiles_m;
+    const int* rl = rel + tk.rel_off;
+    const double* Cc = heap + tk.Coff;
+    int a = ti * ADD_TILE + (threadIdx.x & 31);
+    int ra = a < tk.rc ? rl[a] : 0;
+    for (int jj = threadIdx.x >> 5; jj < ADD_TILE; jj += 8) {
+        int b = tj * ADD_TILE + jj;
+        if (a < tk.rc && b < tk.rc) {
+            int rb = rl[b];
+            double v = Cc[a + (int64_t)b * tk.rc];
+            int64_t d = d_front_entry(ra, rb, tk.sp, tk.mp, nb, tk.Loff, tk.UToff, tk.F22off);
+            heap[d] += v;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// diagonal block LU (kb <= 64), static pivoting with tiny-pivot replacement
+// ------------------------------------------------------------------------------------------
+
+constexpr int NBMAX = 64;
+
+__global__ void __launch_bounds__(256) k_diag(const DiagTask* __restrict__ tasks, double* __restrict__ heap,
+                                              double tiny, int* __restrict__ n_replaced) {
+    __shared__ double D[NBMAX * (NBMAX + 1)];   // column-major, ld = NBMAX+1
+    const DiagTask tk = tasks[blockIdx.x];
+    const int kb = tk.kb, ld = tk.ld;
+    double* G = heap + tk.Doff;
+    const int LDS = NBMAX + 1;
+    for (int e = threadIdx.x; e < NBMAX * NBMAX; e += blockDim.x) {
+        int i = e % NBMAX, j = e / NBMAX;
+        D[i + j * LDS] = (i < kb && j < kb) ? G[i + (int64_t)j * ld] : (i == j ? 1.0 : 0.0);
+    }
+    __syncthreads();
+    const int i = threadIdx.x & 63;      // row owned by this thread
+    const int seg = threadIdx.x >> 6;    // 16-column segment
+    for (int k = 0; k < kb; k++) {
+        // row k and column k are final here; nobody writes them during this step
+        double p = D[k + k * LDS];
+        if (fabs(p) < tiny) {
+            p = p < 0 ? -tiny : tiny;
+            if (threadIdx.x == 0) atomicAdd(n_replaced, 1);
+        }
+        double l = 0.0;
+        if (i > k && i < kb) {
+            l = D[i + k * LDS] / p;
+            const int j0 = seg * 16;
+#pragma unroll
+            for (int jj = 0; jj < 16; jj++) {
+                int j = j0 + jj;
+                if (j > k && j < kb) D[i + j * LDS] -= l * D[k + j * LDS];
+            }
+        }
+        __syncthreads();
+        // column k is dead for the elimination now: store the multipliers / the (replaced) pivot
+        if (seg == 0 && i < kb) {
+            if (i > k) D[i + k * LDS] = l;
+            else if (i == k) D[k + k * LDS] = p;
+        }
+    }
+    __syncthreads();
+    // write back packed LU to Larr, U_kk^T to the UTarr diagonal block
+    double* GU = heap + tk.UTDoff;
+    for (int e = threadIdx.x; e < kb * kb; e += blockDim.x) {
+        int a = e % kb, b = e / kb;
+        double v = D[a + b * LDS];
+        G[a + (int64_t)b * ld] = v;
+        if (a <= b) GU[b + (int64_t)a * ld] = v;   // U(a,b) -> UT[b,a]
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// panel solve  X * T = B,  T upper triangular kb x kb (kb <= 64), one thread per row
+// ------------------------------------------------------------------------------------------
+
+constexpr int TRSM_ROWS = 128;
+
+__global__ void __launch_bounds__(TRSM_ROWS) k_trsm(const TrsmTask* __restrict__ tasks, int ntasks,
+                                                   double* __restrict__ heap) {
+    __shared__ double T[NBMAX * NBMAX];   // T[p + j*NBMAX], p <= j ; diagonal holds 1/T_jj
+    int t = find_task(tasks, ntasks, (int)blockIdx.x, [](const TrsmTask& x) { return x.cta0; });
+    const TrsmTask tk = tasks[t];
+    const int kb = tk.kb, ld = tk.ld;
+    const double* G = heap + tk.Toff;
+    for (int e = threadIdx.x; e < NBMAX * NBMAX; e += blockDim.x) {
+        int p = e % NBMAX, j = e / NBMAX;
+        double v = 0.0;
+        if (p < kb && j < kb) {
+            if (tk.unit == 0) {
+                if (p < j) v = G[p + (int64_t)j * ld];
+                else if (p == j) v = 1.0 / G[p + (int64_t)p * ld];
+            } else {
+                if (p < j) v = G[j + (int64_t)p * ld];   // L_kk^T
+                else if (p == j) v = 1.0;
+            }
+        } else if (p == j) v = 1.0;
+        T[e] = v;
+    }
+    __syncthreads();
+    int row = (blockIdx.x - tk.cta0) * TRSM_ROWS + threadIdx.x;
+    if (row >= tk.nrows) return;
+    double* X = heap + tk.Xoff + row;
+    double x[NBMAX];
+#pragma unroll
+    for (int j = 0; j < NBMAX; j++) x[j] = j < kb ? X[(int64_t)j * ld] : 0.0;
+#pragma unroll
+    for (int j = 0; j < NBMAX; j++) {
+        double acc = x[j];
+#pragma unroll
+        for (int p = 0; p < j; p++) acc -= x[p] * T[p + j * NBMAX];
+        x[j] = acc * T[j + j * NBMAX];
+    }
+#pragma unroll
+    for (int j = 0; j < NBMAX; j++)
+        if (j < kb) X[(int64_t)j * ld] = x[j];
+}
+
+// ------------------------------------------------------------------------------------------
+// Schur update  C[M x N] -= A[M x K] * B[N x K]^T   (K <= 64), FP64 DMMA m8n8k4
+// CTA tile 128 x 64, 8 warps (4 x 2), warp tile 32 x 32.
+// ------------------------------------------------------------------------------------------
+
+constexpr int G_TM = 128, G_TN = 64, G_TK = 64;
+constexpr int G_LDA = G_TM + 4;   // == 4 (mod 16): conflict-free 8-byte fragment loads
+constexpr int G_LDB = G_TN + 4;
+constexpr int G_SMEM = (G_TK * G_LDA + G_TK * G_LDB) * 8;
+
+__global__ void __launch_bounds__(256, 2) k_gemm(const GemmTask* __restrict__ tasks, int ntasks,
+                                                 double* __restrict__ heap, int nb) {
+    extern __shared__ __align__(16) double smem[];
+    double* As = smem;                    // As[k * G_LDA + m]
+    double* Bs = smem + G_TK * G_LDA;     // Bs[k * G_LDB + n]
+    int t = find_task(tasks, ntasks, (int)blockIdx.x, [](const GemmTask& x) { return x.tile0; });
+    const GemmTask tk = tasks[t];
+    int local = blockIdx.x - tk.tile0;
+    int ti = local % tk.tiles_m, tj = local / tk.tiles_m;
+    int rend = (ti + 1) * G_TM;
+    if (tk.skip == 1 && rend <= (tj * G_TN / nb) * nb) return;
+    if (tk.skip == 2 && rend <= min((tj * G_TN / nb + 1) * nb, tk.N)) return;
+    const int m0 = ti * G_TM, n0 = tj * G_TN;
+    const double* A = heap + tk.Aoff + m0;
+    const double* B = heap + tk.Boff + n0;
+    const int mrem = tk.M - m0, nrem = tk.N - n0, K = tk.K;
+
+    // stage A (128 x 64) and B (64 x 64) tiles, zero-filling out-of-range elements
+    for (int e = threadIdx.x; e < G_TK * G_TM; e += 256) {
+        int i = e % G_TM, k = e / G_TM;
+        bool ok = (i < mrem) && (k < K);
+        cp_async8(&As[k * G_LDA + i], ok ? (A + i + (int64_t)k * tk.lda) : A, ok);
+    }
+    for (int e = threadIdx.x; e < G_TK * G_TN; e += 256) {
+        int i = e % G_TN, k = e / G_TN;
+        bool ok = (i < nrem) && (k < K);
+        cp_async8(&Bs[k * G_LDB + i], ok ? (B + i + (int64_t)k * tk.ldb) : B, ok);
+    }
+    cp_async_commit();
+    cp_async_wait_all();
+    __syncthreads();
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int wm = (warp & 3) * 32, wn = (warp >> 2) * 32;
+    const int lr = lane >> 2, lc = lane & 3;
+    double acc[4][4][2];
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int b = 0; b < 4; b++) acc[a][b][0] = acc[a][b][1] = 0.0;
+
+    const int ksteps = (K + 3) >> 2;
+    for (int ks = 0; ks < ksteps; ks++) {
+        const double* ap = As + (ks * 4 + lc) * G_LDA + wm + lr;
+        const double* bp = Bs + (ks * 4 + lc) * G_LDB + wn + lr;
+        double af[4], bf[4];
+#pragma unroll
+        for (int a = 0; a < 4; a++) af[a] = ap[a * 8];
+#pragma unroll
+        for (int b = 0; b < 4; b++) bf[b] = bp[b * 8];
+#pragma unroll
+        for (int a = 0; a < 4; a++)
+#pragma unroll
+            for (int b = 0; b < 4; b++) dmma884(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
+    }
+    __syncthreads();
+    // stage the product through shared memory so that the read-modify-write of C is coalesced
+    double* Cs = smem;   // Cs[n * G_LDA + m]
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+            int r = wm + a * 8 + lr;
+            int c = wn + b * 8 + 2 * lc;
+            Cs[c * G_LDA + r] = acc[a][b][0];
+            Cs[(c + 1) * G_LDA + r] = acc[a][b][1];
+        }
+    __syncthreads();
+    double* C = heap + tk.Coff + m0 + (int64_t)n0 * tk.ldc;
+    for (int e = threadIdx.x; e < G_TM * G_TN; e += 256) {
+        int i = e % G_TM, j = e / G_TM;
+        if (i < mrem && j < nrem) C[i + (int64_t)j * tk.ldc] -= Cs[j * G_LDA + i];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// right-hand-side handling
+// ------------------------------------------------------------------------------------------
+
+// y[perm[i], c] = R[i] * b[i, c]
+__global__ void k_permute_in(int n, int nrhs, const int* __restrict__ perm, const double* __restrict__ R,
+                             const double* __restrict__ b, int ldb, double* __restrict__ y) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int pi = perm[i];
+    double r = R[i];
+    for (int c = 0; c < nrhs; c++) y[pi + (int64_t)c * n] = r * b[i + (int64_t)c * ldb];
+}
+
+// x[i, c] (+)= C[i] * y[perm[i], c]
+__global__ void k_permute_out(int n, int nrhs, const int* __restrict__ perm, const double* __restrict__ Cs,
+                              const double* __restrict__ y, double* __restrict__ x, int ldx, int accumulate) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int pi = perm[i];
+    double cs = Cs[i];
+    for (int c = 0; c < nrhs; c++) {
+        double v = cs * y[pi + (int64_t)c * n];
+        if (accumulate) x[i + (int64_t)c * ldx] += v;
+        else x[i + (int64_t)c * ldx] = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// triangular sweeps: one CTA per front, NR right-hand sides at a time
+// W (work vectors) layout: front t, rhs c  ->  W[(woff_t) * NRtot + c * m_t + a]
+// ------------------------------------------------------------------------------------------
+
+constexpr int SOLVE_THREADS = 256;
+
+template <int NR>
+__global__ void __launch_bounds__(SOLVE_THREADS) k_fwd(const SolveTask* __restrict__ tasks,
+                                                       const SolveChild* __restrict__ children,
+                                                       const int* __restrict__ rel,
+                                                       const double* __restrict__ heap, double* __restrict__ W,
+                                                       double* __restrict__ y, int n, int nrtot) {
+    __shared__ double tri[32 * 33];
+    __shared__ double yb[32 * NR];
+    const SolveTask tk = tasks[blockIdx.x];
+    const int s = tk.s, m = tk.m;
+    double* w = W + tk.woff * nrtot;
+    const double* L = heap + tk.Loff;
+    // 1. load pivots' rhs, clear boundary part
+    for (int a = threadIdx.x; a < m; a += SOLVE_THREADS)
+#pragma unroll
+        for (int c = 0; c < NR; c++) w[a + (int64_t)c * m] = a < s ? y[tk.first + a + (int64_t)c * n] : 0.0;
+    __syncthreads();
+    // 2. add the children's update vectors (children in fixed order: deterministic)
+    for (int ch = 0; ch < tk.nchild; ch++) {
+        const SolveChild sc = children[tk.child_list + ch];
+        const int mc = sc.s + sc.r;
+        const double* wc = W + sc.woff * nrtot + sc.s;
+        const int* rl = rel + sc.rel_off;
+        for (int a = threadIdx.x; a < sc.r; a += SOLVE_THREADS) {
+            int d = rl[a];
+#pragma unroll
+            for (int c = 0; c < NR; c++) w[d + (int64_t)c * m] += wc[a + (int64_t)c * mc];
+        }
+        __syncthreads();
+    }
+    // 3. blocked forward substitution with L (unit lower), 32 columns at a time
+    for (int k0 = 0; k0 < s; k0 += 32) {
+        const int kb = min(32, s - k0);
+        for (int e = threadIdx.x; e < 32 * 32; e += SOLVE_THREADS) {
+            int a = e & 31, p = e >> 5;
+            tri[a + p * 33] = (a < kb && p < kb && a > p) ? L[k0 + a + (int64_t)(k0 + p) * m] : 0.0;
+        }
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            const int a = threadIdx.x;
+            double v[NR];
+#pragma unroll
+            for (int c = 0; c < NR; c++) v[c] = a < kb ? w[k0 + a + (int64_t)c * m] : 0.0;
+            for (int p = 0; p < kb; p++) {
+                double l = tri[a + p * 33];
+#pragma unroll
+                for (int c = 0; c < NR; c++) {
+                    double yp = __shfl_sync(0xffffffffu, v[c], p);
+                    v[c] -= l * yp;
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < NR; c++) {
+                yb[a + 32 * c] = v[c];
+                if (a < kb) w[k0 + a + (int64_t)c * m] = v[c];
+            }
+        }
+        __syncthreads();
+        const int k1 = k0 + kb;
+        for (int a = k1 + threadIdx.x; a < m; a += SOLVE_THREADS) {
+            double acc[NR];
+#pragma unroll
+            for (int c = 0; c < NR; c++) acc[c] = 0.0;
+            const double* Lp = L + a + (int64_t)k0 * m;
+            for (int p = 0; p < kb; p++) {
+                double l = Lp[(int64_t)p * m];
+#pragma unroll
+                for (int c = 0; c < NR; c++) acc[c] += l * yb[p + 32 * c];
+            }
+#pragma unroll
+            for (int c = 0; c < NR; c++) w[a + (int64_t)c * m] -= acc[c];
+        }
+        __syncthreads();
+    }
+    // 4. publish the pivots' part
+    for (int a = threadIdx.x; a < s; a += SOLVE_THREADS)
+#pragma unroll
+        for (int c = 0; c < NR; c++) y[tk.first + a + (int64_t)c * n] = w[a + (int64_t)c * m];
+}
+
+template <int NR>
+__global__ void __launch_bounds__(SOLVE_THREADS) k_bwd(const SolveTask* __restrict__ tasks,
+                                                       const int* __restrict__ bidx,
+                                                       const double* __restrict__ heap, double* __restrict__ W,
+                                                       double* __restrict__ y, int n, int nrtot) {
+    __shared__ double tri[32 * 33];
+    __shared__ double z[32 * NR];
+    const SolveTask tk = tasks[blockIdx.x];
+    const int s = tk.s, m = tk.m;
+    double* w = W + tk.woff * nrtot;
+    const double* UT = heap + tk.UToff;
+    const int* bi = bidx + tk.bidx_off;
+    for (int a = threadIdx.x; a < tk.r; a += SOLVE_THREADS) {
+        int g = bi[a];
+#pragma unroll
+        for (int c = 0; c < NR; c++) w[s + a + (int64_t)c * m] = y[g + (int64_t)c * n];
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nblk = (s + 31) / 32;
+    for (int blk = nblk - 1; blk >= 0; blk--) {
+        const int k0 = blk * 32;
+        const int kb = min(32, s - k0);
+        const int k1 = k0 + kb;
+        // (i) z[p] = y[p] - sum_{a >= k1} UT[a,p] * w[a]   (one warp per column)
+        for (int p = warp; p < kb; p += SOLVE_THREADS / 32) {
+            double acc[NR];
+#pragma unroll
+            for (int c = 0; c < NR; c++) acc[c] = 0.0;
+            const double* Up = UT + (int64_t)(k0 + p) * m;
+            for (int a = k1 + lane; a < m; a += 32) {
+                double u = Up[a];
+#pragma unroll
+                for (int c = 0; c < NR; c++) acc[c] += u * w[a + (int64_t)c * m];
+            }
+#pragma unroll
+            for (int c = 0; c < NR; c++) {
+                double v = acc[c];
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                if (lane == 0) z[p + 32 * c] = y[tk.first + k0 + p + (int64_t)c * n] - v;
+            }
+        }
+        for (int e = threadIdx.x; e < 32 * 32; e += SOLVE_THREADS) {
+            int a = e & 31, p = e >> 5;   // tri[a + p*33] = UT[k0+a, k0+p] = U(p, a), a >= p
+            tri[a + p * 33] = (a < kb && p < kb && a >= p) ? UT[k0 + a + (int64_t)(k0 + p) * m] : 0.0;
+        }
+        __syncthreads();
+        // (ii) back substitution in the 32 x 32 triangle (one warp): lane p owns x[p]
+        if (threadIdx.x < 32) {
+            const int p = threadIdx.x;
+            double v[NR];
+#pragma unroll
+            for (int c = 0; c < NR; c++) v[c] = p < kb ? z[p + 32 * c] : 0.0;
+            double dinv = p < kb ? 1.0 / tri[p + p * 33] : 0.0;
+            for (int q = kb - 1; q >= 0; q--) {
+                // finalize x[q], then eliminate it from rows p < q
+                double u = tri[q + p * 33];   // U(p, q) for p <= q
+#pragma unroll
+                for (int c = 0; c < NR; c++) {
+                    if (p == q) v[c] *= dinv;
+                    double xq = __shfl_sync(0xffffffffu, v[c], q);
+                    if (p < q) v[c] -= u * xq;
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < NR; c++)
+                if (p < kb) {
+                    w[k0 + p + (int64_t)c * m] = v[c];
+                    y[tk.first + k0 + p + (int64_t)c * n] = v[c];
+                }
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// residual and componentwise backward error (pdgsrfs: pdgsmv_AXglobal, pdgsmv_AXglobal_abs)
+//   r = b - A x ;  berr_c = max_i |r_i| / (|A||x| + |b|)_i
+// ------------------------------------------------------------------------------------------
+
+__global__ void k_residual(int n, int nrhs, const int* __restrict__ rowptr, const int* __restrict__ colind,
+                           const double* __restrict__ val, const double* __restrict__ x, int ldx,
+                           const double* __restrict__ b, int ldb, double* __restrict__ r,
+                           double* __restrict__ berr, double safe) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int p0 = rowptr[i], p1 = rowptr[i + 1];
+    for (int c = 0; c < nrhs; c++) {
+        const double* xc = x + (int64_t)c * ldx;
+        double bi = b[i + (int64_t)c * ldb];
+        double acc = bi, aabs = fabs(bi);
+        for (int p = p0; p < p1; p++) {
+            double a = val[p], xv = xc[colind[p]];
+            acc = fma(-a, xv, acc);
+            aabs = fma(fabs(a), fabs(xv), aabs);
+        }
+        r[i + (int64_t)c * n] = acc;
+        if (berr) {
+            double e = aabs > safe ? fabs(acc) / aabs : (fabs(acc) + safe) / (aabs + safe);
+            atomic_max_pos_double(&berr[c], e);
+        }
+    }
+}
+
+// sum of squares per column (for the relative residual reported in the stats)
+__global__ void k_sumsq(int n, int nrhs, const double* __restrict__ v, int ld, double* __restrict__ out) {
+    __shared__ double red[256];
+    for (int c = 0; c < nrhs; c++) {
+        double acc = 0;
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+            double t = v[i + (int64_t)c * ld];
+            acc += t * t;
+        }
+        red[threadIdx.x] = acc;
+        __syncthreads();
+        for (int o = 128; o > 0; o >>= 1) {
+            if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) atomicAdd(&out[c], red[0]);
+        __syncthreads();
+    }
+}
+
+}  // namespace nkp

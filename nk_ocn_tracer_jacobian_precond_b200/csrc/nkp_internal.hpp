@@ -1,0 +1,182 @@
+// nkp_internal.hpp -- shared definitions between the host analysis (analysis.cpp),
+// the CUDA numeric phase (solver.cu / kernels.cuh) and the CPU plan simulator used by
+// the tests (oracle/plan_sim.cpp).
+//
+// The solver replaces what the reference obtains from SuperLU_DIST's pdgssvx*
+// (src/solve_ABglobal.c:353,395 ; src/solve_ABdist.c:518,571): analysis on the host
+// (ordering, assembly tree, symbolic fronts, memory plan, task lists), numeric
+// multifrontal LU + triangular solves + refinement on the GPU.
+//
+// Storage layout of one front t (s pivots, r boundary rows/cols, m = s + r):
+//   Larr  : m x s column-major (ld = m).  Holds every entry (a,b) of the front with
+//           b < s and (a >= s or blk(a) >= blk(b)), i.e. the block-lower part
+//           including the full nb x nb diagonal blocks.  After factorisation:
+//           L (unit lower) below the diagonal blocks, packed LU in the diagonal blocks.
+//   UTarr : m x s column-major (ld = m).  Holds U TRANSPOSED: entry (a,b) of the front
+//           with a < s and (b >= s or blk(b) > blk(a)) is stored at UTarr[b + a*m].
+//           After factorisation the diagonal blocks additionally receive U_kk^T, so the
+//           backward solve reads UTarr only.
+//   F22   : r x r column-major (ld = r), the update (Schur complement) matrix, lives in a
+//           per-level ping-pong pool and dies once the parent has been assembled.
+// Keeping U transposed makes every panel a tall column-major array: the L and U panel
+// solves are one kernel (X * T = B, T upper triangular) and every Schur update is the
+// same "C -= A * B^T" GEMM with coalesced operand loads.
+#pragma once
+#include <cstdint>
+#include <vector>
+
+namespace nkp {
+
+struct Front {
+    int first = 0;       // first pivot (permuted index)
+    int s = 0;           // number of pivots
+    int r = 0;           // boundary size
+    int m = 0;           // s + r
+    int parent = -1;
+    int level = 0;       // depth from the root (roots are level 0)
+    int child_rank = 0;  // position among the parent's children (extend-add pass)
+    int nchild = 0;
+    int64_t Loff = 0;    // offsets in doubles into the device heap
+    int64_t UToff = 0;
+    int64_t F22off = 0;
+    int64_t bidx_off = 0;  // into Plan::bidx (r entries: permuted global index of each boundary row)
+    int64_t rel_off = 0;   // into Plan::rel  (r entries: local index in the parent's front)
+    int64_t woff = 0;      // solve work vector offset (m entries per rhs) in the solve pool
+};
+
+// ---- device task descriptors (plain data, uploaded once per analysis) ----
+
+struct DiagTask {   // factor one kb x kb diagonal block in place (no pivoting, tiny-pivot replacement)
+    int64_t Doff;   // Larr diagonal block
+    int64_t UTDoff; // UTarr diagonal block (receives U_kk^T)
+    int ld;
+    int kb;
+};
+
+struct TrsmTask {   // X * T = B in place on a tall panel: rows [0,nrows) x kb columns
+    int64_t Xoff;
+    int64_t Toff;   // factored diagonal block (in Larr)
+    int ld;         // leading dimension of X and of T's array
+    int nrows;
+    int kb;
+    int unit;       // 0: T = U_kk (upper, non-unit)   1: T = L_kk^T (upper, unit)
+    int cta0;       // first CTA of this task in the launch
+    int pad;
+};
+
+struct GemmTask {   // C[M x N] -= A[M x K] * B[N x K]^T, all column-major
+    int64_t Aoff, Boff, Coff;
+    int M, N, K;
+    int lda, ldb, ldc;
+    int skip;       // tile-skip rule, local coords (row a, col b), bj = b / nb:
+                    //   0 none
+                    //   1 block-lower target (Larr):  rows a <  bj*nb            are unused
+                    //   2 block-upper target (UTarr): rows a <  min((bj+1)*nb,N) are unused
+                    // a tile is skipped when all its rows are unused; partially unused tiles are
+                    // computed in full (the unused part of the arrays is scratch)
+    int tile0;      // first tile of this task in the launch
+    int tiles_m;    // number of tile rows
+    int pad;
+};
+
+struct AddTask {    // extend-add a child's update matrix into its parent front
+    int64_t Coff;   // child F22 (rc x rc, ld = rc)
+    int64_t rel_off;
+    int64_t Loff, UToff, F22off;  // parent arrays
+    int rc;
+    int sp, mp;     // parent pivots / size
+    int tile0;
+    int tiles_m;
+    int pad;
+};
+
+struct SolveTask {  // one front in a forward / backward sweep
+    int64_t Loff, UToff;
+    int64_t bidx_off;
+    int64_t rel_off;
+    int64_t woff;         // this front's work vector (m per rhs)
+    int64_t child_list;   // offset into Plan::solve_children
+    int first, s, r, m;
+    int nchild;
+    int pad;
+};
+
+struct SolveChild {
+    int64_t woff;     // child's work vector
+    int64_t rel_off;
+    int s, r;
+};
+
+struct LevelPlan {
+    int level = 0;
+    std::vector<int> fronts;             // fronts on this level
+    int nsteps = 0;                      // ceil(max s / nb)
+    // per step task ranges into the flat arrays below
+    std::vector<int> diag_begin, trsm_begin, gemm_begin;  // size nsteps+1
+    std::vector<int> trsm_ctas, gemm_tiles;               // per step launch sizes
+    // extend-add passes (children of this level's fronts live on level+1)
+    std::vector<int> add_begin;          // size npass+1
+    std::vector<int> add_tiles;          // per pass
+    int64_t f22_zero_off = 0, f22_zero_len = 0;  // region of the update pool to clear
+    int solve_begin = 0, solve_end = 0;  // into Plan::solve_tasks
+};
+
+struct Options {
+    int nb = 64;           // pivot block width
+    int leaf = 96;         // stop dissecting below this many unknowns
+    int tm = 128, tn = 64; // GEMM tile (must match the kernel)
+    int trsm_rows = 128;   // rows per TRSM CTA
+    int add_tile = 32;     // extend-add tile
+    int period_i = 0;
+    int verbose = 0;
+};
+
+struct Plan {
+    int n = 0;
+    int64_t nnz = 0;
+    Options opt;
+    std::vector<int> perm;     // perm[old] = new
+    std::vector<int> iperm;    // iperm[new] = old
+    std::vector<Front> fronts; // postorder
+    std::vector<int> roots;
+    int nlevels = 0;
+    std::vector<LevelPlan> levels;   // index = level
+    std::vector<int> bidx;           // boundary (permuted) indices, all fronts
+    std::vector<int> rel;            // parent-local indices, all fronts
+    std::vector<int64_t> scatter;    // per nnz (CRS order): destination offset in the heap
+    std::vector<DiagTask> diag_tasks;
+    std::vector<TrsmTask> trsm_tasks;
+    std::vector<GemmTask> gemm_tasks;
+    std::vector<AddTask> add_tasks;
+    std::vector<SolveTask> solve_tasks;   // grouped by level (deepest first)
+    std::vector<SolveChild> solve_children;
+    int64_t factor_len = 0;    // doubles in the factor arena  [0, factor_len)
+    int64_t pool_len[2] = {0, 0};  // update-matrix pools follow the arena
+    int64_t pool_off[2] = {0, 0};
+    int64_t heap_len = 0;
+    int64_t solve_pool_len = 0;    // per rhs
+    double flops = 0;          // algorithmic factor flops
+    int64_t nnz_lu = 0;        // stored factor entries incl. diagonal
+    int max_front = 0;
+    double t_order = 0, t_symbolic = 0, t_plan = 0;
+};
+
+// analysis.cpp
+// coords may be null; otherwise coords[d] (d = 0,1,2) are per-unknown integer coordinates
+int analyse(int n, const int* rowptr, const int* colind, const int* const coords[3],
+            const Options& opt, Plan& plan);
+
+inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
+
+// where does entry (a,b) of a front live?  returns heap offset
+inline int64_t front_entry(int a, int b, int s, int m, int nb,
+                           int64_t Loff, int64_t UToff, int64_t F22off) {
+    if (b < s) {
+        if (a >= s || a / nb >= b / nb) return Loff + a + (int64_t)b * m;
+        return UToff + b + (int64_t)a * m;
+    }
+    if (a < s) return UToff + b + (int64_t)a * m;
+    return F22off + (a - s) + (int64_t)(b - s) * (m - s);
+}
+
+}  // namespace nkp

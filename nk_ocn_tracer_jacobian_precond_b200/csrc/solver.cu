@@ -1,0 +1,529 @@
+// solver.cu -- device-side orchestration and the C ABI (include/nkprecond.h).
+//
+// One nkp_solver owns: the analysis Plan (host), its task lists mirrored in device memory,
+// the device heap (factors + update-matrix pools), the CRS operand on the device and the
+// solve work space.  nkp_factor replays the static launch sequence of the plan on one
+// stream; nkp_solve runs permute/scale -> forward sweep -> backward sweep -> refinement
+// (residual SpMV + correction solves, SuperLU's pdgsrfs stopping rule).
+//
+// There is no CPU fallback: every failure of a CUDA call is reported as NKP_ECUDA.
+#include <cuda_runtime.h>
+
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/nkprecond.h"
+#include "kernels.cuh"
+#include "nkp_internal.hpp"
+
+using namespace nkp;
+
+static thread_local std::string g_err;
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            char b_[512];                                                                          \
+            snprintf(b_, sizeof b_, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            g_err = b_;                                                                            \
+            return NKP_ECUDA;                                                                      \
+        }                                                                                          \
+    } while (0)
+
+static const int MAX_NR = 8;
+
+struct nkp_solver {
+    Plan plan;
+    nkp_options opt;
+    int n = 0;
+    int64_t nnz = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    // device data
+    double* heap = nullptr;
+    int* d_rowptr = nullptr;
+    int* d_colind = nullptr;
+    int* d_rowidx = nullptr;
+    double* d_val = nullptr;
+    int64_t* d_scatter = nullptr;
+    int* d_perm = nullptr;
+    int* d_bidx = nullptr;
+    int* d_rel = nullptr;
+    double* d_R = nullptr;
+    double* d_C = nullptr;
+    DiagTask* d_diag = nullptr;
+    TrsmTask* d_trsm = nullptr;
+    GemmTask* d_gemm = nullptr;
+    AddTask* d_add = nullptr;
+    SolveTask* d_solve = nullptr;
+    SolveChild* d_children = nullptr;
+    double* d_W = nullptr;      // solve work vectors, MAX_NR columns
+    double* d_y = nullptr;      // n x MAX_NR permuted rhs / solution
+    double* d_r = nullptr;      // n x MAX_NR residual
+    double* d_xb = nullptr;     // n x MAX_NR staging for host-pointer solves (B)
+    double* d_x = nullptr;      // n x MAX_NR solution accumulator
+    double* d_berr = nullptr;   // MAX_NR (+ MAX_NR sums)
+    int* d_nrepl = nullptr;
+    double* h_pinned = nullptr; // pinned staging for values / rhs
+    size_t pinned_bytes = 0;
+    bool factored = false;
+    double amax = 0;
+    // stats
+    double t_analysis = 0, t_factor = 0, t_scatter = 0, t_solve = 0;
+    int refine_steps = 0, tiny_pivots = 0;
+    int64_t launches = 0;
+};
+
+template <class T>
+static int upload(T** dptr, const std::vector<T>& v) {
+    size_t bytes = sizeof(T) * (v.size() ? v.size() : 1);
+    CK(cudaMalloc((void**)dptr, bytes));
+    if (!v.empty()) CK(cudaMemcpy(*dptr, v.data(), sizeof(T) * v.size(), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+const char* nkp_last_error(void) { return g_err.c_str(); }
+const char* nkp_version(void) { return "nkprecond-b200 0.1 (sm_100a)"; }
+
+void nkp_default_options(nkp_options* o) {
+    memset(o, 0, sizeof(*o));
+    o->nb = 64;
+    o->leaf = 96;
+    o->equil = 1;
+    o->refine_max = 10;
+    o->device = 0;
+    o->verbose = 0;
+    const char* e;
+    if ((e = getenv("NKP_LEAF"))) o->leaf = atoi(e);
+    if ((e = getenv("NKP_VERBOSE"))) o->verbose = atoi(e);
+    if ((e = getenv("NKP_EQUIL"))) o->equil = atoi(e);
+}
+
+int nkp_create(nkp_solver** out, int n, const int* rowptr, const int* colind, const int* ci,
+               const int* cj, const int* ck, const nkp_options* opt_in) {
+    if (!out || n <= 0 || !rowptr || !colind) {
+        g_err = "nkp_create: invalid argument";
+        return NKP_EINVAL;
+    }
+    nkp_options o;
+    if (opt_in) o = *opt_in;
+    else nkp_default_options(&o);
+    if (o.nb <= 0 || o.nb > NBMAX || o.nb % G_TN != 0) {
+        g_err = "nkp_create: nb must be 64";
+        return NKP_EINVAL;
+    }
+    int ndev = 0;
+    CK(cudaGetDeviceCount(&ndev));
+    if (ndev <= 0) {
+        g_err = "no CUDA device";
+        return NKP_ECUDA;
+    }
+    CK(cudaSetDevice(o.device));
+
+    nkp_solver* s = new nkp_solver();
+    s->opt = o;
+    s->n = n;
+    s->nnz = rowptr[n];
+    Options po;
+    po.nb = o.nb;
+    po.leaf = o.leaf;
+    po.tm = G_TM;
+    po.tn = G_TN;
+    po.trsm_rows = TRSM_ROWS;
+    po.add_tile = ADD_TILE;
+    po.verbose = o.verbose;
+    const int* coords[3] = {ci, cj, ck};
+    auto t0 = std::chrono::steady_clock::now();
+    int rc = analyse(n, rowptr, colind, (ci || cj || ck) ? coords : nullptr, po, s->plan);
+    s->t_analysis = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    if (rc) {
+        char b[128];
+        snprintf(b, sizeof b, "analysis failed with code %d", rc);
+        g_err = b;
+        delete s;
+        return NKP_EANALYSIS;
+    }
+    Plan& P = s->plan;
+#define CKD(x)                 \
+    do {                       \
+        int r_ = (x);          \
+        if (r_) {              \
+            nkp_destroy(s);    \
+            return r_;         \
+        }                      \
+    } while (0)
+    auto body = [&]() -> int {
+        CK(cudaStreamCreate(&s->stream));
+        for (int i = 0; i < 4; i++) CK(cudaEventCreate(&s->ev[i]));
+        CK(cudaMalloc((void**)&s->heap, sizeof(double) * (size_t)std::max<int64_t>(P.heap_len, 1)));
+        std::vector<int> rp(rowptr, rowptr + n + 1), cidx(colind, colind + s->nnz), ridx((size_t)s->nnz);
+        for (int i = 0; i < n; i++)
+            for (int p = rowptr[i]; p < rowptr[i + 1]; p++) ridx[p] = i;
+        if (upload(&s->d_rowptr, rp)) return NKP_ECUDA;
+        if (upload(&s->d_colind, cidx)) return NKP_ECUDA;
+        if (upload(&s->d_rowidx, ridx)) return NKP_ECUDA;
+        if (upload(&s->d_scatter, P.scatter)) return NKP_ECUDA;
+        if (upload(&s->d_perm, P.perm)) return NKP_ECUDA;
+        if (upload(&s->d_bidx, P.bidx)) return NKP_ECUDA;
+        if (upload(&s->d_rel, P.rel)) return NKP_ECUDA;
+        if (upload(&s->d_diag, P.diag_tasks)) return NKP_ECUDA;
+        if (upload(&s->d_trsm, P.trsm_tasks)) return NKP_ECUDA;
+        if (upload(&s->d_gemm, P.gemm_tasks)) return NKP_ECUDA;
+        if (upload(&s->d_add, P.add_tasks)) return NKP_ECUDA;
+        if (upload(&s->d_solve, P.solve_tasks)) return NKP_ECUDA;
+        if (upload(&s->d_children, P.solve_children)) return NKP_ECUDA;
+        CK(cudaMalloc((void**)&s->d_val, sizeof(double) * (size_t)s->nnz));
+        CK(cudaMalloc((void**)&s->d_R, sizeof(double) * n));
+        CK(cudaMalloc((void**)&s->d_C, sizeof(double) * n));
+        CK(cudaMalloc((void**)&s->d_W, sizeof(double) * (size_t)std::max<int64_t>(P.solve_pool_len, 1) * MAX_NR));
+        CK(cudaMalloc((void**)&s->d_y, sizeof(double) * (size_t)n * MAX_NR));
+        CK(cudaMalloc((void**)&s->d_r, sizeof(double) * (size_t)n * MAX_NR));
+        CK(cudaMalloc((void**)&s->d_x, sizeof(double) * (size_t)n * MAX_NR));
+        CK(cudaMalloc((void**)&s->d_xb, sizeof(double) * (size_t)n * MAX_NR));
+        CK(cudaMalloc((void**)&s->d_berr, sizeof(double) * 4 * MAX_NR));
+        CK(cudaMalloc((void**)&s->d_nrepl, sizeof(int)));
+        s->pinned_bytes = sizeof(double) * std::max<size_t>((size_t)s->nnz, (size_t)n * MAX_NR);
+        CK(cudaMallocHost((void**)&s->h_pinned, s->pinned_bytes));
+        CK(cudaFuncSetAttribute(k_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM));
+        // the scatter map and the heap can be large: release the host copies
+        std::vector<int64_t>().swap(P.scatter);
+        return 0;
+    };
+    rc = body();
+    if (rc) {
+        nkp_destroy(s);
+        return rc;
+    }
+    // drop the host copy of big plan arrays we no longer need on the host
+    *out = s;
+    return NKP_OK;
+}
+
+static int do_factor(nkp_solver* s) {
+    Plan& P = s->plan;
+    cudaStream_t st = s->stream;
+    const int n = s->n;
+    const int64_t nnz = s->nnz;
+    const int nb = P.opt.nb;
+    CK(cudaEventRecord(s->ev[0], st));
+    // equilibration
+    if (s->opt.equil) {
+        k_row_scale<<<(n + 255) / 256, 256, 0, st>>>(n, s->d_rowptr, s->d_val, s->d_R);
+        CK(cudaMemsetAsync(s->d_C, 0, sizeof(double) * n, st));
+        k_col_max<<<(unsigned)((nnz + 255) / 256), 256, 0, st>>>(nnz, s->d_rowidx, s->d_colind, s->d_val, s->d_R, s->d_C);
+        k_col_scale<<<(n + 255) / 256, 256, 0, st>>>(n, s->d_C);
+        s->launches += 3;
+    } else {
+        k_fill<<<(n + 255) / 256, 256, 0, st>>>(s->d_R, n, 1.0);
+        k_fill<<<(n + 255) / 256, 256, 0, st>>>(s->d_C, n, 1.0);
+        s->launches += 2;
+    }
+    // zero the factor arena, scatter A
+    CK(cudaMemsetAsync(s->heap, 0, sizeof(double) * (size_t)P.factor_len, st));
+    CK(cudaMemsetAsync(s->d_nrepl, 0, sizeof(int), st));
+    k_scatter<<<(unsigned)((nnz + 255) / 256), 256, 0, st>>>(nnz, s->d_val, s->d_scatter, s->d_rowidx, s->d_colind,
+                                                              s->d_R, s->d_C, s->heap);
+    s->launches++;
+    CK(cudaEventRecord(s->ev[1], st));
+    // with equilibration every row/column max is in [1,2): threshold relative to ||A|| ~ 1
+    double tiny = std::sqrt(2.220446049250313e-16) * (s->opt.equil ? 1.0 : s->amax);
+    for (int l = P.nlevels - 1; l >= 0; l--) {
+        const LevelPlan& L = P.levels[l];
+        if (L.f22_zero_len > 0)
+            CK(cudaMemsetAsync(s->heap + L.f22_zero_off, 0, sizeof(double) * (size_t)L.f22_zero_len, st));
+        int npass = (int)L.add_tiles.size();
+        for (int pass = 0; pass < npass; pass++) {
+            int nt = L.add_begin[pass + 1] - L.add_begin[pass];
+            if (nt == 0 || L.add_tiles[pass] == 0) continue;
+            k_extend_add<<<L.add_tiles[pass], 256, 0, st>>>(s->d_add + L.add_begin[pass], nt, s->d_rel, s->heap, nb);
+            s->launches++;
+        }
+        for (int step = 0; step < L.nsteps; step++) {
+            int nd = L.diag_begin[step + 1] - L.diag_begin[step];
+            if (nd > 0) {
+                k_diag<<<nd, 256, 0, st>>>(s->d_diag + L.diag_begin[step], s->heap, tiny, s->d_nrepl);
+                s->launches++;
+            }
+            int ntr = L.trsm_begin[step + 1] - L.trsm_begin[step];
+            if (ntr > 0 && L.trsm_ctas[step] > 0) {
+                k_trsm<<<L.trsm_ctas[step], TRSM_ROWS, 0, st>>>(s->d_trsm + L.trsm_begin[step], ntr, s->heap);
+                s->launches++;
+            }
+            int ng = L.gemm_begin[step + 1] - L.gemm_begin[step];
+            if (ng > 0 && L.gemm_tiles[step] > 0) {
+                k_gemm<<<L.gemm_tiles[step], 256, G_SMEM, st>>>(s->d_gemm + L.gemm_begin[step], ng, s->heap, nb);
+                s->launches++;
+            }
+        }
+    }
+    CK(cudaEventRecord(s->ev[2], st));
+    CK(cudaGetLastError());
+    int nrepl = 0;
+    CK(cudaMemcpyAsync(&nrepl, s->d_nrepl, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    float ms01 = 0, ms02 = 0;
+    CK(cudaEventElapsedTime(&ms01, s->ev[0], s->ev[1]));
+    CK(cudaEventElapsedTime(&ms02, s->ev[0], s->ev[2]));
+    s->t_scatter = ms01 * 1e-3;
+    s->t_factor = ms02 * 1e-3;
+    s->tiny_pivots = nrepl;
+    s->factored = true;
+    if (s->opt.verbose)
+        fprintf(stderr, "[nkp] factor: %.3f ms (scatter %.3f ms), %.2f TFLOP/s, tiny pivots replaced: %d\n",
+                ms02, ms01, P.flops / (ms02 * 1e-3) * 1e-12, nrepl);
+    return NKP_OK;
+}
+
+int nkp_factor_device(nkp_solver* s, const double* d_nzval) {
+    if (!s || !d_nzval) {
+        g_err = "nkp_factor_device: invalid argument";
+        return NKP_EINVAL;
+    }
+    CK(cudaSetDevice(s->opt.device));
+    if (d_nzval != s->d_val)
+        CK(cudaMemcpyAsync(s->d_val, d_nzval, sizeof(double) * (size_t)s->nnz, cudaMemcpyDeviceToDevice, s->stream));
+    return do_factor(s);
+}
+
+int nkp_factor(nkp_solver* s, const double* nzval) {
+    if (!s || !nzval) {
+        g_err = "nkp_factor: invalid argument";
+        return NKP_EINVAL;
+    }
+    CK(cudaSetDevice(s->opt.device));
+    double amax = 0;
+    if (!s->opt.equil)
+        for (int64_t p = 0; p < s->nnz; p++) amax = std::max(amax, std::fabs(nzval[p]));
+    s->amax = amax;
+    // pageable -> pinned staging -> device (one async copy)
+    memcpy(s->h_pinned, nzval, sizeof(double) * (size_t)s->nnz);
+    CK(cudaMemcpyAsync(s->d_val, s->h_pinned, sizeof(double) * (size_t)s->nnz, cudaMemcpyHostToDevice, s->stream));
+    return do_factor(s);
+}
+
+// forward + backward sweeps on d_y (n x nr, permuted, scaled), in place
+template <int NR>
+static int sweeps(nkp_solver* s) {
+    Plan& P = s->plan;
+    cudaStream_t st = s->stream;
+    for (int l = P.nlevels - 1; l >= 0; l--) {
+        const LevelPlan& L = P.levels[l];
+        int nt = L.solve_end - L.solve_begin;
+        if (nt == 0) continue;
+        k_fwd<NR><<<nt, SOLVE_THREADS, 0, st>>>(s->d_solve + L.solve_begin, s->d_children, s->d_rel, s->heap, s->d_W,
+                                                s->d_y, s->n, NR);
+        s->launches++;
+    }
+    for (int l = 0; l < P.nlevels; l++) {
+        const LevelPlan& L = P.levels[l];
+        int nt = L.solve_end - L.solve_begin;
+        if (nt == 0) continue;
+        k_bwd<NR><<<nt, SOLVE_THREADS, 0, st>>>(s->d_solve + L.solve_begin, s->d_bidx, s->heap, s->d_W, s->d_y, s->n, NR);
+        s->launches++;
+    }
+    CK(cudaGetLastError());
+    return 0;
+}
+
+static int sweeps_nr(nkp_solver* s, int nr) {
+    switch (nr) {
+        case 1: return sweeps<1>(s);
+        case 2: return sweeps<2>(s);
+        case 3:
+        case 4: return sweeps<4>(s);
+        default: return sweeps<8>(s);
+    }
+}
+static int padded_nr(int nr) { return nr <= 2 ? nr : (nr <= 4 ? 4 : 8); }
+
+// solve one chunk of nr <= MAX_NR right-hand sides held in device memory (in place)
+static int solve_chunk(nkp_solver* s, double* dB, int ldb, int nr, double* berr_host, int* steps_out) {
+    const int n = s->n;
+    cudaStream_t st = s->stream;
+    const int nrp = padded_nr(nr);
+    const int g = (n + 255) / 256;
+    const double eps = 2.220446049250313e-16;
+    const double safe = 2.2250738585072014e-308 * (double)(s->nnz / n + 2) / eps;
+    // x = 0-th solve
+    if (nrp > nr) CK(cudaMemsetAsync(s->d_y, 0, sizeof(double) * (size_t)n * nrp, st));
+    k_permute_in<<<g, 256, 0, st>>>(n, nr, s->d_perm, s->d_R, dB, ldb, s->d_y);
+    if (sweeps_nr(s, nrp)) return NKP_ECUDA;
+    k_permute_out<<<g, 256, 0, st>>>(n, nr, s->d_perm, s->d_C, s->d_y, s->d_x, n, 0);
+    s->launches += 2;
+    double last[MAX_NR];
+    for (int c = 0; c < nr; c++) last[c] = 1e300;
+    double berr[MAX_NR] = {0};
+    int it = 0;
+    for (;;) {
+        // r = b - A x, berr
+        CK(cudaMemsetAsync(s->d_berr, 0, sizeof(double) * MAX_NR, st));
+        k_residual<<<g, 256, 0, st>>>(n, nr, s->d_rowptr, s->d_colind, s->d_val, s->d_x, n, dB, ldb, s->d_r, s->d_berr, safe);
+        s->launches++;
+        CK(cudaMemcpyAsync(berr, s->d_berr, sizeof(double) * nr, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        bool go = false;
+        for (int c = 0; c < nr; c++) {
+            // SuperLU pdgsrfs: continue while berr > eps and berr decreased by at least a factor 2
+            if (berr[c] > eps && berr[c] * 2.0 <= last[c]) go = true;
+            last[c] = berr[c];
+        }
+        if (!go || it >= s->opt.refine_max) break;
+        it++;
+        k_permute_in<<<g, 256, 0, st>>>(n, nr, s->d_perm, s->d_R, s->d_r, n, s->d_y);
+        if (sweeps_nr(s, nrp)) return NKP_ECUDA;
+        k_permute_out<<<g, 256, 0, st>>>(n, nr, s->d_perm, s->d_C, s->d_y, s->d_x, n, 1);
+        s->launches += 2;
+    }
+    // write the solution over B
+    CK(cudaMemcpy2DAsync(dB, sizeof(double) * ldb, s->d_x, sizeof(double) * n, sizeof(double) * n, nr,
+                         cudaMemcpyDeviceToDevice, st));
+    if (berr_host)
+        for (int c = 0; c < nr; c++) berr_host[c] = berr[c];
+    *steps_out = it;
+    return 0;
+}
+
+int nkp_solve_device(nkp_solver* s, double* dB, int ldb, int nrhs, double* berr) {
+    if (!s || !dB || ldb < s->n || nrhs < 0) {
+        g_err = "nkp_solve_device: invalid argument";
+        return NKP_EINVAL;
+    }
+    if (!s->factored) {
+        g_err = "nkp_solve: matrix not factored";
+        return NKP_ESTATE;
+    }
+    CK(cudaSetDevice(s->opt.device));
+    CK(cudaEventRecord(s->ev[0], s->stream));
+    int maxsteps = 0;
+    for (int c0 = 0; c0 < nrhs; c0 += MAX_NR) {
+        int nr = std::min(MAX_NR, nrhs - c0);
+        int steps = 0;
+        int rc = solve_chunk(s, dB + (size_t)c0 * ldb, ldb, nr, berr ? berr + c0 : nullptr, &steps);
+        if (rc) return rc;
+        maxsteps = std::max(maxsteps, steps);
+    }
+    CK(cudaEventRecord(s->ev[1], s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, s->ev[0], s->ev[1]));
+    s->t_solve = ms * 1e-3;
+    s->refine_steps = maxsteps;
+    return NKP_OK;
+}
+
+int nkp_solve(nkp_solver* s, double* B, int ldb, int nrhs, double* berr) {
+    if (!s || !B || ldb < s->n || nrhs < 0) {
+        g_err = "nkp_solve: invalid argument";
+        return NKP_EINVAL;
+    }
+    if (!s->factored) {
+        g_err = "nkp_solve: matrix not factored";
+        return NKP_ESTATE;
+    }
+    CK(cudaSetDevice(s->opt.device));
+    const int n = s->n;
+    int maxsteps = 0;
+    double tsum = 0;
+    for (int c0 = 0; c0 < nrhs; c0 += MAX_NR) {
+        int nr = std::min(MAX_NR, nrhs - c0);
+        for (int c = 0; c < nr; c++) memcpy(s->h_pinned + (size_t)c * n, B + (size_t)(c0 + c) * ldb, sizeof(double) * n);
+        CK(cudaMemcpyAsync(s->d_xb, s->h_pinned, sizeof(double) * (size_t)n * nr, cudaMemcpyHostToDevice, s->stream));
+        int rc = nkp_solve_device(s, s->d_xb, n, nr, berr ? berr + c0 : nullptr);
+        if (rc) return rc;
+        tsum += s->t_solve;
+        maxsteps = std::max(maxsteps, s->refine_steps);
+        CK(cudaMemcpyAsync(s->h_pinned, s->d_xb, sizeof(double) * (size_t)n * nr, cudaMemcpyDeviceToHost, s->stream));
+        CK(cudaStreamSynchronize(s->stream));
+        for (int c = 0; c < nr; c++) memcpy(B + (size_t)(c0 + c) * ldb, s->h_pinned + (size_t)c * n, sizeof(double) * n);
+    }
+    s->t_solve = tsum;
+    s->refine_steps = maxsteps;
+    return NKP_OK;
+}
+
+int nkp_residual_device(nkp_solver* s, const double* dx, const double* db, double* dr, int nrhs) {
+    if (!s || !dx || !db || !dr || nrhs < 0) return NKP_EINVAL;
+    CK(cudaSetDevice(s->opt.device));
+    const int n = s->n;
+    k_residual<<<(n + 255) / 256, 256, 0, s->stream>>>(n, nrhs, s->d_rowptr, s->d_colind, s->d_val, dx, n, db, n, dr,
+                                                      nullptr, 0.0);
+    s->launches++;
+    CK(cudaGetLastError());
+    return NKP_OK;
+}
+
+int nkp_sweeps_device(nkp_solver* s, double* dB, int ldb, int nrhs) {
+    if (!s || !dB || nrhs < 1 || nrhs > MAX_NR) return NKP_EINVAL;
+    if (!s->factored) return NKP_ESTATE;
+    CK(cudaSetDevice(s->opt.device));
+    const int n = s->n;
+    const int nrp = padded_nr(nrhs);
+    const int g = (n + 255) / 256;
+    if (nrp > nrhs) CK(cudaMemsetAsync(s->d_y, 0, sizeof(double) * (size_t)n * nrp, s->stream));
+    k_permute_in<<<g, 256, 0, s->stream>>>(n, nrhs, s->d_perm, s->d_R, dB, ldb, s->d_y);
+    if (sweeps_nr(s, nrp)) return NKP_ECUDA;
+    k_permute_out<<<g, 256, 0, s->stream>>>(n, nrhs, s->d_perm, s->d_C, s->d_y, dB, ldb, 0);
+    s->launches += 2;
+    CK(cudaGetLastError());
+    return NKP_OK;
+}
+
+int nkp_get_perm(const nkp_solver* s, int* perm) {
+    if (!s || !perm) return NKP_EINVAL;
+    memcpy(perm, s->plan.perm.data(), sizeof(int) * s->n);
+    return NKP_OK;
+}
+
+int nkp_get_stats(const nkp_solver* s, nkp_stats* st) {
+    if (!s || !st) return NKP_EINVAL;
+    memset(st, 0, sizeof(*st));
+    const Plan& P = s->plan;
+    st->n = s->n;
+    st->nnz = s->nnz;
+    st->n_fronts = (int)P.fronts.size();
+    st->n_levels = P.nlevels;
+    st->max_front = P.max_front;
+    st->nnz_lu = P.nnz_lu;
+    st->factor_flops = P.flops;
+    st->heap_bytes = 8.0 * (double)P.heap_len;
+    st->t_analysis = s->t_analysis;
+    st->t_factor = s->t_factor;
+    st->t_scatter = s->t_scatter;
+    st->t_solve = s->t_solve;
+    st->refine_steps = s->refine_steps;
+    st->tiny_pivots = s->tiny_pivots;
+    st->kernel_launches = s->launches;
+    // 8 (nnz(L)+nnz(U)) + index bytes + 2*8*n per sweep pair
+    st->solve_bytes = 8.0 * (double)P.nnz_lu + 4.0 * (double)(P.bidx.size() + P.rel.size()) + 16.0 * s->n;
+    return NKP_OK;
+}
+
+int nkp_sync(nkp_solver* s) {
+    if (!s) return NKP_EINVAL;
+    CK(cudaStreamSynchronize(s->stream));
+    return NKP_OK;
+}
+
+void nkp_destroy(nkp_solver* s) {
+    if (!s) return;
+    cudaSetDevice(s->opt.device);
+    if (s->stream) cudaStreamSynchronize(s->stream);
+    void* ptrs[] = {s->heap,   s->d_rowptr, s->d_colind, s->d_rowidx, s->d_val,  s->d_scatter, s->d_perm,
+                    s->d_bidx, s->d_rel,    s->d_R,      s->d_C,      s->d_diag, s->d_trsm,    s->d_gemm,
+                    s->d_add,  s->d_solve,  s->d_children, s->d_W,    s->d_y,    s->d_r,       s->d_x,
+                    s->d_xb,   s->d_berr,   s->d_nrepl};
+    for (void* p : ptrs)
+        if (p) cudaFree(p);
+    if (s->h_pinned) cudaFreeHost(s->h_pinned);
+    for (int i = 0; i < 4; i++)
+        if (s->ev[i]) cudaEventDestroy(s->ev[i]);
+    if (s->stream) cudaStreamDestroy(s->stream);
+    delete s;
+}
+

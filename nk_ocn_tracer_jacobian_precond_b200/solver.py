@@ -1,0 +1,171 @@
+"""ctypes binding of the C ABI in include/nkprecond.h (libnkprecond.so).
+
+This is host-side plumbing only: every numeric operation happens in the CUDA library.
+If the library (or a GPU) is missing the calls raise -- there is no CPU fallback.
+
+The class mirrors the two-phase protocol of the reference drivers
+(src/solve_ABglobal.c:350-395): one ``factor`` (pdgssvx_ABglobal with nrhs=0) followed by
+any number of ``solve`` calls (options.Fact = FACTORED, nrhs >= 1), B overwritten by X.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libnkprecond.so")
+
+
+class NkpOptions(C.Structure):
+    _fields_ = [("nb", C.c_int), ("leaf", C.c_int), ("equil", C.c_int), ("refine_max", C.c_int),
+                ("device", C.c_int), ("verbose", C.c_int), ("reserved", C.c_int * 10)]
+
+
+class NkpStats(C.Structure):
+    _fields_ = [("n", C.c_int), ("nnz", C.c_int64), ("n_fronts", C.c_int), ("n_levels", C.c_int),
+                ("max_front", C.c_int), ("nnz_lu", C.c_int64), ("factor_flops", C.c_double),
+                ("heap_bytes", C.c_double), ("t_analysis", C.c_double), ("t_factor", C.c_double),
+                ("t_scatter", C.c_double), ("t_solve", C.c_double), ("refine_steps", C.c_int),
+                ("tiny_pivots", C.c_int), ("kernel_launches", C.c_int64), ("solve_bytes", C.c_double),
+                ("reserved", C.c_double * 8)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
+
+
+_lib = None
+
+
+def load_library():
+    """Load libnkprecond.so; raises OSError with a build hint if it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise OSError(f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'`")
+    lib = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+    P = C.POINTER
+    vp = C.c_void_p
+    lib.nkp_default_options.argtypes = [P(NkpOptions)]
+    lib.nkp_default_options.restype = None
+    lib.nkp_create.argtypes = [P(vp), C.c_int, P(C.c_int), P(C.c_int), P(C.c_int), P(C.c_int), P(C.c_int), P(NkpOptions)]
+    lib.nkp_factor.argtypes = [vp, P(C.c_double)]
+    lib.nkp_factor_device.argtypes = [vp, vp]
+    lib.nkp_solve.argtypes = [vp, P(C.c_double), C.c_int, C.c_int, P(C.c_double)]
+    lib.nkp_solve_device.argtypes = [vp, vp, C.c_int, C.c_int, P(C.c_double)]
+    lib.nkp_residual_device.argtypes = [vp, vp, vp, vp, C.c_int]
+    lib.nkp_sweeps_device.argtypes = [vp, vp, C.c_int, C.c_int]
+    lib.nkp_get_perm.argtypes = [vp, P(C.c_int)]
+    lib.nkp_get_stats.argtypes = [vp, P(NkpStats)]
+    lib.nkp_sync.argtypes = [vp]
+    lib.nkp_destroy.argtypes = [vp]
+    lib.nkp_destroy.restype = None
+    lib.nkp_last_error.restype = C.c_char_p
+    lib.nkp_version.restype = C.c_char_p
+    _lib = lib
+    return lib
+
+
+class NkpError(RuntimeError):
+    pass
+
+
+def _check(rc, what):
+    if rc != 0:
+        msg = load_library().nkp_last_error().decode()
+        raise NkpError(f"{what} failed with code {rc}: {msg}")
+
+
+def _iptr(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int)) if a is not None else None
+
+
+class TracerJacobianSolver:
+    """Analysis handle + numeric factors for one sparsity pattern (CRS, 0-based).
+
+    coords: optional (i, j, k) int arrays per unknown (tracer_state_ind_to_{i,j,k},
+    src/matrix.c:322-329) enabling the geometric nested dissection.
+    """
+
+    def __init__(self, n, rowptr, colind, coords=None, **opts):
+        lib = load_library()
+        self._lib = lib
+        self.n = int(n)
+        rowptr = np.ascontiguousarray(rowptr, dtype=np.int32)
+        colind = np.ascontiguousarray(colind, dtype=np.int32)
+        self.nnz = int(rowptr[-1])
+        o = NkpOptions()
+        lib.nkp_default_options(C.byref(o))
+        for k, v in opts.items():
+            setattr(o, k, int(v))
+        ci = cj = ck = None
+        if coords is not None:
+            ci, cj, ck = (np.ascontiguousarray(c, dtype=np.int32) if c is not None else None for c in coords)
+        self._h = C.c_void_p()
+        _check(lib.nkp_create(C.byref(self._h), self.n, _iptr(rowptr), _iptr(colind), _iptr(ci), _iptr(cj), _iptr(ck),
+                              C.byref(o)), "nkp_create")
+
+    # -- numeric phase -------------------------------------------------------------------
+    def factor(self, nzval):
+        """Numeric LU from host values (includes the host->device copy)."""
+        nzval = np.ascontiguousarray(nzval, dtype=np.float64)
+        assert nzval.size == self.nnz
+        _check(self._lib.nkp_factor(self._h, nzval.ctypes.data_as(C.POINTER(C.c_double))), "nkp_factor")
+
+    def factor_device(self, d_ptr):
+        """Numeric LU with values already on the device (d_ptr: int device address)."""
+        _check(self._lib.nkp_factor_device(self._h, C.c_void_p(d_ptr)), "nkp_factor_device")
+
+    def solve(self, B):
+        """Solve A X = B in place (host memory, Fortran order n x nrhs); returns berr[nrhs]."""
+        assert B.dtype == np.float64
+        if B.ndim == 1:
+            ldb, nrhs = B.shape[0], 1
+            assert B.flags.c_contiguous
+        else:
+            assert B.flags.f_contiguous
+            ldb, nrhs = B.shape
+        berr = np.zeros(max(nrhs, 1))
+        _check(self._lib.nkp_solve(self._h, B.ctypes.data_as(C.POINTER(C.c_double)), ldb, nrhs,
+                                   berr.ctypes.data_as(C.POINTER(C.c_double))), "nkp_solve")
+        return berr
+
+    def solve_device(self, d_ptr, ldb, nrhs):
+        berr = np.zeros(max(nrhs, 1))
+        _check(self._lib.nkp_solve_device(self._h, C.c_void_p(d_ptr), ldb, nrhs,
+                                          berr.ctypes.data_as(C.POINTER(C.c_double))), "nkp_solve_device")
+        return berr
+
+    def sweeps_device(self, d_ptr, ldb, nrhs):
+        _check(self._lib.nkp_sweeps_device(self._h, C.c_void_p(d_ptr), ldb, nrhs), "nkp_sweeps_device")
+
+    def residual_device(self, d_x, d_b, d_r, nrhs):
+        _check(self._lib.nkp_residual_device(self._h, C.c_void_p(d_x), C.c_void_p(d_b), C.c_void_p(d_r), nrhs),
+               "nkp_residual_device")
+
+    def sync(self):
+        _check(self._lib.nkp_sync(self._h), "nkp_sync")
+
+    # -- introspection -------------------------------------------------------------------
+    def perm(self):
+        p = np.zeros(self.n, dtype=np.int32)
+        _check(self._lib.nkp_get_perm(self._h, _iptr(p)), "nkp_get_perm")
+        return p
+
+    def stats(self):
+        st = NkpStats()
+        _check(self._lib.nkp_get_stats(self._h, C.byref(st)), "nkp_get_stats")
+        return st.as_dict()
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.nkp_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
