@@ -208,7 +208,9 @@ def read_matrix_file(path: str) -> dict:
                  "tracer_state_ind_to_i", "tracer_state_ind_to_j", "tracer_state_ind_to_k",
                  "int3_to_tracer_state_ind"):
         if name in f.variables:
-            out[name] = np.array(f.variables[name].data).copy()
+            a = np.array(f.variables[name].data)
+            # the file is big-endian; hand out native-endian arrays (they go through ctypes)
+            out[name] = np.ascontiguousarray(a.astype(a.dtype.newbyteorder("=")))
     out["imt"] = f.dimensions["nlon"]
     out["jmt"] = f.dimensions["nlat"]
     out["km"] = f.dimensions["z_t"]

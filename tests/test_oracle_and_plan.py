@@ -1,0 +1,110 @@
+"""CPU side: the oracle against the golden vectors, and the host analysis (ordering,
+symbolic structure, memory plan, task lists) validated by interpreting the plan on the
+CPU (oracle/plan_sim.cpp) and comparing with the oracle."""
+import ctypes
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from conftest import synth_case
+from oracle import oracle_solve
+
+P = ctypes.POINTER
+
+
+def _ip(a):
+    return a.ctypes.data_as(P(ctypes.c_int)) if a is not None else None
+
+
+def _dp(a):
+    return a.ctypes.data_as(P(ctypes.c_double))
+
+
+def run_sim(lib, n, rp, ci, nz, coords, B, nb=64, leaf=96, analysis_only=0):
+    B = np.asfortranarray(B, dtype=np.float64)
+    nrhs = B.shape[1]
+    X = np.zeros_like(B, order="F")
+    stats = np.zeros(8)
+    perm = np.zeros(n, dtype=np.int32)
+    i, j, k = coords if coords is not None else (None, None, None)
+    rc = lib.nkp_sim_run(n, _ip(rp), _ip(ci), _dp(nz), _ip(i), _ip(j), _ip(k), nb, leaf, _dp(B), nrhs, _dp(X),
+                         _dp(stats), _ip(perm), analysis_only)
+    assert rc == 0, rc
+    return X, stats, perm
+
+
+def test_oracle_reproduces_golden_solutions(golden_matrix, golden_rhs):
+    m = golden_matrix
+    X, info = oracle_solve.solve(m["n"], m["rowptr"], m["colind"], m["nzval_row_wise"], golden_rhs["B"], return_info=True)
+    assert np.allclose(X, golden_rhs["X"], rtol=1e-11, atol=0)
+    A = oracle_solve.csr(m["n"], m["rowptr"], m["colind"], m["nzval_row_wise"])
+    for c in range(X.shape[1]):
+        berr, _ = oracle_solve.berr_of(A, X[:, c], golden_rhs["B"][:, c])
+        assert berr <= 4 * oracle_solve.EPS
+
+
+def test_oracle_manufactured_solution(golden_matrix):
+    """KAT-2: b = A x*, recover x* to <= 1e-8 (BASELINE.json tolerance), residual <= 1e-10."""
+    m = golden_matrix
+    n = m["n"]
+    rng = np.random.default_rng(5)
+    xs = rng.standard_normal(n)
+    b = oracle_solve.spmv(n, m["rowptr"], m["colind"], m["nzval_row_wise"], xs)
+    x = oracle_solve.solve(n, m["rowptr"], m["colind"], m["nzval_row_wise"], b)
+    assert np.linalg.norm(x - xs) / np.linalg.norm(xs) <= 1e-8
+    r = oracle_solve.spmv(n, m["rowptr"], m["colind"], m["nzval_row_wise"], x) - b
+    assert np.linalg.norm(r) / np.linalg.norm(b) <= 1e-10
+
+
+@pytest.mark.parametrize("nb,leaf", [(64, 96), (16, 32), (8, 400)])
+def test_plan_interpreter_matches_oracle_on_golden(sim_lib, golden_matrix, golden_rhs, nb, leaf):
+    m = golden_matrix
+    coords = (m["tracer_state_ind_to_i"], m["tracer_state_ind_to_j"], m["tracer_state_ind_to_k"])
+    X, stats, perm = run_sim(sim_lib, m["n"], m["rowptr"], m["colind"], m["nzval_row_wise"], coords, golden_rhs["B"],
+                             nb=nb, leaf=leaf)
+    assert sorted(perm.tolist()) == list(range(m["n"]))
+    # static pivoting without refinement: a few digits worse than the pivoted oracle
+    rel = np.linalg.norm(X - golden_rhs["X"], axis=0) / np.linalg.norm(golden_rhs["X"], axis=0)
+    assert rel.max() <= 1e-8, rel
+    assert stats[6] == 0  # no tiny pivots replaced
+
+
+@pytest.mark.parametrize("shape", [(12, 10, 5), (24, 28, 16), (30, 34, 20)])
+def test_plan_interpreter_multistep_fronts(sim_lib, shape):
+    """Fronts with several pivot blocks exercise the tile-skip rules and partial blocks."""
+    c = synth_case(*shape, seed=2)
+    n = c["n"]
+    A = sp.csr_matrix((c["nzval"], c["colind"], c["rowptr"]), shape=(n, n))
+    A = (A - 50.0 * sp.eye(n)).tocsr()   # well conditioned: isolates plan logic from pivot growth
+    A.sort_indices()
+    rng = np.random.default_rng(1)
+    xs = rng.standard_normal((n, 2))
+    B = A @ xs
+    X, stats, _ = run_sim(sim_lib, n, A.indptr.astype(np.int32), A.indices.astype(np.int32), A.data,
+                          (c["i"], c["j"], c["k"]), B)
+    assert np.linalg.norm(X - xs) / np.linalg.norm(xs) <= 1e-12
+
+
+def test_plan_without_coordinates_uses_graph_dissection(sim_lib):
+    c = synth_case(16, 14, 8, seed=4)
+    n = c["n"]
+    A = sp.csr_matrix((c["nzval"], c["colind"], c["rowptr"]), shape=(n, n))
+    A = (A - 50.0 * sp.eye(n)).tocsr()
+    A.sort_indices()
+    xs = np.random.default_rng(2).standard_normal((n, 1))
+    X, stats, perm = run_sim(sim_lib, n, A.indptr.astype(np.int32), A.indices.astype(np.int32), A.data, None, A @ xs,
+                             leaf=48)
+    assert sorted(perm.tolist()) == list(range(n))
+    assert stats[0] > 4  # really dissected
+    assert np.linalg.norm(X - xs) / np.linalg.norm(xs) <= 1e-12
+
+
+def test_analysis_reports_fill_and_flops(sim_lib):
+    c = synth_case(40, 46, 24, seed=1)
+    _, stats, _ = run_sim(sim_lib, c["n"], c["rowptr"], c["colind"], c["nzval"], (c["i"], c["j"], c["k"]),
+                          np.zeros((c["n"], 1)), analysis_only=1)
+    nfronts, nlevels, maxfront, nnz_lu, heap, flops = stats[:6]
+    assert nnz_lu >= len(c["nzval"])
+    assert heap >= nnz_lu
+    assert flops > 0 and nlevels >= 5 and maxfront < c["n"]
