@@ -67,6 +67,14 @@ typedef struct nkp_stats {
     int tiny_pivots;         /* pivots replaced in the last factorisation         */
     int64_t kernel_launches; /* kernels launched by this handle so far            */
     double solve_bytes;      /* algorithmic bytes of one forward+backward sweep   */
+    /* per-kernel device times of the last factorisation (only with nkp_set_profile(s,1)) */
+    double t_gemm;           /* Schur-update GEMM launches, seconds                */
+    double gemm_flops;       /* algorithmic flops of those launches                */
+    int64_t n_gemm;          /* number of GEMM launches                            */
+    double t_trsm;
+    double t_diag;
+    double t_extend_add;
+    double t_sweeps;         /* device seconds of the last raw sweep pair(s) (nkp_sweeps_device) */
     double reserved[8];
 } nkp_stats;
 
@@ -106,6 +114,9 @@ int nkp_sweeps_device(nkp_solver* s, double* d_B, int ldb, int nrhs);
 /* The fill-reducing permutation: perm[old] = new (n entries). */
 int nkp_get_perm(const nkp_solver* s, int* perm);
 int nkp_get_stats(const nkp_solver* s, nkp_stats* st);
+/* on != 0: bracket every kernel of nkp_factor* with CUDA events on the solver's stream and
+ * report per-kernel-class times in nkp_stats (small overhead; off by default). */
+int nkp_set_profile(nkp_solver* s, int on);
 /* Block until all device work of this handle has finished. */
 int nkp_sync(nkp_solver* s);
 void nkp_destroy(nkp_solver* s);

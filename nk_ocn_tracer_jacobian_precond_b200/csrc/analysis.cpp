@@ -621,6 +621,16 @@ int analyse(int n, const int* rowptr, const int* colind, const int* const coords
                         gt.pad = 0;
                         tile0 += gt.tiles_m * ((N + opt.tn - 1) / opt.tn);
                         plan.gemm_tasks.push_back(gt);
+                        // useful (algorithmic) entries of this update
+                        double area = 0;
+                        if (skip == 0) area = (double)M * N;
+                        else
+                            for (int c0 = 0; c0 < N; c0 += nb) {
+                                int w = std::min(nb, N - c0);
+                                int first_row = skip == 1 ? c0 : std::min(c0 + nb, N);
+                                area += (double)(M - first_row) * w;
+                            }
+                        plan.gemm_flops += 2.0 * kb * area;
                     };
                     int64_t Lpan = f.Loff + k1 + (int64_t)k0 * f.m;    // L[k1.., k0:k1]
                     int64_t UTpan = f.UToff + k1 + (int64_t)k0 * f.m;  // U^T[k1.., k0:k1]
@@ -676,6 +686,52 @@ int analyse(int n, const int* rowptr, const int* colind, const int* const coords
             plan.solve_tasks.push_back(st);
         }
         L.solve_end = (int)plan.solve_tasks.size();
+        // split into single-CTA fronts and big (multi-CTA dataflow) fronts
+        L.small_begin = (int)plan.solve_small.size();
+        L.big_begin = (int)plan.big_fronts.size();
+        for (int q = L.solve_begin; q < L.solve_end; q++) {
+            const SolveTask& st = plan.solve_tasks[q];
+            if ((int64_t)st.m * st.s >= opt.big_entries && st.s >= 64) {
+                BigFront bf;
+                bf.Loff = st.Loff;
+                bf.UToff = st.UToff;
+                bf.bidx_off = st.bidx_off;
+                bf.woff = st.woff;
+                bf.first = st.first;
+                bf.s = st.s;
+                bf.r = st.r;
+                bf.m = st.m;
+                bf.npiv = (st.s + 63) / 64;
+                bf.nslab = bf.npiv + (st.r + 63) / 64;
+                bf.flag0 = plan.n_big_flags;
+                bf.pad = q;   // index of the full SolveTask (children list for the init kernel)
+                plan.n_big_flags += bf.npiv;
+                plan.big_fronts.push_back(bf);
+            } else {
+                plan.solve_small.push_back(st);
+            }
+        }
+        L.small_end = (int)plan.solve_small.size();
+        L.big_end = (int)plan.big_fronts.size();
+        L.fwd_item_begin = (int)plan.big_fwd_items.size();
+        L.bwd_item_begin = (int)plan.big_bwd_items.size();
+        {
+            int maxslab = 0, maxpiv = 0;
+            for (int b = L.big_begin; b < L.big_end; b++) {
+                maxslab = std::max(maxslab, plan.big_fronts[b].nslab);
+                maxpiv = std::max(maxpiv, plan.big_fronts[b].npiv);
+            }
+            // forward: slabs in increasing order, interleaved over the fronts of the level
+            for (int i = 0; i < maxslab; i++)
+                for (int b = L.big_begin; b < L.big_end; b++)
+                    if (i < plan.big_fronts[b].nslab) plan.big_fwd_items.push_back(BigItem{b, i});
+            // backward: panels from the last one down, interleaved
+            for (int d = 0; d < maxpiv; d++)
+                for (int b = L.big_begin; b < L.big_end; b++)
+                    if (d < plan.big_fronts[b].npiv) plan.big_bwd_items.push_back(BigItem{b, plan.big_fronts[b].npiv - 1 - d});
+        }
+        L.fwd_item_end = (int)plan.big_fwd_items.size();
+        L.bwd_item_end = (int)plan.big_bwd_items.size();
     }
     plan.t_plan = now_s() - t0;
 

@@ -531,6 +531,337 @@ __global__ void __launch_bounds__(SOLVE_THREADS) k_bwd(const SolveTask* __restri
 }
 
 // ------------------------------------------------------------------------------------------
+// big fronts: many CTAs per front, flag-driven dataflow (launched cooperatively so that all
+// CTAs are co-resident; a CTA only ever waits on work items that precede its own in the
+// item list, which some running CTA is processing or has processed).
+//   forward : item = 64-row slab i.   w_i -= sum_{k<i} L[i,k] y_k ; pivot slabs then solve
+//             their 64x64 diagonal block and publish y_i (flag i).
+//   backward: item = 64-column pivot panel i, swept from the last panel down.
+//             z_i = y_i - sum_{rows below} UT[rows, i]^T x_rows ; x_i = U_ii^-1 z_i (flag i).
+// ------------------------------------------------------------------------------------------
+
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu(int* p, int v) {
+    asm volatile("st.release.gpu.global.s32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
+}
+
+template <int NR>
+__global__ void __launch_bounds__(SOLVE_THREADS) k_fwd_big_init(const BigFront* __restrict__ bfs,
+                                                                const SolveTask* __restrict__ alltasks,
+                                                                const SolveChild* __restrict__ children,
+                                                                const int* __restrict__ rel, double* __restrict__ W,
+                                                                const double* __restrict__ y, int n) {
+    const BigFront bf = bfs[blockIdx.x];
+    const SolveTask tk = alltasks[bf.pad];
+    const int s = bf.s, m = bf.m;
+    double* w = W + bf.woff * NR;
+    for (int a = threadIdx.x; a < m; a += SOLVE_THREADS)
+#pragma unroll
+        for (int c = 0; c < NR; c++) w[a + (int64_t)c * m] = a < s ? y[bf.first + a + (int64_t)c * n] : 0.0;
+    __syncthreads();
+    for (int ch = 0; ch < tk.nchild; ch++) {
+        const SolveChild sc = children[tk.child_list + ch];
+        const int mc = sc.s + sc.r;
+        const double* wc = W + sc.woff * NR + sc.s;
+        const int* rl = rel + sc.rel_off;
+        for (int a = threadIdx.x; a < sc.r; a += SOLVE_THREADS) {
+            int d = rl[a];
+#pragma unroll
+            for (int c = 0; c < NR; c++) w[d + (int64_t)c * m] += wc[a + (int64_t)c * mc];
+        }
+        __syncthreads();
+    }
+}
+
+template <int NR>
+__global__ void __launch_bounds__(SOLVE_THREADS) k_bwd_big_init(const BigFront* __restrict__ bfs,
+                                                                const int* __restrict__ bidx, double* __restrict__ W,
+                                                                const double* __restrict__ y, int n) {
+    const BigFront bf = bfs[blockIdx.x];
+    double* w = W + bf.woff * NR;
+    const int* bi = bidx + bf.bidx_off;
+    for (int a = threadIdx.x; a < bf.r; a += SOLVE_THREADS) {
+        int g = bi[a];
+#pragma unroll
+        for (int c = 0; c < NR; c++) w[bf.s + a + (int64_t)c * bf.m] = y[g + (int64_t)c * n];
+    }
+}
+
+template <int NR>
+__global__ void __launch_bounds__(256) k_fwd_big(const BigFront* __restrict__ bfs, const BigItem* __restrict__ items,
+                                                 int nitems, const double* __restrict__ heap, double* __restrict__ W,
+                                                 double* __restrict__ y, int n, int* __restrict__ flags, int epoch) {
+    __shared__ double buf[64 * 65];   // reduction scratch, then the diagonal block
+    __shared__ double ys[64 * NR];
+    const int tid = threadIdx.x, row = tid & 63, cg = tid >> 6;
+    for (int it = blockIdx.x; it < nitems; it += gridDim.x) {
+        const BigItem item = items[it];
+        const BigFront bf = bfs[item.front];
+        const int i = item.idx, s = bf.s, m = bf.m;
+        const bool pivot = i < bf.npiv;
+        const int r0 = pivot ? 64 * i : s + 64 * (i - bf.npiv);
+        const int nrow = min(64, (pivot ? s : m) - r0);
+        const int kmax = pivot ? i : bf.npiv;
+        const double* L = heap + bf.Loff;
+        double* w = W + bf.woff * NR;
+        double acc[NR];
+#pragma unroll
+        for (int c = 0; c < NR; c++) acc[c] = 0.0;
+        double lreg[16], treg[16];
+        if (pivot) {
+#pragma unroll
+            for (int pp = 0; pp < 16; pp++) {
+                int p = cg * 16 + pp;
+                treg[pp] = (row < nrow && p < nrow && row > p) ? L[r0 + row + (int64_t)(r0 + p) * m] : 0.0;
+            }
+        }
+        auto loadL = [&](int k) {
+            const int kb = min(64, s - 64 * k);
+#pragma unroll
+            for (int pp = 0; pp < 16; pp++) {
+                int p = cg * 16 + pp;
+                lreg[pp] = (row < nrow && p < kb) ? L[r0 + row + (int64_t)(64 * k + p) * m] : 0.0;
+            }
+        };
+        if (kmax > 0) loadL(0);
+        for (int k = 0; k < kmax; k++) {
+            if (tid == 0)
+                while (ld_acquire_gpu(&flags[bf.flag0 + k]) != epoch) __nanosleep(32);
+            __syncthreads();
+            const int kb = min(64, s - 64 * k);
+            for (int e = tid; e < 64 * NR; e += 256) {
+                int p = e & 63, c = e >> 6;
+                ys[e] = p < kb ? __ldcg(&y[bf.first + 64 * k + p + (int64_t)c * n]) : 0.0;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int pp = 0; pp < 16; pp++)
+#pragma unroll
+                for (int c = 0; c < NR; c++) acc[c] += lreg[pp] * ys[cg * 16 + pp + 64 * c];
+            if (k + 1 < kmax) loadL(k + 1);
+            __syncthreads();
+        }
+        // reduce the four column groups
+#pragma unroll
+        for (int c = 0; c < NR; c++) buf[(cg * 64 + row) * NR + c] = acc[c];
+        __syncthreads();
+        double val[NR];
+        if (tid < 64) {
+#pragma unroll
+            for (int c = 0; c < NR; c++) {
+                double sum = buf[(0 * 64 + tid) * NR + c] + buf[(1 * 64 + tid) * NR + c] + buf[(2 * 64 + tid) * NR + c] +
+                             buf[(3 * 64 + tid) * NR + c];
+                val[c] = tid < nrow ? __ldcg(&w[r0 + tid + (int64_t)c * m]) - sum : 0.0;
+            }
+        }
+        if (!pivot) {
+            if (tid < nrow)
+#pragma unroll
+                for (int c = 0; c < NR; c++) w[r0 + tid + (int64_t)c * m] = val[c];
+            __syncthreads();
+            continue;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int pp = 0; pp < 16; pp++) buf[row + 65 * (cg * 16 + pp)] = treg[pp];
+        if (tid < 64)
+#pragma unroll
+            for (int c = 0; c < NR; c++) ys[tid + 64 * c] = val[c];
+        __syncthreads();
+        if (tid < 32) {   // rows 0..31
+            double v[NR];
+#pragma unroll
+            for (int c = 0; c < NR; c++) v[c] = ys[tid + 64 * c];
+            for (int p = 0; p < 32; p++) {
+                double l = buf[tid + 65 * p];
+#pragma unroll
+                for (int c = 0; c < NR; c++) {
+                    double yp = __shfl_sync(0xffffffffu, v[c], p);
+                    v[c] -= l * yp;
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < NR; c++) ys[tid + 64 * c] = v[c];
+        }
+        __syncthreads();
+        if (tid >= 32 && tid < 64) {   // rows 32..63
+            const int a = tid;
+            double v[NR];
+#pragma unroll
+            for (int c = 0; c < NR; c++) v[c] = ys[a + 64 * c];
+            for (int p = 0; p < 32; p++) {
+                double l = buf[a + 65 * p];
+#pragma unroll
+                for (int c = 0; c < NR; c++) v[c] -= l * ys[p + 64 * c];
+            }
+            for (int p = 0; p < 32; p++) {
+                double l = buf[a + 65 * (32 + p)];
+#pragma unroll
+                for (int c = 0; c < NR; c++) {
+                    double yp = __shfl_sync(0xffffffffu, v[c], p);
+                    v[c] -= l * yp;
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < NR; c++) ys[a + 64 * c] = v[c];
+        }
+        __syncthreads();
+        for (int e = tid; e < 64 * NR; e += 256) {
+            int a = e & 63, c = e >> 6;
+            if (a < nrow) y[bf.first + r0 + a + (int64_t)c * n] = ys[e];
+        }
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) st_release_gpu(&flags[bf.flag0 + i], epoch);
+    }
+}
+
+template <int NR>
+__global__ void __launch_bounds__(256) k_bwd_big(const BigFront* __restrict__ bfs, const BigItem* __restrict__ items,
+                                                 int nitems, const double* __restrict__ heap, double* __restrict__ W,
+                                                 double* __restrict__ y, int n, int* __restrict__ flags, int epoch) {
+    __shared__ double tile[64 * 65];
+    __shared__ double xs[64 * NR];
+    const int tid = threadIdx.x, lo = tid & 63, hi = tid >> 6;
+    for (int it = blockIdx.x; it < nitems; it += gridDim.x) {
+        const BigItem item = items[it];
+        const BigFront bf = bfs[item.front];
+        const int i = item.idx, s = bf.s, m = bf.m;
+        const int c0 = 64 * i;
+        const int kb = min(64, s - c0);
+        const double* UT = heap + bf.UToff;
+        double* w = W + bf.woff * NR;
+        double acc[NR];
+#pragma unroll
+        for (int c = 0; c < NR; c++) acc[c] = 0.0;
+        double dreg[16], treg[16];
+        // diagonal block UT[c0+a, c0+p] = U(p,a), a >= p
+#pragma unroll
+        for (int pp = 0; pp < 16; pp++) {
+            int p = hi * 16 + pp;
+            dreg[pp] = (lo < kb && p < kb && lo >= p) ? UT[c0 + lo + (int64_t)(c0 + p) * m] : 0.0;
+        }
+        const int nbb = (bf.r + 63) / 64;
+        const int nblk = nbb + (bf.npiv - 1 - i);
+        for (int b = 0; b < nblk; b++) {
+            int a0, na, waitk;
+            if (b < nbb) {
+                a0 = s + 64 * b;
+                na = min(64, m - a0);
+                waitk = -1;
+            } else {
+                waitk = bf.npiv - 1 - (b - nbb);
+                a0 = 64 * waitk;
+                na = min(64, s - a0);
+            }
+#pragma unroll
+            for (int pp = 0; pp < 16; pp++) {
+                int p = hi * 16 + pp;
+                treg[pp] = (lo < na && p < kb) ? UT[a0 + lo + (int64_t)(c0 + p) * m] : 0.0;
+            }
+            if (waitk >= 0 && tid == 0)
+                while (ld_acquire_gpu(&flags[bf.flag0 + waitk]) != epoch) __nanosleep(32);
+            __syncthreads();
+#pragma unroll
+            for (int pp = 0; pp < 16; pp++) tile[lo + 65 * (hi * 16 + pp)] = treg[pp];
+            for (int e = tid; e < 64 * NR; e += 256) {
+                int a = e & 63, c = e >> 6;
+                xs[e] = a < na ? __ldcg(&w[a0 + a + (int64_t)c * m]) : 0.0;
+            }
+            __syncthreads();
+            // thread (column lo, row group hi)
+#pragma unroll
+            for (int rr = 0; rr < 16; rr++) {
+                int a = hi * 16 + rr;
+                double u = tile[a + 65 * lo];
+#pragma unroll
+                for (int c = 0; c < NR; c++) acc[c] += u * xs[a + 64 * c];
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int c = 0; c < NR; c++) tile[(hi * 64 + lo) * NR + c] = acc[c];
+        __syncthreads();
+        double z[NR];
+        if (tid < 64) {
+#pragma unroll
+            for (int c = 0; c < NR; c++) {
+                double sum = tile[(0 * 64 + tid) * NR + c] + tile[(1 * 64 + tid) * NR + c] + tile[(2 * 64 + tid) * NR + c] +
+                             tile[(3 * 64 + tid) * NR + c];
+                z[c] = tid < kb ? y[bf.first + c0 + tid + (int64_t)c * n] - sum : 0.0;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int pp = 0; pp < 16; pp++) tile[lo + 65 * (hi * 16 + pp)] = dreg[pp];   // tile[a + 65 p] = U(p, a)
+        if (tid < 64)
+#pragma unroll
+            for (int c = 0; c < NR; c++) xs[tid + 64 * c] = z[c];
+        __syncthreads();
+        if (tid >= 32 && tid < 64) {   // unknowns 32..63 first
+            const int p = tid, lane = tid - 32;
+            double v[NR];
+#pragma unroll
+            for (int c = 0; c < NR; c++) v[c] = xs[p + 64 * c];
+            const double d = tile[p + 65 * p];
+            const double dinv = p < kb ? 1.0 / d : 0.0;
+            for (int q = 63; q >= 32; q--) {
+                double u = tile[q + 65 * p];
+#pragma unroll
+                for (int c = 0; c < NR; c++) {
+                    if (p == q) v[c] *= dinv;
+                    double xq = __shfl_sync(0xffffffffu, v[c], q - 32);
+                    if (p < q) v[c] -= u * xq;
+                }
+            }
+            (void)lane;
+#pragma unroll
+            for (int c = 0; c < NR; c++) xs[p + 64 * c] = v[c];
+        }
+        __syncthreads();
+        if (tid < 32) {
+            const int p = tid;
+            double v[NR];
+#pragma unroll
+            for (int c = 0; c < NR; c++) v[c] = xs[p + 64 * c];
+            for (int q = 32; q < 64; q++) {
+                double u = tile[q + 65 * p];
+#pragma unroll
+                for (int c = 0; c < NR; c++) v[c] -= u * xs[q + 64 * c];
+            }
+            const double d = tile[p + 65 * p];
+            const double dinv = p < kb ? 1.0 / d : 0.0;
+            for (int q = 31; q >= 0; q--) {
+                double u = tile[q + 65 * p];
+#pragma unroll
+                for (int c = 0; c < NR; c++) {
+                    if (p == q) v[c] *= dinv;
+                    double xq = __shfl_sync(0xffffffffu, v[c], q);
+                    if (p < q) v[c] -= u * xq;
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < NR; c++) xs[p + 64 * c] = v[c];
+        }
+        __syncthreads();
+        for (int e = tid; e < 64 * NR; e += 256) {
+            int a = e & 63, c = e >> 6;
+            if (a < kb) {
+                w[c0 + a + (int64_t)c * m] = xs[e];
+                y[bf.first + c0 + a + (int64_t)c * n] = xs[e];
+            }
+        }
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) st_release_gpu(&flags[bf.flag0 + i], epoch);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // residual and componentwise backward error (pdgsrfs: pdgsmv_AXglobal, pdgsmv_AXglobal_abs)
 //   r = b - A x ;  berr_c = max_i |r_i| / (|A||x| + |b|)_i
 // ------------------------------------------------------------------------------------------

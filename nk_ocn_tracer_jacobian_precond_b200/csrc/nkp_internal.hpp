@@ -107,6 +107,21 @@ struct SolveChild {
     int s, r;
 };
 
+// big fronts are swept by many CTAs with a flag-driven dataflow (k_fwd_big / k_bwd_big)
+struct BigFront {
+    int64_t Loff, UToff, bidx_off, woff;
+    int first, s, r, m;
+    int npiv;    // ceil(s / 64) pivot blocks
+    int nslab;   // npiv + ceil(r / 64) row slabs
+    int flag0;   // first flag of this front (one per pivot block)
+    int pad;
+};
+
+struct BigItem {
+    int front;   // index into Plan::big_fronts
+    int idx;     // row slab (forward) or pivot panel (backward)
+};
+
 struct LevelPlan {
     int level = 0;
     std::vector<int> fronts;             // fronts on this level
@@ -118,7 +133,11 @@ struct LevelPlan {
     std::vector<int> add_begin;          // size npass+1
     std::vector<int> add_tiles;          // per pass
     int64_t f22_zero_off = 0, f22_zero_len = 0;  // region of the update pool to clear
-    int solve_begin = 0, solve_end = 0;  // into Plan::solve_tasks
+    int solve_begin = 0, solve_end = 0;  // into Plan::solve_tasks (all fronts of the level)
+    int small_begin = 0, small_end = 0;  // into Plan::solve_small (fronts swept by one CTA each)
+    int big_begin = 0, big_end = 0;      // into Plan::big_fronts
+    int fwd_item_begin = 0, fwd_item_end = 0;  // into Plan::big_fwd_items
+    int bwd_item_begin = 0, bwd_item_end = 0;  // into Plan::big_bwd_items
 };
 
 struct Options {
@@ -129,6 +148,7 @@ struct Options {
     int add_tile = 32;     // extend-add tile
     int period_i = 0;
     int verbose = 0;
+    int64_t big_entries = 1 << 19;  // fronts with m*s >= this use the multi-CTA dataflow sweeps
 };
 
 struct Plan {
@@ -150,12 +170,17 @@ struct Plan {
     std::vector<AddTask> add_tasks;
     std::vector<SolveTask> solve_tasks;   // grouped by level (deepest first)
     std::vector<SolveChild> solve_children;
+    std::vector<SolveTask> solve_small;   // the non-big subset, grouped by level like solve_tasks
+    std::vector<BigFront> big_fronts;
+    std::vector<BigItem> big_fwd_items, big_bwd_items;
+    int n_big_flags = 0;
     int64_t factor_len = 0;    // doubles in the factor arena  [0, factor_len)
     int64_t pool_len[2] = {0, 0};  // update-matrix pools follow the arena
     int64_t pool_off[2] = {0, 0};
     int64_t heap_len = 0;
     int64_t solve_pool_len = 0;    // per rhs
     double flops = 0;          // algorithmic factor flops
+    double gemm_flops = 0;     // of which performed by the Schur-update GEMM launches (useful entries only)
     int64_t nnz_lu = 0;        // stored factor entries incl. diagonal
     int max_front = 0;
     double t_order = 0, t_symbolic = 0, t_plan = 0;

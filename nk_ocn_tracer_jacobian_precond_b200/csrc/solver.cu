@@ -62,7 +62,14 @@ struct nkp_solver {
     GemmTask* d_gemm = nullptr;
     AddTask* d_add = nullptr;
     SolveTask* d_solve = nullptr;
+    SolveTask* d_small = nullptr;
     SolveChild* d_children = nullptr;
+    BigFront* d_big = nullptr;
+    BigItem* d_fwd_items = nullptr;
+    BigItem* d_bwd_items = nullptr;
+    int* d_flags = nullptr;     // [0, nflags): forward, [nflags, 2 nflags): backward
+    int epoch = 0;
+    int coop_ctas = 0;          // co-resident CTAs for the dataflow sweeps
     double* d_W = nullptr;      // solve work vectors, MAX_NR columns
     double* d_y = nullptr;      // n x MAX_NR permuted rhs / solution
     double* d_r = nullptr;      // n x MAX_NR residual
@@ -78,7 +85,42 @@ struct nkp_solver {
     double t_analysis = 0, t_factor = 0, t_scatter = 0, t_solve = 0;
     int refine_steps = 0, tiny_pivots = 0;
     int64_t launches = 0;
+    // optional per-kernel-class event profiling of the factorisation
+    bool prof_on = false;
+    std::vector<cudaEvent_t> prof_ev;
+    std::vector<int> prof_cls;
+    int prof_used = 0;
+    double t_cls[5] = {0, 0, 0, 0, 0};
+    int64_t n_cls[5] = {0, 0, 0, 0, 0};
+    double t_sweeps = 0;
 };
+
+enum { KC_OTHER = 0, KC_ADD = 1, KC_DIAG = 2, KC_TRSM = 3, KC_GEMM = 4 };
+
+// record "everything launched so far belongs to class cls" on the solver's stream
+static void prof_mark(nkp_solver* s, int cls) {
+    if (!s->prof_on) return;
+    if (s->prof_used == (int)s->prof_ev.size()) {
+        cudaEvent_t e;
+        if (cudaEventCreate(&e) != cudaSuccess) return;
+        s->prof_ev.push_back(e);
+        s->prof_cls.push_back(0);
+    }
+    cudaEventRecord(s->prof_ev[s->prof_used], s->stream);
+    s->prof_cls[s->prof_used] = cls;
+    s->prof_used++;
+}
+
+static void prof_collect(nkp_solver* s) {
+    for (int c = 0; c < 5; c++) s->t_cls[c] = 0, s->n_cls[c] = 0;
+    for (int i = 1; i < s->prof_used; i++) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, s->prof_ev[i - 1], s->prof_ev[i]) != cudaSuccess) continue;
+        s->t_cls[s->prof_cls[i]] += ms * 1e-3;
+        s->n_cls[s->prof_cls[i]]++;
+    }
+    s->prof_used = 0;
+}
 
 template <class T>
 static int upload(T** dptr, const std::vector<T>& v) {
@@ -138,6 +180,7 @@ int nkp_create(nkp_solver** out, int n, const int* rowptr, const int* colind, co
     po.trsm_rows = TRSM_ROWS;
     po.add_tile = ADD_TILE;
     po.verbose = o.verbose;
+    if (getenv("NKP_BIG_ENTRIES")) po.big_entries = atoll(getenv("NKP_BIG_ENTRIES"));
     const int* coords[3] = {ci, cj, ck};
     auto t0 = std::chrono::steady_clock::now();
     int rc = analyse(n, rowptr, colind, (ci || cj || ck) ? coords : nullptr, po, s->plan);
@@ -178,6 +221,26 @@ int nkp_create(nkp_solver** out, int n, const int* rowptr, const int* colind, co
         if (upload(&s->d_add, P.add_tasks)) return NKP_ECUDA;
         if (upload(&s->d_solve, P.solve_tasks)) return NKP_ECUDA;
         if (upload(&s->d_children, P.solve_children)) return NKP_ECUDA;
+        if (upload(&s->d_small, P.solve_small)) return NKP_ECUDA;
+        if (upload(&s->d_big, P.big_fronts)) return NKP_ECUDA;
+        if (upload(&s->d_fwd_items, P.big_fwd_items)) return NKP_ECUDA;
+        if (upload(&s->d_bwd_items, P.big_bwd_items)) return NKP_ECUDA;
+        CK(cudaMalloc((void**)&s->d_flags, sizeof(int) * (size_t)(2 * P.n_big_flags + 2)));
+        CK(cudaMemset(s->d_flags, 0, sizeof(int) * (size_t)(2 * P.n_big_flags + 2)));
+        {
+            cudaDeviceProp prop;
+            CK(cudaGetDeviceProperties(&prop, o.device));
+            int occ = 0, minocc = 1 << 30;
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_fwd_big<8>, 256, 0));
+            minocc = std::min(minocc, occ);
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_bwd_big<8>, 256, 0));
+            minocc = std::min(minocc, occ);
+            if (!prop.cooperativeLaunch || minocc < 1) {
+                g_err = "device cannot run the cooperative dataflow sweeps";
+                return NKP_ECUDA;
+            }
+            s->coop_ctas = prop.multiProcessorCount * std::min(minocc, 2);
+        }
         CK(cudaMalloc((void**)&s->d_val, sizeof(double) * (size_t)s->nnz));
         CK(cudaMalloc((void**)&s->d_R, sizeof(double) * n));
         CK(cudaMalloc((void**)&s->d_C, sizeof(double) * n));
@@ -231,34 +294,42 @@ static int do_factor(nkp_solver* s) {
                                                               s->d_R, s->d_C, s->heap);
     s->launches++;
     CK(cudaEventRecord(s->ev[1], st));
+    s->prof_used = 0;
+    prof_mark(s, KC_OTHER);
     // with equilibration every row/column max is in [1,2): threshold relative to ||A|| ~ 1
     double tiny = std::sqrt(2.220446049250313e-16) * (s->opt.equil ? 1.0 : s->amax);
     for (int l = P.nlevels - 1; l >= 0; l--) {
         const LevelPlan& L = P.levels[l];
-        if (L.f22_zero_len > 0)
+        if (L.f22_zero_len > 0) {
             CK(cudaMemsetAsync(s->heap + L.f22_zero_off, 0, sizeof(double) * (size_t)L.f22_zero_len, st));
+            prof_mark(s, KC_OTHER);
+        }
         int npass = (int)L.add_tiles.size();
         for (int pass = 0; pass < npass; pass++) {
             int nt = L.add_begin[pass + 1] - L.add_begin[pass];
             if (nt == 0 || L.add_tiles[pass] == 0) continue;
             k_extend_add<<<L.add_tiles[pass], 256, 0, st>>>(s->d_add + L.add_begin[pass], nt, s->d_rel, s->heap, nb);
             s->launches++;
+            prof_mark(s, KC_ADD);
         }
         for (int step = 0; step < L.nsteps; step++) {
             int nd = L.diag_begin[step + 1] - L.diag_begin[step];
             if (nd > 0) {
                 k_diag<<<nd, 256, 0, st>>>(s->d_diag + L.diag_begin[step], s->heap, tiny, s->d_nrepl);
                 s->launches++;
+                prof_mark(s, KC_DIAG);
             }
             int ntr = L.trsm_begin[step + 1] - L.trsm_begin[step];
             if (ntr > 0 && L.trsm_ctas[step] > 0) {
                 k_trsm<<<L.trsm_ctas[step], TRSM_ROWS, 0, st>>>(s->d_trsm + L.trsm_begin[step], ntr, s->heap);
                 s->launches++;
+                prof_mark(s, KC_TRSM);
             }
             int ng = L.gemm_begin[step + 1] - L.gemm_begin[step];
             if (ng > 0 && L.gemm_tiles[step] > 0) {
                 k_gemm<<<L.gemm_tiles[step], 256, G_SMEM, st>>>(s->d_gemm + L.gemm_begin[step], ng, s->heap, nb);
                 s->launches++;
+                prof_mark(s, KC_GEMM);
             }
         }
     }
@@ -274,6 +345,7 @@ static int do_factor(nkp_solver* s) {
     s->t_factor = ms02 * 1e-3;
     s->tiny_pivots = nrepl;
     s->factored = true;
+    if (s->prof_on) prof_collect(s);
     if (s->opt.verbose)
         fprintf(stderr, "[nkp] factor: %.3f ms (scatter %.3f ms), %.2f TFLOP/s, tiny pivots replaced: %d\n",
                 ms02, ms01, P.flops / (ms02 * 1e-3) * 1e-12, nrepl);
@@ -312,20 +384,58 @@ template <int NR>
 static int sweeps(nkp_solver* s) {
     Plan& P = s->plan;
     cudaStream_t st = s->stream;
+    s->epoch++;
+    int epoch = s->epoch;
+    int n = s->n;
+    int* flags_f = s->d_flags;
+    int* flags_b = s->d_flags + P.n_big_flags;
+    const double* heap = s->heap;
     for (int l = P.nlevels - 1; l >= 0; l--) {
         const LevelPlan& L = P.levels[l];
-        int nt = L.solve_end - L.solve_begin;
-        if (nt == 0) continue;
-        k_fwd<NR><<<nt, SOLVE_THREADS, 0, st>>>(s->d_solve + L.solve_begin, s->d_children, s->d_rel, s->heap, s->d_W,
-                                                s->d_y, s->n, NR);
-        s->launches++;
+        int nsmall = L.small_end - L.small_begin;
+        if (nsmall > 0) {
+            k_fwd<NR><<<nsmall, SOLVE_THREADS, 0, st>>>(s->d_small + L.small_begin, s->d_children, s->d_rel, s->heap,
+                                                        s->d_W, s->d_y, s->n, NR);
+            s->launches++;
+        }
+        int nbig = L.big_end - L.big_begin;
+        if (nbig > 0) {
+            k_fwd_big_init<NR><<<nbig, SOLVE_THREADS, 0, st>>>(s->d_big + L.big_begin, s->d_solve, s->d_children,
+                                                               s->d_rel, s->d_W, s->d_y, s->n);
+            const BigFront* bfs = s->d_big;
+            const BigItem* items = s->d_fwd_items + L.fwd_item_begin;
+            int nitems = L.fwd_item_end - L.fwd_item_begin;
+            double* W = s->d_W;
+            double* y = s->d_y;
+            void* args[] = {(void*)&bfs, (void*)&items, (void*)&nitems, (void*)&heap, (void*)&W,
+                            (void*)&y,   (void*)&n,     (void*)&flags_f, (void*)&epoch};
+            int grid = std::min(nitems, s->coop_ctas);
+            CK(cudaLaunchCooperativeKernel((void*)k_fwd_big<NR>, dim3(grid), dim3(256), args, 0, st));
+            s->launches += 2;
+        }
     }
     for (int l = 0; l < P.nlevels; l++) {
         const LevelPlan& L = P.levels[l];
-        int nt = L.solve_end - L.solve_begin;
-        if (nt == 0) continue;
-        k_bwd<NR><<<nt, SOLVE_THREADS, 0, st>>>(s->d_solve + L.solve_begin, s->d_bidx, s->heap, s->d_W, s->d_y, s->n, NR);
-        s->launches++;
+        int nsmall = L.small_end - L.small_begin;
+        if (nsmall > 0) {
+            k_bwd<NR><<<nsmall, SOLVE_THREADS, 0, st>>>(s->d_small + L.small_begin, s->d_bidx, s->heap, s->d_W, s->d_y,
+                                                        s->n, NR);
+            s->launches++;
+        }
+        int nbig = L.big_end - L.big_begin;
+        if (nbig > 0) {
+            k_bwd_big_init<NR><<<nbig, SOLVE_THREADS, 0, st>>>(s->d_big + L.big_begin, s->d_bidx, s->d_W, s->d_y, s->n);
+            const BigFront* bfs = s->d_big;
+            const BigItem* items = s->d_bwd_items + L.bwd_item_begin;
+            int nitems = L.bwd_item_end - L.bwd_item_begin;
+            double* W = s->d_W;
+            double* y = s->d_y;
+            void* args[] = {(void*)&bfs, (void*)&items, (void*)&nitems, (void*)&heap, (void*)&W,
+                            (void*)&y,   (void*)&n,     (void*)&flags_b, (void*)&epoch};
+            int grid = std::min(nitems, s->coop_ctas);
+            CK(cudaLaunchCooperativeKernel((void*)k_bwd_big<NR>, dim3(grid), dim3(256), args, 0, st));
+            s->launches += 2;
+        }
     }
     CK(cudaGetLastError());
     return 0;
@@ -465,12 +575,18 @@ int nkp_sweeps_device(nkp_solver* s, double* dB, int ldb, int nrhs) {
     const int n = s->n;
     const int nrp = padded_nr(nrhs);
     const int g = (n + 255) / 256;
+    CK(cudaEventRecord(s->ev[2], s->stream));
     if (nrp > nrhs) CK(cudaMemsetAsync(s->d_y, 0, sizeof(double) * (size_t)n * nrp, s->stream));
     k_permute_in<<<g, 256, 0, s->stream>>>(n, nrhs, s->d_perm, s->d_R, dB, ldb, s->d_y);
     if (sweeps_nr(s, nrp)) return NKP_ECUDA;
     k_permute_out<<<g, 256, 0, s->stream>>>(n, nrhs, s->d_perm, s->d_C, s->d_y, dB, ldb, 0);
     s->launches += 2;
+    CK(cudaEventRecord(s->ev[3], s->stream));
     CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(s->stream));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, s->ev[2], s->ev[3]));
+    s->t_sweeps = ms * 1e-3;
     return NKP_OK;
 }
 
@@ -501,6 +617,19 @@ int nkp_get_stats(const nkp_solver* s, nkp_stats* st) {
     st->kernel_launches = s->launches;
     // 8 (nnz(L)+nnz(U)) + index bytes + 2*8*n per sweep pair
     st->solve_bytes = 8.0 * (double)P.nnz_lu + 4.0 * (double)(P.bidx.size() + P.rel.size()) + 16.0 * s->n;
+    st->t_gemm = s->t_cls[KC_GEMM];
+    st->gemm_flops = P.gemm_flops;
+    st->n_gemm = s->n_cls[KC_GEMM];
+    st->t_trsm = s->t_cls[KC_TRSM];
+    st->t_diag = s->t_cls[KC_DIAG];
+    st->t_extend_add = s->t_cls[KC_ADD];
+    st->t_sweeps = s->t_sweeps;
+    return NKP_OK;
+}
+
+int nkp_set_profile(nkp_solver* s, int on) {
+    if (!s) return NKP_EINVAL;
+    s->prof_on = on != 0;
     return NKP_OK;
 }
 
@@ -517,12 +646,14 @@ void nkp_destroy(nkp_solver* s) {
     void* ptrs[] = {s->heap,   s->d_rowptr, s->d_colind, s->d_rowidx, s->d_val,  s->d_scatter, s->d_perm,
                     s->d_bidx, s->d_rel,    s->d_R,      s->d_C,      s->d_diag, s->d_trsm,    s->d_gemm,
                     s->d_add,  s->d_solve,  s->d_children, s->d_W,    s->d_y,    s->d_r,       s->d_x,
-                    s->d_xb,   s->d_berr,   s->d_nrepl};
+                    s->d_xb,   s->d_berr,   s->d_nrepl,  s->d_small,  s->d_big,  s->d_fwd_items, s->d_bwd_items,
+                    s->d_flags};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (s->h_pinned) cudaFreeHost(s->h_pinned);
     for (int i = 0; i < 4; i++)
         if (s->ev[i]) cudaEventDestroy(s->ev[i]);
+    for (cudaEvent_t e : s->prof_ev) cudaEventDestroy(e);
     if (s->stream) cudaStreamDestroy(s->stream);
     delete s;
 }

@@ -29,7 +29,9 @@ class NkpStats(C.Structure):
                 ("heap_bytes", C.c_double), ("t_analysis", C.c_double), ("t_factor", C.c_double),
                 ("t_scatter", C.c_double), ("t_solve", C.c_double), ("refine_steps", C.c_int),
                 ("tiny_pivots", C.c_int), ("kernel_launches", C.c_int64), ("solve_bytes", C.c_double),
-                ("reserved", C.c_double * 8)]
+                ("t_gemm", C.c_double), ("gemm_flops", C.c_double), ("n_gemm", C.c_int64),
+                ("t_trsm", C.c_double), ("t_diag", C.c_double), ("t_extend_add", C.c_double),
+                ("t_sweeps", C.c_double), ("reserved", C.c_double * 8)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
@@ -60,6 +62,7 @@ def load_library():
     lib.nkp_get_perm.argtypes = [vp, P(C.c_int)]
     lib.nkp_get_stats.argtypes = [vp, P(NkpStats)]
     lib.nkp_sync.argtypes = [vp]
+    lib.nkp_set_profile.argtypes = [vp, C.c_int]
     lib.nkp_destroy.argtypes = [vp]
     lib.nkp_destroy.restype = None
     lib.nkp_last_error.restype = C.c_char_p
@@ -144,6 +147,9 @@ class TracerJacobianSolver:
     def residual_device(self, d_x, d_b, d_r, nrhs):
         _check(self._lib.nkp_residual_device(self._h, C.c_void_p(d_x), C.c_void_p(d_b), C.c_void_p(d_r), nrhs),
                "nkp_residual_device")
+
+    def set_profile(self, on=True):
+        _check(self._lib.nkp_set_profile(self._h, int(bool(on))), "nkp_set_profile")
 
     def sync(self):
         _check(self._lib.nkp_sync(self._h), "nkp_sync")

@@ -118,7 +118,7 @@ int nkp_sim_run(int n, const int* rowptr, const int* colind, const double* val, 
     if (opt.tn > nb) opt.tn = nb;
     if (getenv("NKP_SIM_TM")) opt.tm = atoi(getenv("NKP_SIM_TM"));
     if (getenv("NKP_SIM_TN")) opt.tn = atoi(getenv("NKP_SIM_TN"));
-    opt.verbose = 1;
+    opt.verbose = getenv("NKP_SIM_VERBOSE") ? 1 : 0;
     const int* coords[3] = {ci, cj, ck};
     Plan P;
     int rc = analyse(n, rowptr, colind, (ci || cj || ck) ? coords : nullptr, opt, P);
