@@ -704,7 +704,8 @@ int analyse(int n, const int* rowptr, const int* colind, const int* const coords
                 bf.npiv = (st.s + 63) / 64;
                 bf.nslab = bf.npiv + (st.r + 63) / 64;
                 bf.flag0 = plan.n_big_flags;
-                bf.pad = q;   // index of the full SolveTask (children list for the init kernel)
+                bf.nchild = st.nchild;
+                bf.child_list = st.child_list;
                 plan.n_big_flags += bf.npiv;
                 plan.big_fronts.push_back(bf);
             } else {

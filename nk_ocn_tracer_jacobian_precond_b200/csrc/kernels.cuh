@@ -261,9 +261,14 @@ __global__ void __launch_bounds__(TRSM_ROWS) k_trsm(const TrsmTask* __restrict__
 // ------------------------------------------------------------------------------------------
 
 constexpr int G_TM = 128, G_TN = 64, G_TK = 64;
+constexpr int G_KC = 32;          // K chunk of the cp.async pipeline (2 chunks per tile)
 constexpr int G_LDA = G_TM + 4;   // == 4 (mod 16): conflict-free 8-byte fragment loads
 constexpr int G_LDB = G_TN + 4;
+constexpr int G_LDC = G_TM + 2;   // == 2 (mod 16): conflict-free accumulator staging
 constexpr int G_SMEM = (G_TK * G_LDA + G_TK * G_LDB) * 8;
+
+__device__ __forceinline__ void cp_async_wait_1() { asm volatile("cp.async.wait_group 1;\n" ::); }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p)); }
 
 __global__ void __launch_bounds__(256, 2) k_gemm(const GemmTask* __restrict__ tasks, int ntasks,
                                                  double* __restrict__ heap, int nb) {
@@ -281,21 +286,31 @@ __global__ void __launch_bounds__(256, 2) k_gemm(const GemmTask* __restrict__ ta
     const double* A = heap + tk.Aoff + m0;
     const double* B = heap + tk.Boff + n0;
     const int mrem = tk.M - m0, nrem = tk.N - n0, K = tk.K;
+    double* C = heap + tk.Coff + m0 + (int64_t)n0 * tk.ldc;
 
-    // stage A (128 x 64) and B (64 x 64) tiles, zero-filling out-of-range elements
-    for (int e = threadIdx.x; e < G_TK * G_TM; e += 256) {
-        int i = e % G_TM, k = e / G_TM;
-        bool ok = (i < mrem) && (k < K);
-        cp_async8(&As[k * G_LDA + i], ok ? (A + i + (int64_t)k * tk.lda) : A, ok);
+    // stage A (128 x 64) and B (64 x 64) in two K chunks (two cp.async groups), zero-filling
+    // out-of-range elements; meanwhile pull the C tile towards L2 for the epilogue
+#pragma unroll
+    for (int ch = 0; ch < G_TK / G_KC; ch++) {
+        for (int e = threadIdx.x; e < G_KC * G_TM; e += 256) {
+            int i = e % G_TM, k = ch * G_KC + e / G_TM;
+            bool ok = (i < mrem) && (k < K);
+            cp_async8(&As[k * G_LDA + i], ok ? (A + i + (int64_t)k * tk.lda) : A, ok);
+        }
+        for (int e = threadIdx.x; e < G_KC * G_TN; e += 256) {
+            int i = e % G_TN, k = ch * G_KC + e / G_TN;
+            bool ok = (i < nrem) && (k < K);
+            cp_async8(&Bs[k * G_LDB + i], ok ? (B + i + (int64_t)k * tk.ldb) : B, ok);
+        }
+        cp_async_commit();
     }
-    for (int e = threadIdx.x; e < G_TK * G_TN; e += 256) {
-        int i = e % G_TN, k = e / G_TN;
-        bool ok = (i < nrem) && (k < K);
-        cp_async8(&Bs[k * G_LDB + i], ok ? (B + i + (int64_t)k * tk.ldb) : B, ok);
+    {
+        // 128 rows x 8 B = 1 KB per column = 8 lines; 64 columns -> 512 lines, 2 per thread
+        for (int e = threadIdx.x; e < G_TN * 8; e += 256) {
+            int j = e >> 3, seg = e & 7;
+            if (j < nrem && seg * 16 < mrem) prefetch_l2(C + seg * 16 + (int64_t)j * tk.ldc);
+        }
     }
-    cp_async_commit();
-    cp_async_wait_all();
-    __syncthreads();
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int wm = (warp & 3) * 32, wn = (warp >> 2) * 32;
@@ -307,36 +322,55 @@ __global__ void __launch_bounds__(256, 2) k_gemm(const GemmTask* __restrict__ ta
         for (int b = 0; b < 4; b++) acc[a][b][0] = acc[a][b][1] = 0.0;
 
     const int ksteps = (K + 3) >> 2;
-    for (int ks = 0; ks < ksteps; ks++) {
-        const double* ap = As + (ks * 4 + lc) * G_LDA + wm + lr;
-        const double* bp = Bs + (ks * 4 + lc) * G_LDB + wn + lr;
-        double af[4], bf[4];
 #pragma unroll
-        for (int a = 0; a < 4; a++) af[a] = ap[a * 8];
+    for (int ch = 0; ch < G_TK / G_KC; ch++) {
+        if (ch == 0) cp_async_wait_1();
+        else cp_async_wait_all();
+        __syncthreads();
+        const int ks1 = min(ksteps, (ch + 1) * (G_KC / 4));
+        for (int ks = ch * (G_KC / 4); ks < ks1; ks++) {
+            const double* ap = As + (ks * 4 + lc) * G_LDA + wm + lr;
+            const double* bp = Bs + (ks * 4 + lc) * G_LDB + wn + lr;
+            double af[4], bf[4];
 #pragma unroll
-        for (int b = 0; b < 4; b++) bf[b] = bp[b * 8];
+            for (int a = 0; a < 4; a++) af[a] = ap[a * 8];
 #pragma unroll
-        for (int a = 0; a < 4; a++)
+            for (int b = 0; b < 4; b++) bf[b] = bp[b * 8];
 #pragma unroll
-            for (int b = 0; b < 4; b++) dmma884(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
+            for (int a = 0; a < 4; a++)
+#pragma unroll
+                for (int b = 0; b < 4; b++) dmma884(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
+        }
     }
     __syncthreads();
     // stage the product through shared memory so that the read-modify-write of C is coalesced
-    double* Cs = smem;   // Cs[n * G_LDA + m]
+    double* Cs = smem;   // Cs[n * G_LDC + m]
 #pragma unroll
     for (int a = 0; a < 4; a++)
 #pragma unroll
         for (int b = 0; b < 4; b++) {
             int r = wm + a * 8 + lr;
             int c = wn + b * 8 + 2 * lc;
-            Cs[c * G_LDA + r] = acc[a][b][0];
-            Cs[(c + 1) * G_LDA + r] = acc[a][b][1];
+            Cs[c * G_LDC + r] = acc[a][b][0];
+            Cs[(c + 1) * G_LDC + r] = acc[a][b][1];
         }
     __syncthreads();
-    double* C = heap + tk.Coff + m0 + (int64_t)n0 * tk.ldc;
-    for (int e = threadIdx.x; e < G_TM * G_TN; e += 256) {
-        int i = e % G_TM, j = e / G_TM;
-        if (i < mrem && j < nrem) C[i + (int64_t)j * tk.ldc] -= Cs[j * G_LDA + i];
+    // all loads of C first (independent, deep memory-level parallelism), then update + store
+    constexpr int PER = 16;   // 2 passes x 16 elements per thread
+    const int i = threadIdx.x % G_TM, jb = threadIdx.x / G_TM;   // jb in {0,1}
+#pragma unroll
+    for (int half = 0; half < 2; half++) {
+        double cv[PER];
+#pragma unroll
+        for (int q = 0; q < PER; q++) {
+            int j = jb + 2 * (half * PER + q);
+            cv[q] = (i < mrem && j < nrem) ? C[i + (int64_t)j * tk.ldc] : 0.0;
+        }
+#pragma unroll
+        for (int q = 0; q < PER; q++) {
+            int j = jb + 2 * (half * PER + q);
+            if (i < mrem && j < nrem) C[i + (int64_t)j * tk.ldc] = cv[q] - Cs[j * G_LDC + i];
+        }
     }
 }
 
@@ -550,51 +584,11 @@ __device__ __forceinline__ void st_release_gpu(int* p, int v) {
 }
 
 template <int NR>
-__global__ void __launch_bounds__(SOLVE_THREADS) k_fwd_big_init(const BigFront* __restrict__ bfs,
-                                                                const SolveTask* __restrict__ alltasks,
-                                                                const SolveChild* __restrict__ children,
-                                                                const int* __restrict__ rel, double* __restrict__ W,
-                                                                const double* __restrict__ y, int n) {
-    const BigFront bf = bfs[blockIdx.x];
-    const SolveTask tk = alltasks[bf.pad];
-    const int s = bf.s, m = bf.m;
-    double* w = W + bf.woff * NR;
-    for (int a = threadIdx.x; a < m; a += SOLVE_THREADS)
-#pragma unroll
-        for (int c = 0; c < NR; c++) w[a + (int64_t)c * m] = a < s ? y[bf.first + a + (int64_t)c * n] : 0.0;
-    __syncthreads();
-    for (int ch = 0; ch < tk.nchild; ch++) {
-        const SolveChild sc = children[tk.child_list + ch];
-        const int mc = sc.s + sc.r;
-        const double* wc = W + sc.woff * NR + sc.s;
-        const int* rl = rel + sc.rel_off;
-        for (int a = threadIdx.x; a < sc.r; a += SOLVE_THREADS) {
-            int d = rl[a];
-#pragma unroll
-            for (int c = 0; c < NR; c++) w[d + (int64_t)c * m] += wc[a + (int64_t)c * mc];
-        }
-        __syncthreads();
-    }
-}
-
-template <int NR>
-__global__ void __launch_bounds__(SOLVE_THREADS) k_bwd_big_init(const BigFront* __restrict__ bfs,
-                                                                const int* __restrict__ bidx, double* __restrict__ W,
-                                                                const double* __restrict__ y, int n) {
-    const BigFront bf = bfs[blockIdx.x];
-    double* w = W + bf.woff * NR;
-    const int* bi = bidx + bf.bidx_off;
-    for (int a = threadIdx.x; a < bf.r; a += SOLVE_THREADS) {
-        int g = bi[a];
-#pragma unroll
-        for (int c = 0; c < NR; c++) w[bf.s + a + (int64_t)c * bf.m] = y[g + (int64_t)c * n];
-    }
-}
-
-template <int NR>
 __global__ void __launch_bounds__(256) k_fwd_big(const BigFront* __restrict__ bfs, const BigItem* __restrict__ items,
-                                                 int nitems, const double* __restrict__ heap, double* __restrict__ W,
-                                                 double* __restrict__ y, int n, int* __restrict__ flags, int epoch) {
+                                                 int nitems, const SolveChild* __restrict__ children,
+                                                 const int* __restrict__ rel, const double* __restrict__ heap,
+                                                 double* __restrict__ W, double* __restrict__ y, int n,
+                                                 int* __restrict__ flags, int epoch) {
     __shared__ double buf[64 * 65];   // reduction scratch, then the diagonal block
     __shared__ double ys[64 * NR];
     const int tid = threadIdx.x, row = tid & 63, cg = tid >> 6;
@@ -617,6 +611,34 @@ __global__ void __launch_bounds__(256) k_fwd_big(const BigFront* __restrict__ bf
             for (int pp = 0; pp < 16; pp++) {
                 int p = cg * 16 + pp;
                 treg[pp] = (row < nrow && p < nrow && row > p) ? L[r0 + row + (int64_t)(r0 + p) * m] : 0.0;
+            }
+        }
+        // initial value of this slab's rows: the pivots' right-hand side plus the children's
+        // update vectors (children in fixed order: deterministic).  rel[] of a child is
+        // ascending, so the entry mapping to row r0+tid is found by bisection.
+        double base[NR];
+#pragma unroll
+        for (int c = 0; c < NR; c++) base[c] = 0.0;
+        if (tid < nrow) {
+            if (pivot)
+#pragma unroll
+                for (int c = 0; c < NR; c++) base[c] = y[bf.first + r0 + tid + (int64_t)c * n];
+            const int target = r0 + tid;
+            for (int ch = 0; ch < bf.nchild; ch++) {
+                const SolveChild sc = children[bf.child_list + ch];
+                const int* rl = rel + sc.rel_off;
+                int lo = 0, hi = sc.r;
+                while (lo < hi) {
+                    int mid = (lo + hi) >> 1;
+                    if (rl[mid] < target) lo = mid + 1;
+                    else hi = mid;
+                }
+                if (lo < sc.r && rl[lo] == target) {
+                    const int mc = sc.s + sc.r;
+                    const double* wc = W + sc.woff * NR + sc.s;
+#pragma unroll
+                    for (int c = 0; c < NR; c++) base[c] += wc[lo + (int64_t)c * mc];
+                }
             }
         }
         auto loadL = [&](int k) {
@@ -655,7 +677,7 @@ __global__ void __launch_bounds__(256) k_fwd_big(const BigFront* __restrict__ bf
             for (int c = 0; c < NR; c++) {
                 double sum = buf[(0 * 64 + tid) * NR + c] + buf[(1 * 64 + tid) * NR + c] + buf[(2 * 64 + tid) * NR + c] +
                              buf[(3 * 64 + tid) * NR + c];
-                val[c] = tid < nrow ? __ldcg(&w[r0 + tid + (int64_t)c * m]) - sum : 0.0;
+                val[c] = tid < nrow ? base[c] - sum : 0.0;
             }
         }
         if (!pivot) {
@@ -722,8 +744,9 @@ __global__ void __launch_bounds__(256) k_fwd_big(const BigFront* __restrict__ bf
 
 template <int NR>
 __global__ void __launch_bounds__(256) k_bwd_big(const BigFront* __restrict__ bfs, const BigItem* __restrict__ items,
-                                                 int nitems, const double* __restrict__ heap, double* __restrict__ W,
-                                                 double* __restrict__ y, int n, int* __restrict__ flags, int epoch) {
+                                                 int nitems, const int* __restrict__ bidx,
+                                                 const double* __restrict__ heap, double* __restrict__ y, int n,
+                                                 int* __restrict__ flags, int epoch) {
     __shared__ double tile[64 * 65];
     __shared__ double xs[64 * NR];
     const int tid = threadIdx.x, lo = tid & 63, hi = tid >> 6;
@@ -734,7 +757,7 @@ __global__ void __launch_bounds__(256) k_bwd_big(const BigFront* __restrict__ bf
         const int c0 = 64 * i;
         const int kb = min(64, s - c0);
         const double* UT = heap + bf.UToff;
-        double* w = W + bf.woff * NR;
+        const int* bi = bidx + bf.bidx_off;
         double acc[NR];
 #pragma unroll
         for (int c = 0; c < NR; c++) acc[c] = 0.0;
@@ -770,7 +793,13 @@ __global__ void __launch_bounds__(256) k_bwd_big(const BigFront* __restrict__ bf
             for (int pp = 0; pp < 16; pp++) tile[lo + 65 * (hi * 16 + pp)] = treg[pp];
             for (int e = tid; e < 64 * NR; e += 256) {
                 int a = e & 63, c = e >> 6;
-                xs[e] = a < na ? __ldcg(&w[a0 + a + (int64_t)c * m]) : 0.0;
+                double xv = 0.0;
+                if (a < na) {
+                    // boundary rows: final solution of an ancestor; pivot rows: published by a later panel
+                    int g = waitk < 0 ? bi[a0 - s + a] : bf.first + a0 + a;
+                    xv = __ldcg(&y[g + (int64_t)c * n]);
+                }
+                xs[e] = xv;
             }
             __syncthreads();
             // thread (column lo, row group hi)
@@ -850,10 +879,7 @@ __global__ void __launch_bounds__(256) k_bwd_big(const BigFront* __restrict__ bf
         __syncthreads();
         for (int e = tid; e < 64 * NR; e += 256) {
             int a = e & 63, c = e >> 6;
-            if (a < kb) {
-                w[c0 + a + (int64_t)c * m] = xs[e];
-                y[bf.first + c0 + a + (int64_t)c * n] = xs[e];
-            }
+            if (a < kb) y[bf.first + c0 + a + (int64_t)c * n] = xs[e];
         }
         __threadfence();
         __syncthreads();
@@ -866,27 +892,37 @@ __global__ void __launch_bounds__(256) k_bwd_big(const BigFront* __restrict__ bf
 //   r = b - A x ;  berr_c = max_i |r_i| / (|A||x| + |b|)_i
 // ------------------------------------------------------------------------------------------
 
-__global__ void k_residual(int n, int nrhs, const int* __restrict__ rowptr, const int* __restrict__ colind,
-                           const double* __restrict__ val, const double* __restrict__ x, int ldx,
-                           const double* __restrict__ b, int ldb, double* __restrict__ r,
-                           double* __restrict__ berr, double safe) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    int p0 = rowptr[i], p1 = rowptr[i + 1];
-    for (int c = 0; c < nrhs; c++) {
+// grid: (ceil(n/256), nrhs); one thread per (row, rhs); the matrix is re-read per rhs from L2
+__global__ void __launch_bounds__(256) k_residual(int n, int nrhs, const int* __restrict__ rowptr,
+                                                  const int* __restrict__ colind, const double* __restrict__ val,
+                                                  const double* __restrict__ x, int ldx, const double* __restrict__ b,
+                                                  int ldb, double* __restrict__ r, double* __restrict__ berr,
+                                                  double safe) {
+    __shared__ double wmax[8];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = blockIdx.y;
+    double e = 0.0;
+    if (i < n) {
         const double* xc = x + (int64_t)c * ldx;
-        double bi = b[i + (int64_t)c * ldb];
+        const double bi = b[i + (int64_t)c * ldb];
         double acc = bi, aabs = fabs(bi);
-        for (int p = p0; p < p1; p++) {
+        const int p1 = rowptr[i + 1];
+        for (int p = rowptr[i]; p < p1; p++) {
             double a = val[p], xv = xc[colind[p]];
             acc = fma(-a, xv, acc);
             aabs = fma(fabs(a), fabs(xv), aabs);
         }
         r[i + (int64_t)c * n] = acc;
-        if (berr) {
-            double e = aabs > safe ? fabs(acc) / aabs : (fabs(acc) + safe) / (aabs + safe);
-            atomic_max_pos_double(&berr[c], e);
-        }
+        e = aabs > safe ? fabs(acc) / aabs : (fabs(acc) + safe) / (aabs + safe);
+    }
+    if (berr == nullptr) return;
+    for (int o = 16; o > 0; o >>= 1) e = fmax(e, __shfl_xor_sync(0xffffffffu, e, o));
+    if ((threadIdx.x & 31) == 0) wmax[threadIdx.x >> 5] = e;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double m = wmax[0];
+        for (int w = 1; w < 8; w++) m = fmax(m, wmax[w]);
+        atomic_max_pos_double(&berr[c], m);
     }
 }
 

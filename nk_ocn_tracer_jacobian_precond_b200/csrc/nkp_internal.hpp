@@ -114,7 +114,8 @@ struct BigFront {
     int npiv;    // ceil(s / 64) pivot blocks
     int nslab;   // npiv + ceil(r / 64) row slabs
     int flag0;   // first flag of this front (one per pivot block)
-    int pad;
+    int nchild;
+    int64_t child_list;  // into Plan::solve_children
 };
 
 struct BigItem {
@@ -148,7 +149,7 @@ struct Options {
     int add_tile = 32;     // extend-add tile
     int period_i = 0;
     int verbose = 0;
-    int64_t big_entries = 1 << 19;  // fronts with m*s >= this use the multi-CTA dataflow sweeps
+    int64_t big_entries = 1 << 16;  // fronts with m*s >= this use the multi-CTA dataflow sweeps
 };
 
 struct Plan {

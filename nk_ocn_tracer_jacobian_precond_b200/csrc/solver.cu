@@ -398,20 +398,19 @@ static int sweeps(nkp_solver* s) {
                                                         s->d_W, s->d_y, s->n, NR);
             s->launches++;
         }
-        int nbig = L.big_end - L.big_begin;
-        if (nbig > 0) {
-            k_fwd_big_init<NR><<<nbig, SOLVE_THREADS, 0, st>>>(s->d_big + L.big_begin, s->d_solve, s->d_children,
-                                                               s->d_rel, s->d_W, s->d_y, s->n);
+        int nitems = L.fwd_item_end - L.fwd_item_begin;
+        if (nitems > 0) {
             const BigFront* bfs = s->d_big;
             const BigItem* items = s->d_fwd_items + L.fwd_item_begin;
-            int nitems = L.fwd_item_end - L.fwd_item_begin;
+            const SolveChild* ch = s->d_children;
+            const int* rel = s->d_rel;
             double* W = s->d_W;
             double* y = s->d_y;
-            void* args[] = {(void*)&bfs, (void*)&items, (void*)&nitems, (void*)&heap, (void*)&W,
-                            (void*)&y,   (void*)&n,     (void*)&flags_f, (void*)&epoch};
+            void* args[] = {(void*)&bfs, (void*)&items, (void*)&nitems, (void*)&ch,      (void*)&rel,  (void*)&heap,
+                            (void*)&W,   (void*)&y,     (void*)&n,      (void*)&flags_f, (void*)&epoch};
             int grid = std::min(nitems, s->coop_ctas);
             CK(cudaLaunchCooperativeKernel((void*)k_fwd_big<NR>, dim3(grid), dim3(256), args, 0, st));
-            s->launches += 2;
+            s->launches++;
         }
     }
     for (int l = 0; l < P.nlevels; l++) {
@@ -422,19 +421,17 @@ static int sweeps(nkp_solver* s) {
                                                         s->n, NR);
             s->launches++;
         }
-        int nbig = L.big_end - L.big_begin;
-        if (nbig > 0) {
-            k_bwd_big_init<NR><<<nbig, SOLVE_THREADS, 0, st>>>(s->d_big + L.big_begin, s->d_bidx, s->d_W, s->d_y, s->n);
+        int nitems = L.bwd_item_end - L.bwd_item_begin;
+        if (nitems > 0) {
             const BigFront* bfs = s->d_big;
             const BigItem* items = s->d_bwd_items + L.bwd_item_begin;
-            int nitems = L.bwd_item_end - L.bwd_item_begin;
-            double* W = s->d_W;
+            const int* bidx = s->d_bidx;
             double* y = s->d_y;
-            void* args[] = {(void*)&bfs, (void*)&items, (void*)&nitems, (void*)&heap, (void*)&W,
+            void* args[] = {(void*)&bfs, (void*)&items, (void*)&nitems, (void*)&bidx, (void*)&heap,
                             (void*)&y,   (void*)&n,     (void*)&flags_b, (void*)&epoch};
             int grid = std::min(nitems, s->coop_ctas);
             CK(cudaLaunchCooperativeKernel((void*)k_bwd_big<NR>, dim3(grid), dim3(256), args, 0, st));
-            s->launches += 2;
+            s->launches++;
         }
     }
     CK(cudaGetLastError());
@@ -473,7 +470,7 @@ static int solve_chunk(nkp_solver* s, double* dB, int ldb, int nr, double* berr_
     for (;;) {
         // r = b - A x, berr
         CK(cudaMemsetAsync(s->d_berr, 0, sizeof(double) * MAX_NR, st));
-        k_residual<<<g, 256, 0, st>>>(n, nr, s->d_rowptr, s->d_colind, s->d_val, s->d_x, n, dB, ldb, s->d_r, s->d_berr, safe);
+        k_residual<<<dim3(g, nr), 256, 0, st>>>(n, nr, s->d_rowptr, s->d_colind, s->d_val, s->d_x, n, dB, ldb, s->d_r, s->d_berr, safe);
         s->launches++;
         CK(cudaMemcpyAsync(berr, s->d_berr, sizeof(double) * nr, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
@@ -559,9 +556,10 @@ int nkp_solve(nkp_solver* s, double* B, int ldb, int nrhs, double* berr) {
 
 int nkp_residual_device(nkp_solver* s, const double* dx, const double* db, double* dr, int nrhs) {
     if (!s || !dx || !db || !dr || nrhs < 0) return NKP_EINVAL;
+    if (nrhs == 0) return NKP_OK;
     CK(cudaSetDevice(s->opt.device));
     const int n = s->n;
-    k_residual<<<(n + 255) / 256, 256, 0, s->stream>>>(n, nrhs, s->d_rowptr, s->d_colind, s->d_val, dx, n, db, n, dr,
+    k_residual<<<dim3((n + 255) / 256, nrhs), 256, 0, s->stream>>>(n, nrhs, s->d_rowptr, s->d_colind, s->d_val, dx, n, db, n, dr,
                                                       nullptr, 0.0);
     s->launches++;
     CK(cudaGetLastError());

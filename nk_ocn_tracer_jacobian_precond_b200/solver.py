@@ -47,7 +47,7 @@ def load_library():
         return _lib
     if not os.path.exists(LIB_PATH):
         raise OSError(f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'`")
-    lib = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+    lib = C.CDLL(LIB_PATH)
     P = C.POINTER
     vp = C.c_void_p
     lib.nkp_default_options.argtypes = [P(NkpOptions)]

@@ -5,7 +5,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from nk_ocn_tracer_jacobian_precond_b200 import solver, synth
 import scipy.sparse as sp
 
-def run(imt, jmt, km, nrhs=1, reps=3):
+def run(imt, jmt, km, nrhs=1, reps=int(os.environ.get("NKP_CHECK_REPS", "3"))):
     g = synth.make_grid(imt, jmt, km, seed=1); c = synth.make_circulation(g, seed=1)
     n, rp, ci, nz, (ii, jj, kk, _) = synth.assemble_crs(g, c)
     A = sp.csr_matrix((nz, ci, rp), shape=(n, n))
