@@ -602,8 +602,16 @@ int analyse(int n, const int* rowptr, const int* colind, const int* const coords
                         cta0 += (below + opt.trsm_rows - 1) / opt.trsm_rows;
                         plan.trsm_tasks.push_back(tt);
                     }
-                    int trail_s = f.s - k1;  // remaining pivot columns
-                    auto push_gemm = [&](int64_t A, int64_t B, int64_t C, int M, int N, int lda, int ldb, int ldc, int skip) {
+                    // Two-level blocking: G inner panels (nb columns each) form an outer block.
+                    // After every inner panel only the rest of the outer block is updated
+                    // ("narrow", K = kb); after the last inner panel of the outer block everything
+                    // beyond it receives ONE update with K = width of the outer block ("wide").
+                    // The big trailing matrices are therefore read and written once per G panels.
+                    const int G = std::max(1, opt.outer);
+                    const int ko0 = (step / G) * G * nb;                 // first column of the outer block
+                    const int ke = std::min(f.s, ko0 + G * nb);          // one past its last column
+                    auto push_gemm = [&](int64_t A, int64_t B, int64_t C, int M, int N, int K, int lda, int ldb, int ldc,
+                                         int skip) {
                         if (M <= 0 || N <= 0) return;
                         GemmTask gt;
                         gt.Aoff = A;
@@ -611,7 +619,7 @@ int analyse(int n, const int* rowptr, const int* colind, const int* const coords
                         gt.Coff = C;
                         gt.M = M;
                         gt.N = N;
-                        gt.K = kb;
+                        gt.K = K;
                         gt.lda = lda;
                         gt.ldb = ldb;
                         gt.ldc = ldc;
@@ -630,20 +638,31 @@ int analyse(int n, const int* rowptr, const int* colind, const int* const coords
                                 int first_row = skip == 1 ? c0 : std::min(c0 + nb, N);
                                 area += (double)(M - first_row) * w;
                             }
-                        plan.gemm_flops += 2.0 * kb * area;
+                        plan.gemm_flops += 2.0 * K * area;
                     };
-                    int64_t Lpan = f.Loff + k1 + (int64_t)k0 * f.m;    // L[k1.., k0:k1]
-                    int64_t UTpan = f.UToff + k1 + (int64_t)k0 * f.m;  // U^T[k1.., k0:k1]
-                    if (trail_s > 0) {
-                        // block-lower targets in Larr: rows k1..m, cols k1..s
-                        push_gemm(Lpan, UTpan, f.Loff + k1 + (int64_t)k1 * f.m, below, trail_s, f.m, f.m, f.m, 1);
-                        // strictly block-upper targets in UTarr: rows (front cols) k1..m, cols (front rows) k1..s
-                        push_gemm(UTpan, Lpan, f.UToff + k1 + (int64_t)k1 * f.m, below, trail_s, f.m, f.m, f.m, 2);
-                    }
-                    if (f.r > 0) {
-                        int64_t Lb = f.Loff + f.s + (int64_t)k0 * f.m;
-                        int64_t UTb = f.UToff + f.s + (int64_t)k0 * f.m;
-                        push_gemm(Lb, UTb, f.F22off, f.r, f.r, f.m, f.m, f.r, 0);
+                    const int64_t ld = f.m;
+                    if (k1 < ke) {
+                        // narrow: block columns / rows [k1, ke) of the outer block, all rows below
+                        int64_t Lpan = f.Loff + k1 + (int64_t)k0 * ld;    // L[k1.., k0:k1]
+                        int64_t UTpan = f.UToff + k1 + (int64_t)k0 * ld;  // U^T[k1.., k0:k1]
+                        push_gemm(Lpan, UTpan, f.Loff + k1 + (int64_t)k1 * ld, below, ke - k1, kb, f.m, f.m, f.m, 1);
+                        push_gemm(UTpan, Lpan, f.UToff + k1 + (int64_t)k1 * ld, below, ke - k1, kb, f.m, f.m, f.m, 2);
+                    } else {
+                        // wide: k1 == ke, the outer block [ko0, ke) is completely factored
+                        const int K = ke - ko0;
+                        const int rest = f.m - ke;
+                        const int trail_s = f.s - ke;
+                        int64_t Lpan = f.Loff + ke + (int64_t)ko0 * ld;    // L[ke.., ko0:ke]
+                        int64_t UTpan = f.UToff + ke + (int64_t)ko0 * ld;  // U^T[ke.., ko0:ke]
+                        if (trail_s > 0) {
+                            push_gemm(Lpan, UTpan, f.Loff + ke + (int64_t)ke * ld, rest, trail_s, K, f.m, f.m, f.m, 1);
+                            push_gemm(UTpan, Lpan, f.UToff + ke + (int64_t)ke * ld, rest, trail_s, K, f.m, f.m, f.m, 2);
+                        }
+                        if (f.r > 0) {
+                            int64_t Lb = f.Loff + f.s + (int64_t)ko0 * ld;
+                            int64_t UTb = f.UToff + f.s + (int64_t)ko0 * ld;
+                            push_gemm(Lb, UTb, f.F22off, f.r, f.r, K, f.m, f.m, f.r, 0);
+                        }
                     }
                 }
             }

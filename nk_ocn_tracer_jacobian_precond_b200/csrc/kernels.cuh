@@ -260,12 +260,14 @@ __global__ void __launch_bounds__(TRSM_ROWS) k_trsm(const TrsmTask* __restrict__
 // CTA tile 128 x 64, 8 warps (4 x 2), warp tile 32 x 32.
 // ------------------------------------------------------------------------------------------
 
-constexpr int G_TM = 128, G_TN = 64, G_TK = 64;
-constexpr int G_KC = 32;          // K chunk of the cp.async pipeline (2 chunks per tile)
+constexpr int G_TM = 128, G_TN = 64;
+constexpr int G_KC = 32;          // K chunk of the cp.async ring (2 stages)
 constexpr int G_LDA = G_TM + 4;   // == 4 (mod 16): conflict-free 8-byte fragment loads
 constexpr int G_LDB = G_TN + 4;
 constexpr int G_LDC = G_TM + 2;   // == 2 (mod 16): conflict-free accumulator staging
-constexpr int G_SMEM = (G_TK * G_LDA + G_TK * G_LDB) * 8;
+constexpr int G_STAGE = G_KC * (G_LDA + G_LDB);   // doubles per stage
+constexpr int G_SMEM = 2 * G_STAGE * 8;
+static_assert(G_TN * G_LDC <= 2 * G_STAGE, "accumulator staging must fit in the ring");
 
 __device__ __forceinline__ void cp_async_wait_1() { asm volatile("cp.async.wait_group 1;\n" ::); }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p)); }
@@ -273,8 +275,6 @@ __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefe
 __global__ void __launch_bounds__(256, 2) k_gemm(const GemmTask* __restrict__ tasks, int ntasks,
                                                  double* __restrict__ heap, int nb) {
     extern __shared__ __align__(16) double smem[];
-    double* As = smem;                    // As[k * G_LDA + m]
-    double* Bs = smem + G_TK * G_LDA;     // Bs[k * G_LDB + n]
     int t = find_task(tasks, ntasks, (int)blockIdx.x, [](const GemmTask& x) { return x.tile0; });
     const GemmTask tk = tasks[t];
     int local = blockIdx.x - tk.tile0;
@@ -287,29 +287,31 @@ __global__ void __launch_bounds__(256, 2) k_gemm(const GemmTask* __restrict__ ta
     const double* B = heap + tk.Boff + n0;
     const int mrem = tk.M - m0, nrem = tk.N - n0, K = tk.K;
     double* C = heap + tk.Coff + m0 + (int64_t)n0 * tk.ldc;
+    const int nchunks = (K + G_KC - 1) / G_KC;
 
-    // stage A (128 x 64) and B (64 x 64) in two K chunks (two cp.async groups), zero-filling
-    // out-of-range elements; meanwhile pull the C tile towards L2 for the epilogue
-#pragma unroll
-    for (int ch = 0; ch < G_TK / G_KC; ch++) {
+    // stage one K chunk of A (128 x 32) and B (64 x 32), zero-filling out-of-range elements
+    auto issue = [&](int ch) {
+        double* As = smem + (ch & 1) * G_STAGE;   // As[k * G_LDA + m]
+        double* Bs = As + G_KC * G_LDA;           // Bs[k * G_LDB + n]
+        const int kbase = ch * G_KC;
         for (int e = threadIdx.x; e < G_KC * G_TM; e += 256) {
-            int i = e % G_TM, k = ch * G_KC + e / G_TM;
+            int i = e % G_TM, kk = e / G_TM, k = kbase + kk;
             bool ok = (i < mrem) && (k < K);
-            cp_async8(&As[k * G_LDA + i], ok ? (A + i + (int64_t)k * tk.lda) : A, ok);
+            cp_async8(&As[kk * G_LDA + i], ok ? (A + i + (int64_t)k * tk.lda) : A, ok);
         }
         for (int e = threadIdx.x; e < G_KC * G_TN; e += 256) {
-            int i = e % G_TN, k = ch * G_KC + e / G_TN;
+            int i = e % G_TN, kk = e / G_TN, k = kbase + kk;
             bool ok = (i < nrem) && (k < K);
-            cp_async8(&Bs[k * G_LDB + i], ok ? (B + i + (int64_t)k * tk.ldb) : B, ok);
+            cp_async8(&Bs[kk * G_LDB + i], ok ? (B + i + (int64_t)k * tk.ldb) : B, ok);
         }
         cp_async_commit();
-    }
-    {
-        // 128 rows x 8 B = 1 KB per column = 8 lines; 64 columns -> 512 lines, 2 per thread
-        for (int e = threadIdx.x; e < G_TN * 8; e += 256) {
-            int j = e >> 3, seg = e & 7;
-            if (j < nrem && seg * 16 < mrem) prefetch_l2(C + seg * 16 + (int64_t)j * tk.ldc);
-        }
+    };
+    issue(0);
+    if (nchunks > 1) issue(1);
+    // pull the C tile towards L2 for the epilogue: 512 lines of 128 B, 2 per thread
+    for (int e = threadIdx.x; e < G_TN * 8; e += 256) {
+        int j = e >> 3, seg = e & 7;
+        if (j < nrem && seg * 16 < mrem) prefetch_l2(C + seg * 16 + (int64_t)j * tk.ldc);
     }
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -321,14 +323,15 @@ __global__ void __launch_bounds__(256, 2) k_gemm(const GemmTask* __restrict__ ta
 #pragma unroll
         for (int b = 0; b < 4; b++) acc[a][b][0] = acc[a][b][1] = 0.0;
 
-    const int ksteps = (K + 3) >> 2;
-#pragma unroll
-    for (int ch = 0; ch < G_TK / G_KC; ch++) {
-        if (ch == 0) cp_async_wait_1();
+    for (int ch = 0; ch < nchunks; ch++) {
+        if (ch + 1 < nchunks) cp_async_wait_1();
         else cp_async_wait_all();
         __syncthreads();
-        const int ks1 = min(ksteps, (ch + 1) * (G_KC / 4));
-        for (int ks = ch * (G_KC / 4); ks < ks1; ks++) {
+        const double* As = smem + (ch & 1) * G_STAGE;
+        const double* Bs = As + G_KC * G_LDA;
+        const int ksteps = min(G_KC, K - ch * G_KC + 3) >> 2;
+#pragma unroll 4
+        for (int ks = 0; ks < ksteps; ks++) {
             const double* ap = As + (ks * 4 + lc) * G_LDA + wm + lr;
             const double* bp = Bs + (ks * 4 + lc) * G_LDB + wn + lr;
             double af[4], bf[4];
@@ -341,8 +344,9 @@ __global__ void __launch_bounds__(256, 2) k_gemm(const GemmTask* __restrict__ ta
 #pragma unroll
                 for (int b = 0; b < 4; b++) dmma884(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
         }
+        __syncthreads();
+        if (ch + 2 < nchunks) issue(ch + 2);
     }
-    __syncthreads();
     // stage the product through shared memory so that the read-modify-write of C is coalesced
     double* Cs = smem;   // Cs[n * G_LDC + m]
 #pragma unroll

@@ -64,7 +64,7 @@ struct TrsmTask {   // X * T = B in place on a tall panel: rows [0,nrows) x kb c
     int pad;
 };
 
-struct GemmTask {   // C[M x N] -= A[M x K] * B[N x K]^T, all column-major
+struct GemmTask {   // C[M x N] -= A[M x K] * B[N x K]^T, all column-major, K <= outer*nb
     int64_t Aoff, Boff, Coff;
     int M, N, K;
     int lda, ldb, ldc;
@@ -142,7 +142,8 @@ struct LevelPlan {
 };
 
 struct Options {
-    int nb = 64;           // pivot block width
+    int nb = 64;           // pivot block width (inner panel)
+    int outer = 4;         // inner panels per outer block (wide Schur updates use K = outer*nb)
     int leaf = 96;         // stop dissecting below this many unknowns
     int tm = 128, tn = 64; // GEMM tile (must match the kernel)
     int trsm_rows = 128;   // rows per TRSM CTA

@@ -181,6 +181,7 @@ int nkp_create(nkp_solver** out, int n, const int* rowptr, const int* colind, co
     po.add_tile = ADD_TILE;
     po.verbose = o.verbose;
     if (getenv("NKP_BIG_ENTRIES")) po.big_entries = atoll(getenv("NKP_BIG_ENTRIES"));
+    if (getenv("NKP_OUTER")) po.outer = std::max(1, atoi(getenv("NKP_OUTER")));
     const int* coords[3] = {ci, cj, ck};
     auto t0 = std::chrono::steady_clock::now();
     int rc = analyse(n, rowptr, colind, (ci || cj || ck) ? coords : nullptr, po, s->plan);
@@ -474,6 +475,11 @@ static int solve_chunk(nkp_solver* s, double* dB, int ldb, int nr, double* berr_
         s->launches++;
         CK(cudaMemcpyAsync(berr, s->d_berr, sizeof(double) * nr, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
+        if (s->opt.verbose > 1) {
+            fprintf(stderr, "[nkp] refine it %d berr:", it);
+            for (int c = 0; c < nr; c++) fprintf(stderr, " %.2e", berr[c]);
+            fprintf(stderr, "\n");
+        }
         bool go = false;
         for (int c = 0; c < nr; c++) {
             // SuperLU pdgsrfs: continue while berr > eps and berr decreased by at least a factor 2

@@ -116,6 +116,7 @@ int nkp_sim_run(int n, const int* rowptr, const int* colind, const double* val, 
     opt.nb = nb;
     opt.leaf = leaf;
     if (opt.tn > nb) opt.tn = nb;
+    if (getenv("NKP_OUTER")) opt.outer = atoi(getenv("NKP_OUTER"));
     if (getenv("NKP_SIM_TM")) opt.tm = atoi(getenv("NKP_SIM_TM"));
     if (getenv("NKP_SIM_TN")) opt.tn = atoi(getenv("NKP_SIM_TN"));
     opt.verbose = getenv("NKP_SIM_VERBOSE") ? 1 : 0;
