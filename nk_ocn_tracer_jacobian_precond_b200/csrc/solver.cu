@@ -388,6 +388,20 @@ static int sweeps(nkp_solver* s) {
     s->epoch++;
     int epoch = s->epoch;
     int n = s->n;
+    const bool trace = s->opt.verbose >= 3;
+    std::vector<cudaEvent_t> tev;
+    std::vector<std::string> tname;
+    auto mark = [&](const char* what, int level, int count) {
+        if (!trace) return;
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, st);
+        tev.push_back(e);
+        char b[96];
+        snprintf(b, sizeof b, "%s level %d (%d)", what, level, count);
+        tname.push_back(b);
+    };
+    mark("start", -1, 0);
     int* flags_f = s->d_flags;
     int* flags_b = s->d_flags + P.n_big_flags;
     const double* heap = s->heap;
@@ -398,6 +412,7 @@ static int sweeps(nkp_solver* s) {
             k_fwd<NR><<<nsmall, SOLVE_THREADS, 0, st>>>(s->d_small + L.small_begin, s->d_children, s->d_rel, s->heap,
                                                         s->d_W, s->d_y, s->n, NR);
             s->launches++;
+            mark("fwd small", l, nsmall);
         }
         int nitems = L.fwd_item_end - L.fwd_item_begin;
         if (nitems > 0) {
@@ -412,6 +427,7 @@ static int sweeps(nkp_solver* s) {
             int grid = std::min(nitems, s->coop_ctas);
             CK(cudaLaunchCooperativeKernel((void*)k_fwd_big<NR>, dim3(grid), dim3(256), args, 0, st));
             s->launches++;
+            mark("fwd big", l, nitems);
         }
     }
     for (int l = 0; l < P.nlevels; l++) {
@@ -421,6 +437,7 @@ static int sweeps(nkp_solver* s) {
             k_bwd<NR><<<nsmall, SOLVE_THREADS, 0, st>>>(s->d_small + L.small_begin, s->d_bidx, s->heap, s->d_W, s->d_y,
                                                         s->n, NR);
             s->launches++;
+            mark("bwd small", l, nsmall);
         }
         int nitems = L.bwd_item_end - L.bwd_item_begin;
         if (nitems > 0) {
@@ -433,9 +450,19 @@ static int sweeps(nkp_solver* s) {
             int grid = std::min(nitems, s->coop_ctas);
             CK(cudaLaunchCooperativeKernel((void*)k_bwd_big<NR>, dim3(grid), dim3(256), args, 0, st));
             s->launches++;
+            mark("bwd big", l, nitems);
         }
     }
     CK(cudaGetLastError());
+    if (trace) {
+        cudaStreamSynchronize(st);
+        for (size_t i = 1; i < tev.size(); i++) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, tev[i - 1], tev[i]);
+            fprintf(stderr, "[nkp] sweep %-28s %9.3f ms\n", tname[i].c_str(), ms);
+        }
+        for (cudaEvent_t e : tev) cudaEventDestroy(e);
+    }
     return 0;
 }
 
@@ -467,6 +494,7 @@ static int solve_chunk(nkp_solver* s, double* dB, int ldb, int nr, double* berr_
     double last[MAX_NR];
     for (int c = 0; c < nr; c++) last[c] = 1e300;
     double berr[MAX_NR] = {0};
+    bool done[MAX_NR] = {false};
     int it = 0;
     for (;;) {
         // r = b - A x, berr
@@ -482,8 +510,10 @@ static int solve_chunk(nkp_solver* s, double* dB, int ldb, int nr, double* berr_
         }
         bool go = false;
         for (int c = 0; c < nr; c++) {
-            // SuperLU pdgsrfs: continue while berr > eps and berr decreased by at least a factor 2
-            if (berr[c] > eps && berr[c] * 2.0 <= last[c]) go = true;
+            // SuperLU pdgsrfs, per right-hand side: continue while berr > eps and berr decreased by
+            // at least a factor 2; a column that stops once stays stopped
+            if (!done[c] && berr[c] > eps && berr[c] * 2.0 <= last[c]) go = true;
+            else done[c] = true;
             last[c] = berr[c];
         }
         if (!go || it >= s->opt.refine_max) break;
