@@ -215,11 +215,17 @@ def run_own(args):
     case = build_case(wl)
     t_gen = time.perf_counter() - t0
     n, nnz = case["n"], len(case["nzval"])
-    s = solver.TracerJacobianSolver(n, case["rowptr"], case["colind"], coords=case["coords"], device=local)
+    comm = None
+    if world > 1:
+        # subtree-to-GPU sharding: NCCL communicator of the solver, id shipped through torch.distributed
+        uid = [solver.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        comm = (rank, world, uid[0])
+    s = solver.TracerJacobianSolver(n, case["rowptr"], case["colind"], coords=case["coords"], comm=comm, device=local)
     st0 = s.stats()
 
     nsteps = args.warmup + args.steps
-    rng = np.random.default_rng(1234 + rank)
+    rng = np.random.default_rng(1234)   # identical operands on every rank (A, B, X are replicated)
     import scipy.sparse as sp
     # Newton sequence: new values every step, same pattern (BASELINE.json configs[4])
     host_vals = [case["nzval"] * (1.0 + 1e-3 * rng.standard_normal(nnz)) for _ in range(min(nsteps, 3))]
@@ -341,7 +347,8 @@ def run_own(args):
         cb = cpu_baseline(st["factor_flops"])
         line = {
             "metric": "numeric_factor_time_s", "value": factor_s, "unit": "s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": False, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": False,
+            "scaling": "weak" if world == 1 else "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {
                 "workload": f"{desc}: one numeric refactorisation + one batched solve of {NRHS} tracers per step",
@@ -349,14 +356,16 @@ def run_own(args):
                 "nnz_lu": st["nnz_lu"], "factor_flops": st["factor_flops"], "fronts": st["n_fronts"],
                 "levels": st["n_levels"], "max_front": st["max_front"], "analysis_s": st0["t_analysis"],
                 "l2": "operand and factors exceed L2 (%.1f GB heap); no flush needed" % (st["heap_bytes"] * 1e-9),
-                "parallelism": "1 GPU" if world == 1 else f"{world} independent replicas (subtree sharding not implemented yet)",
+                "parallelism": "1 GPU" if world == 1 else
+                f"{world} GPUs: nested-dissection subtrees sharded over the GPUs, top separator fronts on their heaviest "
+                f"child's GPU, NCCL send/recv of update matrices and broadcast of separator solutions ({int(st['n_xfers'])} transfers)",
                 "generate_s": t_gen,
             },
-            "solve_s": solve_s, "solves_per_sec": NRHS * world / solve_s, "refine_steps": float(np.mean(refine)),
+            "solve_s": solve_s, "solves_per_sec": NRHS / solve_s, "refine_steps": float(np.mean(refine)),
             "relres_max": relres, "solution_err_max": solerr, "berr_max": float(np.max(berr)),
             "roofline": roofline, "roofline_solve": roofline_solve, "cpu_baseline": cb,
             "e2e": {"value": e2e_factor, "unit": "s", "h2d_bytes_per_step": 8 * nnz + 8 * n * NRHS,
-                    "d2h_bytes_per_step": 8 * n * NRHS, "solve_s": e2e_solve, "solves_per_sec": NRHS * world / e2e_solve},
+                    "d2h_bytes_per_step": 8 * n * NRHS, "solve_s": e2e_solve, "solves_per_sec": NRHS / e2e_solve},
             "gpu_launches": int(launches), "clocks": clocks,
         }
         print(json.dumps(line))

@@ -75,7 +75,10 @@ typedef struct nkp_stats {
     double t_diag;
     double t_extend_add;
     double t_sweeps;         /* device seconds of the last raw sweep pair(s) (nkp_sweeps_device) */
-    double reserved[8];
+    double factor_flops_local; /* multi-GPU: flops of the fronts owned by this rank       */
+    double nnz_lu_local;
+    double n_xfers;          /* parent/child pairs whose data crosses GPUs               */
+    double reserved[5];
 } nkp_stats;
 
 void nkp_default_options(nkp_options* opt);
@@ -89,6 +92,19 @@ void nkp_default_options(nkp_options* opt);
 int nkp_create(nkp_solver** out, int n, const int* rowptr, const int* colind,
                const int* coord_i, const int* coord_j, const int* coord_k,
                const nkp_options* opt);
+
+/* Multi-GPU (one process per GPU): every rank calls nkp_create_dist with the
+ * same pattern; rank 0 obtains `unique_id` (NKP_UNIQUE_ID_BYTES bytes) from
+ * nkp_comm_unique_id and ships it to the other ranks by any means (the bench uses
+ * torch.distributed).  Independent nested-dissection subtrees are factored and swept on their
+ * owner GPU; only the update matrices / vectors of the top separator fronts and the
+ * separator solutions cross NVLink (NCCL send/recv/broadcast).  A, B and X are replicated
+ * on every rank, like solve_ABglobal (src/solve_ABglobal.c:132-139,194). */
+#define NKP_UNIQUE_ID_BYTES 128
+int nkp_comm_unique_id(void* unique_id);
+int nkp_create_dist(nkp_solver** out, int n, const int* rowptr, const int* colind,
+                    const int* coord_i, const int* coord_j, const int* coord_k,
+                    const nkp_options* opt, int rank, int nranks, const void* unique_id);
 
 /* Numeric factorisation from HOST values (nzval_row_wise, src/matrix.c:84), includes the
  * host->device copy.  Replaces pdgssvx*(nrhs = 0). */

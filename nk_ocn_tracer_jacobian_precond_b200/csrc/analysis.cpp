@@ -440,21 +440,94 @@ int analyse(int n, const int* rowptr, const int* colind, const int* const coords
     }
     plan.t_symbolic = now_s() - t0;
 
-    // ---- memory plan ------------------------------------------------------------------------
+    // ---- multi-GPU partition: rank-private subtrees + a shared top ----------------------------
+    //  Subtrees are independent: their factorisation and their part of the sweeps
+    // need no communication.  The heaviest candidates are split until there is one subtree per
+    // rank; the fronts that were split form the top of the tree.  A top front is owned by the
+    // owner of its heaviest child; update matrices / vectors of children owned elsewhere
+    // travel over NCCL (Plan::xfers).
     t0 = now_s();
+    const int P = std::max(1, opt.nranks);
+    plan.rank = opt.rank;
+    plan.nranks = P;
+    plan.owner.assign(nf, 0);
+    plan.is_top.assign(nf, 0);
+    std::vector<double> fl(nf, 0.0), flsub(nf, 0.0);
+    for (int t = 0; t < nf; t++) {
+        double s = plan.fronts[t].s, r = plan.fronts[t].r;
+        fl[t] = 2.0 / 3.0 * s * s * s + 2.0 * s * s * r + 2.0 * s * r * r;
+        flsub[t] += fl[t];
+        if (plan.fronts[t].parent >= 0) flsub[plan.fronts[t].parent] += flsub[t];
+    }
+    {
+        std::vector<int> cand(roots.begin(), roots.end());
+        while ((int)cand.size() < P) {
+            int best = -1;
+            for (size_t q = 0; q < cand.size(); q++)
+                if (!nodes[cand[q]].children.empty() && (best < 0 || flsub[cand[q]] > flsub[cand[best]])) best = (int)q;
+            if (best < 0) break;
+            int t = cand[best];
+            plan.is_top[t] = 1;
+            cand.erase(cand.begin() + best);
+            for (int c : nodes[t].children) cand.push_back(c);
+        }
+        // longest-processing-time assignment of the subtrees to ranks
+        std::sort(cand.begin(), cand.end(), [&](int x, int y) { return flsub[x] > flsub[y] || (flsub[x] == flsub[y] && x < y); });
+        std::vector<double> load(P, 0.0);
+        std::vector<int> cand_owner(nf, -1);
+        for (int t : cand) {
+            int r = (int)(std::min_element(load.begin(), load.end()) - load.begin());
+            cand_owner[t] = r;
+            load[r] += flsub[t];
+        }
+        plan.subtree_roots = cand;
+        std::sort(plan.subtree_roots.begin(), plan.subtree_roots.end());
+        // owners: subtree members inherit top-down, top fronts take the owner of their heaviest child
+        for (int t = nf - 1; t >= 0; t--) {
+            if (plan.is_top[t]) continue;
+            if (cand_owner[t] >= 0) plan.owner[t] = cand_owner[t];
+            else plan.owner[t] = plan.owner[plan.fronts[t].parent];
+        }
+        for (int t = 0; t < nf; t++) {
+            if (!plan.is_top[t]) continue;
+            int best = -1;
+            for (int c : nodes[t].children)
+                if (best < 0 || flsub[c] > flsub[best]) best = c;
+            plan.owner[t] = plan.owner[best];
+        }
+        // first permuted index of every subtree (postorder => contiguous ranges)
+        std::vector<int> lo(nf);
+        for (int t = 0; t < nf; t++) {
+            lo[t] = plan.fronts[t].first;
+            for (int c : nodes[t].children) lo[t] = std::min(lo[t], lo[c]);
+        }
+        plan.subtree_lo.clear();
+        for (int t : plan.subtree_roots) plan.subtree_lo.push_back(lo[t]);
+    }
+    auto mine = [&](int t) { return plan.owner[t] == plan.rank; };
+    auto ghost = [&](int t) {
+        return !mine(t) && plan.fronts[t].parent >= 0 && mine(plan.fronts[t].parent);
+    };
+
+    // ---- memory plan (this rank's fronts only) ---------------------------------------------------
     const int64_t AL = 16;  // 128-byte alignment in doubles
     int64_t off = 0;
     double flops = 0;
     int64_t nnz_lu = 0;
     for (int t = 0; t < nf; t++) {
         Front& f = plan.fronts[t];
+        flops += fl[t];
+        nnz_lu += (int64_t)f.s * f.s + 2 * (int64_t)f.s * f.r;
+        if (!mine(t)) {
+            f.Loff = f.UToff = -1;
+            continue;
+        }
+        plan.flops_local += fl[t];
+        plan.nnz_lu_local += (int64_t)f.s * f.s + 2 * (int64_t)f.s * f.r;
         f.Loff = off;
         off = align_up(off + (int64_t)f.m * f.s, AL);
         f.UToff = off;
         off = align_up(off + (int64_t)f.m * f.s, AL);
-        double s = f.s, r = f.r;
-        flops += 2.0 / 3.0 * s * s * s + 2.0 * s * s * r + 2.0 * s * r * r;
-        nnz_lu += (int64_t)f.s * f.s + 2 * (int64_t)f.s * f.r;
     }
     plan.factor_len = off;
     plan.flops = flops;
@@ -462,14 +535,29 @@ int analyse(int n, const int* rowptr, const int* colind, const int* const coords
 
     plan.levels.assign(plan.nlevels, LevelPlan());
     for (int l = 0; l < plan.nlevels; l++) plan.levels[l].level = l;
-    for (int t = 0; t < nf; t++) plan.levels[plan.fronts[t].level].fronts.push_back(t);
-    // update-matrix pools: level l uses pool l & 1
+    for (int t = 0; t < nf; t++) {
+        LevelPlan& L = plan.levels[plan.fronts[t].level];
+        L.fronts.push_back(t);
+        if (mine(t)) L.mine.push_back(t);
+        else if (ghost(t)) L.ghosts.push_back(t);
+        if (plan.is_top[t]) L.tops.push_back(t);
+        int pa = plan.fronts[t].parent;
+        if (pa >= 0 && plan.owner[pa] != plan.owner[t]) {
+            L.xfers.push_back((int)plan.xfers.size());
+            plan.xfers.push_back(Xfer{t, plan.owner[t], plan.owner[pa], plan.fronts[t].level});
+        }
+    }
+    // update-matrix pools: level l uses pool l & 1 (own fronts and ghost children)
     {
         int64_t len[2] = {0, 0};
         for (int l = 0; l < plan.nlevels; l++) {
             int64_t o = 0;
             for (int t : plan.levels[l].fronts) {
                 Front& f = plan.fronts[t];
+                if (!mine(t) && !ghost(t)) {
+                    f.F22off = -1;
+                    continue;
+                }
                 f.F22off = o;  // relative to the pool start, fixed up below
                 o = align_up(o + (int64_t)f.r * f.r, AL);
             }
@@ -483,13 +571,18 @@ int analyse(int n, const int* rowptr, const int* colind, const int* const coords
         plan.heap_len = plan.factor_len + len[0] + len[1];
         for (int l = 0; l < plan.nlevels; l++) {
             plan.levels[l].f22_zero_off = plan.pool_off[l & 1];
-            for (int t : plan.levels[l].fronts) plan.fronts[t].F22off += plan.pool_off[l & 1];
+            for (int t : plan.levels[l].fronts)
+                if (plan.fronts[t].F22off >= 0) plan.fronts[t].F22off += plan.pool_off[l & 1];
         }
     }
-    // solve work vectors
+    // solve work vectors (own fronts and ghost children)
     {
         int64_t o = 0;
         for (int t = 0; t < nf; t++) {
+            if (!mine(t) && !ghost(t)) {
+                plan.fronts[t].woff = -1;
+                continue;
+            }
             plan.fronts[t].woff = o;
             o += plan.fronts[t].m;
         }
@@ -509,6 +602,10 @@ int analyse(int n, const int* rowptr, const int* colind, const int* const coords
                 int pj = plan.perm[colind[p]];
                 int t = front_of[std::min(pi, pj)];
                 const Front& f = plan.fronts[t];
+                if (!mine(t)) {
+                    plan.scatter[p] = -1;
+                    continue;
+                }
                 auto local = [&](int x) -> int {
                     if (x < f.first + f.s) return x - f.first;
                     const int* b = plan.bidx.data() + f.bidx_off;
@@ -528,12 +625,12 @@ int analyse(int n, const int* rowptr, const int* colind, const int* const coords
     for (int l = plan.nlevels - 1; l >= 0; l--) {
         LevelPlan& L = plan.levels[l];
         int maxs = 0;
-        for (int t : L.fronts) maxs = std::max(maxs, plan.fronts[t].s);
+        for (int t : L.mine) maxs = std::max(maxs, plan.fronts[t].s);
         L.nsteps = (maxs + nb - 1) / nb;
 
         // extend-add passes: children (level l+1) grouped by child_rank
         int npass = 0;
-        for (int t : L.fronts) npass = std::max(npass, plan.fronts[t].nchild);
+        for (int t : L.mine) npass = std::max(npass, plan.fronts[t].nchild);
         L.add_begin.assign(npass + 1, 0);
         L.add_tiles.assign(npass, 0);
         if (l + 1 < plan.nlevels) {
@@ -542,7 +639,7 @@ int analyse(int n, const int* rowptr, const int* colind, const int* const coords
                 int tile0 = 0;
                 for (int c : plan.levels[l + 1].fronts) {
                     const Front& fc = plan.fronts[c];
-                    if (fc.child_rank != pass || fc.r == 0) continue;
+                    if (fc.child_rank != pass || fc.r == 0 || !mine(fc.parent)) continue;
                     const Front& fp = plan.fronts[fc.parent];
                     AddTask a;
                     a.Coff = fc.F22off;
@@ -575,7 +672,7 @@ int analyse(int n, const int* rowptr, const int* colind, const int* const coords
             L.gemm_begin[step] = (int)plan.gemm_tasks.size();
             int cta0 = 0, tile0 = 0;
             int k0 = step * nb;
-            for (int t : L.fronts) {
+            for (int t : L.mine) {
                 const Front& f = plan.fronts[t];
                 if (k0 >= f.s) continue;
                 int kb = std::min(nb, f.s - k0);
@@ -678,7 +775,7 @@ int analyse(int n, const int* rowptr, const int* colind, const int* const coords
     for (int l = plan.nlevels - 1; l >= 0; l--) {
         LevelPlan& L = plan.levels[l];
         L.solve_begin = (int)plan.solve_tasks.size();
-        for (int t : L.fronts) {
+        for (int t : L.mine) {
             const Front& f = plan.fronts[t];
             SolveTask st;
             st.Loff = f.Loff;

@@ -122,8 +122,10 @@ __global__ void k_scatter(int64_t nnz, const double* __restrict__ val, const int
                           double* __restrict__ heap) {
     int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= nnz) return;
+    const int64_t d = dst[p];
+    if (d < 0) return;   // entry of a front owned by another GPU
     double v = val[p] * R[rowidx[p]] * C[colind[p]];
-    atomicAdd(&heap[dst[p]], v);   // duplicates in the CRS (if any) are summed, as sum_dup_vals would
+    atomicAdd(&heap[d], v);   // duplicates in the CRS (if any) are summed, as sum_dup_vals would
 }
 
 // ------------------------------------------------------------------------------------------

@@ -123,9 +123,21 @@ struct BigItem {
     int idx;     // row slab (forward) or pivot panel (backward)
 };
 
+// multi-GPU: the update matrix (factorisation) / update vector (forward sweep) of `front`
+// travels from the owner of the front to the owner of its parent
+struct Xfer {
+    int front;
+    int src, dst;
+    int level;   // level of `front` (the child)
+};
+
 struct LevelPlan {
     int level = 0;
-    std::vector<int> fronts;             // fronts on this level
+    std::vector<int> fronts;             // fronts on this level (all ranks)
+    std::vector<int> mine;               // ... owned by this rank
+    std::vector<int> ghosts;             // ... not owned, but children of fronts owned by this rank
+    std::vector<int> xfers;              // indices into Plan::xfers whose child lives on this level
+    std::vector<int> tops;               // top fronts (shared part of the tree) on this level
     int nsteps = 0;                      // ceil(max s / nb)
     // per step task ranges into the flat arrays below
     std::vector<int> diag_begin, trsm_begin, gemm_begin;  // size nsteps+1
@@ -151,6 +163,7 @@ struct Options {
     int period_i = 0;
     int verbose = 0;
     int64_t big_entries = 1 << 16;  // fronts with m*s >= this use the multi-CTA dataflow sweeps
+    int rank = 0, nranks = 1;       // multi-GPU: this process' rank (one GPU per rank)
 };
 
 struct Plan {
@@ -186,6 +199,15 @@ struct Plan {
     int64_t nnz_lu = 0;        // stored factor entries incl. diagonal
     int max_front = 0;
     double t_order = 0, t_symbolic = 0, t_plan = 0;
+    // multi-GPU partition (identical on every rank)
+    int rank = 0, nranks = 1;
+    std::vector<int> owner;          // per front
+    std::vector<char> is_top;        // per front: part of the shared top of the tree
+    std::vector<int> subtree_roots;  // roots of the rank-private subtrees
+    std::vector<int> subtree_lo;     // per subtree root: first permuted index of the subtree
+    std::vector<Xfer> xfers;         // every parent/child pair with different owners
+    double flops_local = 0;          // factor flops of the fronts owned by this rank
+    int64_t nnz_lu_local = 0;
 };
 
 // analysis.cpp

@@ -8,6 +8,7 @@
 //
 // There is no CPU fallback: every failure of a CUDA call is reported as NKP_ECUDA.
 #include <cuda_runtime.h>
+#include <nccl.h>
 
 #include <chrono>
 #include <cmath>
@@ -31,6 +32,17 @@ static thread_local std::string g_err;
         if (e_ != cudaSuccess) {                                                                   \
             char b_[512];                                                                          \
             snprintf(b_, sizeof b_, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            g_err = b_;                                                                            \
+            return NKP_ECUDA;                                                                      \
+        }                                                                                          \
+    } while (0)
+
+#define CKN(call)                                                                                  \
+    do {                                                                                           \
+        ncclResult_t e_ = (call);                                                                  \
+        if (e_ != ncclSuccess) {                                                                   \
+            char b_[512];                                                                          \
+            snprintf(b_, sizeof b_, "%s failed: %s (%s:%d)", #call, ncclGetErrorString(e_), __FILE__, __LINE__); \
             g_err = b_;                                                                            \
             return NKP_ECUDA;                                                                      \
         }                                                                                          \
@@ -70,6 +82,8 @@ struct nkp_solver {
     int* d_flags = nullptr;     // [0, nflags): forward, [nflags, 2 nflags): backward
     int epoch = 0;
     int coop_ctas = 0;          // co-resident CTAs for the dataflow sweeps
+    ncclComm_t comm = nullptr;  // multi-GPU only
+    int rank = 0, nranks = 1;
     double* d_W = nullptr;      // solve work vectors, MAX_NR columns
     double* d_y = nullptr;      // n x MAX_NR permuted rhs / solution
     double* d_r = nullptr;      // n x MAX_NR residual
@@ -147,9 +161,11 @@ void nkp_default_options(nkp_options* o) {
     if ((e = getenv("NKP_EQUIL"))) o->equil = atoi(e);
 }
 
-int nkp_create(nkp_solver** out, int n, const int* rowptr, const int* colind, const int* ci,
-               const int* cj, const int* ck, const nkp_options* opt_in) {
-    if (!out || n <= 0 || !rowptr || !colind) {
+static int create_impl(nkp_solver** out, int n, const int* rowptr, const int* colind, const int* ci,
+                       const int* cj, const int* ck, const nkp_options* opt_in, int rank, int nranks,
+                       const void* unique_id) {
+    if (!out || n <= 0 || !rowptr || !colind || rank < 0 || nranks < 1 || rank >= nranks ||
+        (nranks > 1 && !unique_id)) {
         g_err = "nkp_create: invalid argument";
         return NKP_EINVAL;
     }
@@ -179,7 +195,11 @@ int nkp_create(nkp_solver** out, int n, const int* rowptr, const int* colind, co
     po.tn = G_TN;
     po.trsm_rows = TRSM_ROWS;
     po.add_tile = ADD_TILE;
-    po.verbose = o.verbose;
+    po.verbose = (rank == 0) ? o.verbose : 0;
+    po.rank = rank;
+    po.nranks = nranks;
+    s->rank = rank;
+    s->nranks = nranks;
     if (getenv("NKP_BIG_ENTRIES")) po.big_entries = atoll(getenv("NKP_BIG_ENTRIES"));
     if (getenv("NKP_OUTER")) po.outer = std::max(1, atoi(getenv("NKP_OUTER")));
     const int* coords[3] = {ci, cj, ck};
@@ -205,6 +225,12 @@ int nkp_create(nkp_solver** out, int n, const int* rowptr, const int* colind, co
     auto body = [&]() -> int {
         CK(cudaStreamCreate(&s->stream));
         for (int i = 0; i < 4; i++) CK(cudaEventCreate(&s->ev[i]));
+        if (nranks > 1) {
+            ncclUniqueId id;
+            static_assert(sizeof(ncclUniqueId) <= NKP_UNIQUE_ID_BYTES, "unique id size");
+            memcpy(&id, unique_id, sizeof(id));
+            CKN(ncclCommInitRank(&s->comm, nranks, id, rank));
+        }
         CK(cudaMalloc((void**)&s->heap, sizeof(double) * (size_t)std::max<int64_t>(P.heap_len, 1)));
         std::vector<int> rp(rowptr, rowptr + n + 1), cidx(colind, colind + s->nnz), ridx((size_t)s->nnz);
         for (int i = 0; i < n; i++)
@@ -269,6 +295,47 @@ int nkp_create(nkp_solver** out, int n, const int* rowptr, const int* colind, co
     return NKP_OK;
 }
 
+int nkp_create(nkp_solver** out, int n, const int* rowptr, const int* colind, const int* ci,
+               const int* cj, const int* ck, const nkp_options* opt_in) {
+    return create_impl(out, n, rowptr, colind, ci, cj, ck, opt_in, 0, 1, nullptr);
+}
+
+int nkp_create_dist(nkp_solver** out, int n, const int* rowptr, const int* colind, const int* ci,
+                    const int* cj, const int* ck, const nkp_options* opt_in, int rank, int nranks,
+                    const void* unique_id) {
+    return create_impl(out, n, rowptr, colind, ci, cj, ck, opt_in, rank, nranks, unique_id);
+}
+
+int nkp_comm_unique_id(void* unique_id) {
+    if (!unique_id) return NKP_EINVAL;
+    ncclUniqueId id;
+    CKN(ncclGetUniqueId(&id));
+    memset(unique_id, 0, NKP_UNIQUE_ID_BYTES);
+    memcpy(unique_id, &id, sizeof(id));
+    return NKP_OK;
+}
+
+// update matrices of the children on level `child_level` that live on another GPU than their parent
+static int exchange_updates(nkp_solver* s, int child_level) {
+    Plan& P = s->plan;
+    if (s->nranks == 1 || child_level >= P.nlevels) return 0;
+    const LevelPlan& L = P.levels[child_level];
+    bool any = false;
+    for (int q : L.xfers) any = any || P.xfers[q].src == s->rank || P.xfers[q].dst == s->rank;
+    if (!any) return 0;
+    CKN(ncclGroupStart());
+    for (int q : L.xfers) {
+        const Xfer& x = P.xfers[q];
+        const Front& f = P.fronts[x.front];
+        size_t cnt = (size_t)f.r * f.r;
+        if (cnt == 0) continue;
+        if (x.src == s->rank) CKN(ncclSend(s->heap + f.F22off, cnt, ncclDouble, x.dst, s->comm, s->stream));
+        if (x.dst == s->rank) CKN(ncclRecv(s->heap + f.F22off, cnt, ncclDouble, x.src, s->comm, s->stream));
+    }
+    CKN(ncclGroupEnd());
+    return 0;
+}
+
 static int do_factor(nkp_solver* s) {
     Plan& P = s->plan;
     cudaStream_t st = s->stream;
@@ -305,6 +372,7 @@ static int do_factor(nkp_solver* s) {
             CK(cudaMemsetAsync(s->heap + L.f22_zero_off, 0, sizeof(double) * (size_t)L.f22_zero_len, st));
             prof_mark(s, KC_OTHER);
         }
+        if (exchange_updates(s, l + 1)) return NKP_ECUDA;
         int npass = (int)L.add_tiles.size();
         for (int pass = 0; pass < npass; pass++) {
             int nt = L.add_begin[pass + 1] - L.add_begin[pass];
@@ -407,6 +475,24 @@ static int sweeps(nkp_solver* s) {
     const double* heap = s->heap;
     for (int l = P.nlevels - 1; l >= 0; l--) {
         const LevelPlan& L = P.levels[l];
+        if (s->nranks > 1 && l + 1 < P.nlevels) {
+            // update vectors of children that live on another GPU (whole work vector: m x NR)
+            const LevelPlan& Lc = P.levels[l + 1];
+            bool any = false;
+            for (int q : Lc.xfers) any = any || P.xfers[q].src == s->rank || P.xfers[q].dst == s->rank;
+            if (any) {
+                CKN(ncclGroupStart());
+                for (int q : Lc.xfers) {
+                    const Xfer& x = P.xfers[q];
+                    const Front& f = P.fronts[x.front];
+                    size_t cnt = (size_t)f.m * NR;
+                    if (x.src == s->rank) CKN(ncclSend(s->d_W + f.woff * NR, cnt, ncclDouble, x.dst, s->comm, st));
+                    if (x.dst == s->rank) CKN(ncclRecv(s->d_W + f.woff * NR, cnt, ncclDouble, x.src, s->comm, st));
+                }
+                CKN(ncclGroupEnd());
+                mark("fwd xfer", l, (int)Lc.xfers.size());
+            }
+        }
         int nsmall = L.small_end - L.small_begin;
         if (nsmall > 0) {
             k_fwd<NR><<<nsmall, SOLVE_THREADS, 0, st>>>(s->d_small + L.small_begin, s->d_children, s->d_rel, s->heap,
@@ -452,6 +538,33 @@ static int sweeps(nkp_solver* s) {
             s->launches++;
             mark("bwd big", l, nitems);
         }
+        if (s->nranks > 1 && !L.tops.empty()) {
+            // separator solutions of the shared top of the tree go to every GPU
+            CKN(ncclGroupStart());
+            for (int t : L.tops) {
+                const Front& f = P.fronts[t];
+                for (int c = 0; c < NR; c++) {
+                    double* p = s->d_y + f.first + (size_t)c * n;
+                    CKN(ncclBroadcast(p, p, (size_t)f.s, ncclDouble, P.owner[t], s->comm, st));
+                }
+            }
+            CKN(ncclGroupEnd());
+            mark("bwd bcast", l, (int)L.tops.size());
+        }
+    }
+    if (s->nranks > 1) {
+        // every rank-private subtree range is published by its owner: all ranks hold the full solution
+        CKN(ncclGroupStart());
+        for (size_t q = 0; q < P.subtree_roots.size(); q++) {
+            int t = P.subtree_roots[q];
+            int lo = P.subtree_lo[q], hi = P.fronts[t].first + P.fronts[t].s;
+            for (int c = 0; c < NR; c++) {
+                double* p = s->d_y + lo + (size_t)c * n;
+                CKN(ncclBroadcast(p, p, (size_t)(hi - lo), ncclDouble, P.owner[t], s->comm, st));
+            }
+        }
+        CKN(ncclGroupEnd());
+        mark("subtree bcast", -1, (int)P.subtree_roots.size());
     }
     CK(cudaGetLastError());
     if (trace) {
@@ -658,6 +771,9 @@ int nkp_get_stats(const nkp_solver* s, nkp_stats* st) {
     st->t_diag = s->t_cls[KC_DIAG];
     st->t_extend_add = s->t_cls[KC_ADD];
     st->t_sweeps = s->t_sweeps;
+    st->factor_flops_local = P.flops_local;
+    st->nnz_lu_local = (double)P.nnz_lu_local;
+    st->n_xfers = (double)P.xfers.size();
     return NKP_OK;
 }
 
@@ -677,6 +793,7 @@ void nkp_destroy(nkp_solver* s) {
     if (!s) return;
     cudaSetDevice(s->opt.device);
     if (s->stream) cudaStreamSynchronize(s->stream);
+    if (s->comm) ncclCommDestroy(s->comm);
     void* ptrs[] = {s->heap,   s->d_rowptr, s->d_colind, s->d_rowidx, s->d_val,  s->d_scatter, s->d_perm,
                     s->d_bidx, s->d_rel,    s->d_R,      s->d_C,      s->d_diag, s->d_trsm,    s->d_gemm,
                     s->d_add,  s->d_solve,  s->d_children, s->d_W,    s->d_y,    s->d_r,       s->d_x,

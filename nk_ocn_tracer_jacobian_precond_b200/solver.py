@@ -31,7 +31,8 @@ class NkpStats(C.Structure):
                 ("tiny_pivots", C.c_int), ("kernel_launches", C.c_int64), ("solve_bytes", C.c_double),
                 ("t_gemm", C.c_double), ("gemm_flops", C.c_double), ("n_gemm", C.c_int64),
                 ("t_trsm", C.c_double), ("t_diag", C.c_double), ("t_extend_add", C.c_double),
-                ("t_sweeps", C.c_double), ("reserved", C.c_double * 8)]
+                ("t_sweeps", C.c_double), ("factor_flops_local", C.c_double), ("nnz_lu_local", C.c_double),
+                ("n_xfers", C.c_double), ("reserved", C.c_double * 5)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
@@ -53,6 +54,9 @@ def load_library():
     lib.nkp_default_options.argtypes = [P(NkpOptions)]
     lib.nkp_default_options.restype = None
     lib.nkp_create.argtypes = [P(vp), C.c_int, P(C.c_int), P(C.c_int), P(C.c_int), P(C.c_int), P(C.c_int), P(NkpOptions)]
+    lib.nkp_create_dist.argtypes = [P(vp), C.c_int, P(C.c_int), P(C.c_int), P(C.c_int), P(C.c_int), P(C.c_int),
+                                    P(NkpOptions), C.c_int, C.c_int, C.c_char_p]
+    lib.nkp_comm_unique_id.argtypes = [C.c_char_p]
     lib.nkp_factor.argtypes = [vp, P(C.c_double)]
     lib.nkp_factor_device.argtypes = [vp, vp]
     lib.nkp_solve.argtypes = [vp, P(C.c_double), C.c_int, C.c_int, P(C.c_double)]
@@ -75,6 +79,16 @@ class NkpError(RuntimeError):
     pass
 
 
+UNIQUE_ID_BYTES = 128
+
+
+def comm_unique_id() -> bytes:
+    """NCCL unique id for nkp_create_dist (call on rank 0, ship to the other ranks)."""
+    buf = C.create_string_buffer(UNIQUE_ID_BYTES)
+    _check(load_library().nkp_comm_unique_id(buf), "nkp_comm_unique_id")
+    return buf.raw
+
+
 def _check(rc, what):
     if rc != 0:
         msg = load_library().nkp_last_error().decode()
@@ -92,7 +106,8 @@ class TracerJacobianSolver:
     src/matrix.c:322-329) enabling the geometric nested dissection.
     """
 
-    def __init__(self, n, rowptr, colind, coords=None, **opts):
+    def __init__(self, n, rowptr, colind, coords=None, comm=None, **opts):
+        """comm: None (one GPU) or (rank, nranks, unique_id_bytes) for one-process-per-GPU runs."""
         lib = load_library()
         self._lib = lib
         self.n = int(n)
@@ -107,8 +122,14 @@ class TracerJacobianSolver:
         if coords is not None:
             ci, cj, ck = (np.ascontiguousarray(c, dtype=np.int32) if c is not None else None for c in coords)
         self._h = C.c_void_p()
-        _check(lib.nkp_create(C.byref(self._h), self.n, _iptr(rowptr), _iptr(colind), _iptr(ci), _iptr(cj), _iptr(ck),
-                              C.byref(o)), "nkp_create")
+        if comm is None:
+            _check(lib.nkp_create(C.byref(self._h), self.n, _iptr(rowptr), _iptr(colind), _iptr(ci), _iptr(cj),
+                                  _iptr(ck), C.byref(o)), "nkp_create")
+        else:
+            rank, nranks, uid = comm
+            assert len(uid) == UNIQUE_ID_BYTES
+            _check(lib.nkp_create_dist(C.byref(self._h), self.n, _iptr(rowptr), _iptr(colind), _iptr(ci), _iptr(cj),
+                                       _iptr(ck), C.byref(o), int(rank), int(nranks), bytes(uid)), "nkp_create_dist")
 
     # -- numeric phase -------------------------------------------------------------------
     def factor(self, nzval):

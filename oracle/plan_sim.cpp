@@ -108,10 +108,15 @@ void sim_add(double* H, const AddTask& t, const int* rel, int nb) {
 
 extern "C" {
 
-// stats_out[0..7]: n_fronts, n_levels, max_front, nnz_lu, heap_len, flops, tiny_pivots, analysis seconds
-int nkp_sim_run(int n, const int* rowptr, const int* colind, const double* val, const int* ci,
-                const int* cj, const int* ck, int nb, int leaf, const double* B, int nrhs,
-                double* X, double* stats_out, int* perm_out, int analysis_only) {
+// Interprets the plans of `nranks` ranks in lockstep inside one process: every rank has its own
+// heap / work vectors; Plan::xfers and the top-front broadcasts are carried out as memcpys.
+// With nranks == 1 this is the plain single-GPU plan.  Returns the solution seen by rank 0.
+// stats_out[0..7]: n_fronts, n_levels, max_front, nnz_lu, heap_len(rank 0), flops, tiny_pivots, analysis seconds
+// part_out (may be null, 4 ints per rank): fronts owned, xfers as src, xfers as dst, local flops / 1e6
+int nkp_sim_run_dist(int n, const int* rowptr, const int* colind, const double* val, const int* ci,
+                     const int* cj, const int* ck, int nb, int leaf, const double* B, int nrhs,
+                     double* X, double* stats_out, int* perm_out, int analysis_only, int nranks,
+                     double* part_out) {
     Options opt;
     opt.nb = nb;
     opt.leaf = leaf;
@@ -120,63 +125,96 @@ int nkp_sim_run(int n, const int* rowptr, const int* colind, const double* val, 
     if (getenv("NKP_SIM_TM")) opt.tm = atoi(getenv("NKP_SIM_TM"));
     if (getenv("NKP_SIM_TN")) opt.tn = atoi(getenv("NKP_SIM_TN"));
     opt.verbose = getenv("NKP_SIM_VERBOSE") ? 1 : 0;
+    opt.nranks = nranks;
     const int* coords[3] = {ci, cj, ck};
-    Plan P;
-    int rc = analyse(n, rowptr, colind, (ci || cj || ck) ? coords : nullptr, opt, P);
-    if (rc) return rc;
-    if (stats_out) {
-        stats_out[0] = (double)P.fronts.size();
-        stats_out[1] = P.nlevels;
-        stats_out[2] = P.max_front;
-        stats_out[3] = (double)P.nnz_lu;
-        stats_out[4] = (double)P.heap_len;
-        stats_out[5] = P.flops;
-        stats_out[7] = P.t_order + P.t_symbolic + P.t_plan;
+    std::vector<Plan> plans(nranks);
+    for (int r = 0; r < nranks; r++) {
+        opt.rank = r;
+        int rc = analyse(n, rowptr, colind, (ci || cj || ck) ? coords : nullptr, opt, plans[r]);
+        if (rc) return rc;
     }
-    if (perm_out) memcpy(perm_out, P.perm.data(), sizeof(int) * n);
+    Plan& P0 = plans[0];
+    if (stats_out) {
+        stats_out[0] = (double)P0.fronts.size();
+        stats_out[1] = P0.nlevels;
+        stats_out[2] = P0.max_front;
+        stats_out[3] = (double)P0.nnz_lu;
+        stats_out[4] = (double)P0.heap_len;
+        stats_out[5] = P0.flops;
+        stats_out[7] = P0.t_order + P0.t_symbolic + P0.t_plan;
+    }
+    if (perm_out) memcpy(perm_out, P0.perm.data(), sizeof(int) * n);
+    if (part_out)
+        for (int r = 0; r < nranks; r++) {
+            int owned = 0, as_src = 0, as_dst = 0;
+            for (int o : plans[r].owner) owned += (o == r);
+            for (const Xfer& x : plans[r].xfers) as_src += (x.src == r), as_dst += (x.dst == r);
+            part_out[4 * r + 0] = owned;
+            part_out[4 * r + 1] = as_src;
+            part_out[4 * r + 2] = as_dst;
+            part_out[4 * r + 3] = plans[r].flops_local;
+        }
+    // the partition must be identical on all ranks
+    for (int r = 1; r < nranks; r++) {
+        if (plans[r].owner != P0.owner || plans[r].xfers.size() != P0.xfers.size()) return -20;
+        for (size_t q = 0; q < P0.xfers.size(); q++)
+            if (plans[r].xfers[q].front != P0.xfers[q].front || plans[r].xfers[q].src != P0.xfers[q].src ||
+                plans[r].xfers[q].dst != P0.xfers[q].dst)
+                return -21;
+    }
     if (analysis_only) return 0;
 
-    std::vector<double> heap((size_t)P.heap_len, 0.0);
-    double* H = heap.data();
     double amax = 0;
-    for (int64_t p = 0; p < P.nnz; p++) amax = std::max(amax, std::fabs(val[p]));
+    for (int64_t p = 0; p < P0.nnz; p++) amax = std::max(amax, std::fabs(val[p]));
     double tiny = std::sqrt(2.220446049250313e-16) * amax;
-    for (int64_t p = 0; p < P.nnz; p++) H[P.scatter[p]] += val[p];
+    std::vector<std::vector<double>> heaps(nranks);
+    for (int r = 0; r < nranks; r++) {
+        heaps[r].assign((size_t)plans[r].heap_len, 0.0);
+        for (int64_t p = 0; p < plans[r].nnz; p++)
+            if (plans[r].scatter[p] >= 0) heaps[r][plans[r].scatter[p]] += val[p];
+    }
 
     int nrepl = 0;
-    for (int l = P.nlevels - 1; l >= 0; l--) {
-        const LevelPlan& L = P.levels[l];
-        memset(H + L.f22_zero_off, 0, sizeof(double) * (size_t)L.f22_zero_len);
-        int npass = (int)L.add_tiles.size();
-        for (int pass = 0; pass < npass; pass++) {
-#pragma omp parallel for schedule(dynamic)
-            for (int q = L.add_begin[pass]; q < L.add_begin[pass + 1]; q++) sim_add(H, P.add_tasks[q], P.rel.data(), nb);
+    for (int l = P0.nlevels - 1; l >= 0; l--) {
+        for (int r = 0; r < nranks; r++) {
+            const LevelPlan& L = plans[r].levels[l];
+            memset(heaps[r].data() + L.f22_zero_off, 0, sizeof(double) * (size_t)L.f22_zero_len);
         }
-        for (int step = 0; step < L.nsteps; step++) {
-#pragma omp parallel for schedule(dynamic) reduction(+ : nrepl)
-            for (int q = L.diag_begin[step]; q < L.diag_begin[step + 1]; q++) sim_diag(H, P.diag_tasks[q], tiny, &nrepl);
-            if (getenv("NKP_SIM_POISON")) {
-                for (int q = L.diag_begin[step]; q < L.diag_begin[step + 1]; q++) {
-                    const DiagTask& d = P.diag_tasks[q];
-                    for (int a = 0; a < d.kb; a++) for (int b = 0; b < d.kb; b++)
-                        if (std::isnan(H[d.Doff + a + (int64_t)b * d.ld])) { fprintf(stderr, "NaN in diag block level %d step %d task %d (%d,%d) kb=%d ld=%d\n", l, step, q - L.diag_begin[step], a, b, d.kb, d.ld); a = b = 1 << 20; }
-                }
-                for (int q = L.trsm_begin[step]; q < L.trsm_begin[step + 1]; q++) {
-                    const TrsmTask& d = P.trsm_tasks[q];
-                    for (int a = 0; a < d.nrows; a++) for (int b = 0; b < d.kb; b++)
-                        if (std::isnan(H[d.Xoff + a + (int64_t)b * d.ld])) { fprintf(stderr, "NaN in trsm X level %d step %d unit %d (%d,%d) nrows=%d kb=%d ld=%d\n", l, step, d.unit, a, b, d.nrows, d.kb, d.ld); a = b = 1 << 20; }
-                }
+        // update matrices of children (level l+1) owned elsewhere: src -> dst
+        if (l + 1 < P0.nlevels)
+            for (int q : P0.levels[l + 1].xfers) {
+                const Xfer& x = P0.xfers[q];
+                const Front& fs = plans[x.src].fronts[x.front];
+                const Front& fd = plans[x.dst].fronts[x.front];
+                if (fs.F22off < 0 || fd.F22off < 0) return -22;
+                memcpy(heaps[x.dst].data() + fd.F22off, heaps[x.src].data() + fs.F22off, sizeof(double) * (size_t)fs.r * fs.r);
             }
-            for (int q = L.trsm_begin[step]; q < L.trsm_begin[step + 1]; q++) sim_trsm(H, P.trsm_tasks[q]);
-            for (int q = L.gemm_begin[step]; q < L.gemm_begin[step + 1]; q++) sim_gemm(H, P.gemm_tasks[q], opt);
+        for (int r = 0; r < nranks; r++) {
+            Plan& P = plans[r];
+            double* H = heaps[r].data();
+            const LevelPlan& L = P.levels[l];
+            int npass = (int)L.add_tiles.size();
+            for (int pass = 0; pass < npass; pass++) {
+#pragma omp parallel for schedule(dynamic)
+                for (int q = L.add_begin[pass]; q < L.add_begin[pass + 1]; q++) sim_add(H, P.add_tasks[q], P.rel.data(), nb);
+            }
+            for (int step = 0; step < L.nsteps; step++) {
+#pragma omp parallel for schedule(dynamic) reduction(+ : nrepl)
+                for (int q = L.diag_begin[step]; q < L.diag_begin[step + 1]; q++) sim_diag(H, P.diag_tasks[q], tiny, &nrepl);
+                for (int q = L.trsm_begin[step]; q < L.trsm_begin[step + 1]; q++) sim_trsm(H, P.trsm_tasks[q]);
+                for (int q = L.gemm_begin[step]; q < L.gemm_begin[step + 1]; q++) sim_gemm(H, P.gemm_tasks[q], P.opt);
+            }
         }
     }
     if (stats_out) stats_out[6] = nrepl;
     if (nrhs <= 0) return 0;
 
-    // ---- solves: y = permuted rhs; forward deepest -> root, backward root -> deepest --------
-    std::vector<double> W((size_t)P.solve_pool_len);
-    std::vector<double> y(n);
+    // ---- solves: y = permuted rhs (replicated); forward deepest -> root, backward root -> deepest
+    std::vector<std::vector<double>> Ws(nranks), ys(nranks);
+    for (int r = 0; r < nranks; r++) {
+        Ws[r].assign((size_t)plans[r].solve_pool_len, 0.0);
+        ys[r].assign(n, 0.0);
+    }
     int nref = getenv("NKP_SIM_REFINE") ? atoi(getenv("NKP_SIM_REFINE")) : 0;
     std::vector<double> rhs(n), xacc(n);
     for (int c = 0; c < nrhs; c++)
@@ -196,51 +234,129 @@ int nkp_sim_run(int n, const int* rowptr, const int* colind, const double* val, 
             }
             fprintf(stderr, "[sim] rhs %d refine it %d: relres before = %.3e\n", c, it, std::sqrt(rn / bn));
         }
-        for (int i = 0; i < n; i++) y[P.perm[i]] = rhs[i];
-        for (int l = P.nlevels - 1; l >= 0; l--) {
-            const LevelPlan& L = P.levels[l];
+        for (int r = 0; r < nranks; r++)
+            for (int i = 0; i < n; i++) ys[r][P0.perm[i]] = rhs[i];
+        for (int l = P0.nlevels - 1; l >= 0; l--) {
+            // update vectors of children owned elsewhere
+            if (l + 1 < P0.nlevels)
+                for (int q : P0.levels[l + 1].xfers) {
+                    const Xfer& x = P0.xfers[q];
+                    const Front& fs = plans[x.src].fronts[x.front];
+                    const Front& fd = plans[x.dst].fronts[x.front];
+                    if (fs.woff < 0 || fd.woff < 0) return -23;
+                    memcpy(Ws[x.dst].data() + fd.woff, Ws[x.src].data() + fs.woff, sizeof(double) * (size_t)fs.m);
+                }
+            for (int r = 0; r < nranks; r++) {
+                Plan& P = plans[r];
+                const double* H = heaps[r].data();
+                std::vector<double>& W = Ws[r];
+                std::vector<double>& y = ys[r];
+                const LevelPlan& L = P.levels[l];
 #pragma omp parallel for schedule(dynamic)
-            for (int q = L.solve_begin; q < L.solve_end; q++) {
-                const SolveTask& t = P.solve_tasks[q];
-                double* w = W.data() + t.woff;
-                for (int a = 0; a < t.s; a++) w[a] = y[t.first + a];
-                for (int a = t.s; a < t.m; a++) w[a] = 0;
-                for (int c2 = 0; c2 < t.nchild; c2++) {
-                    const SolveChild& sc = P.solve_children[t.child_list + c2];
-                    const double* wc = W.data() + sc.woff + sc.s;
-                    const int* rl = P.rel.data() + sc.rel_off;
-                    for (int a = 0; a < sc.r; a++) w[rl[a]] += wc[a];
+                for (int q = L.solve_begin; q < L.solve_end; q++) {
+                    const SolveTask& t = P.solve_tasks[q];
+                    double* w = W.data() + t.woff;
+                    for (int a = 0; a < t.s; a++) w[a] = y[t.first + a];
+                    for (int a = t.s; a < t.m; a++) w[a] = 0;
+                    for (int c2 = 0; c2 < t.nchild; c2++) {
+                        const SolveChild& sc = P.solve_children[t.child_list + c2];
+                        const double* wc = W.data() + sc.woff + sc.s;
+                        const int* rl = P.rel.data() + sc.rel_off;
+                        for (int a = 0; a < sc.r; a++) w[rl[a]] += wc[a];
+                    }
+                    const double* Lr = H + t.Loff;
+                    for (int p = 0; p < t.s; p++) {
+                        double yp = w[p];
+                        for (int a = p + 1; a < t.m; a++) w[a] -= Lr[a + (int64_t)p * t.m] * yp;
+                    }
+                    for (int a = 0; a < t.s; a++) y[t.first + a] = w[a];
                 }
-                const double* Lr = H + t.Loff;
-                for (int p = 0; p < t.s; p++) {
-                    double yp = w[p];
-                    for (int a = p + 1; a < t.m; a++) w[a] -= Lr[a + (int64_t)p * t.m] * yp;
-                }
-                for (int a = 0; a < t.s; a++) y[t.first + a] = w[a];
             }
         }
-        for (int l = 0; l < P.nlevels; l++) {
-            const LevelPlan& L = P.levels[l];
+        for (int l = 0; l < P0.nlevels; l++) {
+            for (int r = 0; r < nranks; r++) {
+                Plan& P = plans[r];
+                const double* H = heaps[r].data();
+                std::vector<double>& W = Ws[r];
+                std::vector<double>& y = ys[r];
+                const LevelPlan& L = P.levels[l];
 #pragma omp parallel for schedule(dynamic)
-            for (int q = L.solve_begin; q < L.solve_end; q++) {
-                const SolveTask& t = P.solve_tasks[q];
-                double* w = W.data() + t.woff;
-                const int* bi = P.bidx.data() + t.bidx_off;
-                for (int a = 0; a < t.r; a++) w[t.s + a] = y[bi[a]];
-                const double* UT = H + t.UToff;
-                for (int p = t.s - 1; p >= 0; p--) {
-                    double z = y[t.first + p];
-                    for (int a = p + 1; a < t.m; a++) z -= UT[a + (int64_t)p * t.m] * w[a];
-                    w[p] = z / UT[p + (int64_t)p * t.m];
-                    y[t.first + p] = w[p];
+                for (int q = L.solve_begin; q < L.solve_end; q++) {
+                    const SolveTask& t = P.solve_tasks[q];
+                    double* w = W.data() + t.woff;
+                    const int* bi = P.bidx.data() + t.bidx_off;
+                    for (int a = 0; a < t.r; a++) w[t.s + a] = y[bi[a]];
+                    const double* UT = H + t.UToff;
+                    for (int p = t.s - 1; p >= 0; p--) {
+                        double z = y[t.first + p];
+                        for (int a = p + 1; a < t.m; a++) z -= UT[a + (int64_t)p * t.m] * w[a];
+                        w[p] = z / UT[p + (int64_t)p * t.m];
+                        y[t.first + p] = w[p];
+                    }
                 }
             }
+            // the owner of every top front of this level broadcasts its solution
+            for (int t : P0.levels[l].tops) {
+                int o = P0.owner[t];
+                const Front& f = P0.fronts[t];
+                for (int r = 0; r < nranks; r++)
+                    if (r != o) memcpy(ys[r].data() + f.first, ys[o].data() + f.first, sizeof(double) * (size_t)f.s);
+            }
+        }
+        // finally every rank-private subtree range is broadcast by its owner
+        for (size_t q = 0; q < P0.subtree_roots.size(); q++) {
+            int t = P0.subtree_roots[q];
+            int o = P0.owner[t];
+            int lo = P0.subtree_lo[q], hi = P0.fronts[t].first + P0.fronts[t].s;
+            for (int r = 0; r < nranks; r++)
+                if (r != o) memcpy(ys[r].data() + lo, ys[o].data() + lo, sizeof(double) * (size_t)(hi - lo));
         }
         for (int i = 0; i < n; i++) {
-            xacc[i] += y[P.perm[i]];
+            xacc[i] += ys[0][P0.perm[i]];
             X[i + (int64_t)c * n] = xacc[i];
         }
       }
     return 0;
+}
+
+// Partition as seen by ONE rank (for the world_size-2 gloo test): owner_out[n_fronts],
+// xfer_out[3 * n_xfers] = (front, src, dst); returns n_fronts, or a negative error.
+int nkp_sim_partition(int n, const int* rowptr, const int* colind, const int* ci, const int* cj, const int* ck,
+                      int nb, int leaf, int rank, int nranks, int* owner_out, int owner_cap, int* xfer_out,
+                      int xfer_cap, int* n_xfers, double* local_out) {
+    Options opt;
+    opt.nb = nb;
+    opt.leaf = leaf;
+    if (opt.tn > nb) opt.tn = nb;
+    opt.rank = rank;
+    opt.nranks = nranks;
+    const int* coords[3] = {ci, cj, ck};
+    Plan P;
+    int rc = analyse(n, rowptr, colind, (ci || cj || ck) ? coords : nullptr, opt, P);
+    if (rc) return rc;
+    int nf = (int)P.fronts.size();
+    if (nf > owner_cap || (int)P.xfers.size() > xfer_cap) return -30;
+    for (int t = 0; t < nf; t++) owner_out[t] = P.owner[t];
+    for (size_t q = 0; q < P.xfers.size(); q++) {
+        xfer_out[3 * q + 0] = P.xfers[q].front;
+        xfer_out[3 * q + 1] = P.xfers[q].src;
+        xfer_out[3 * q + 2] = P.xfers[q].dst;
+    }
+    *n_xfers = (int)P.xfers.size();
+    if (local_out) {
+        local_out[0] = P.flops_local;
+        local_out[1] = P.flops;
+        local_out[2] = (double)P.heap_len;
+        local_out[3] = (double)P.nnz_lu_local;
+    }
+    return nf;
+}
+
+int nkp_sim_run(int n, const int* rowptr, const int* colind, const double* val, const int* ci,
+                const int* cj, const int* ck, int nb, int leaf, const double* B, int nrhs,
+                double* X, double* stats_out, int* perm_out, int analysis_only) {
+    int nranks = getenv("NKP_SIM_RANKS") ? atoi(getenv("NKP_SIM_RANKS")) : 1;
+    return nkp_sim_run_dist(n, rowptr, colind, val, ci, cj, ck, nb, leaf, B, nrhs, X, stats_out, perm_out,
+                            analysis_only, nranks, nullptr);
 }
 }
