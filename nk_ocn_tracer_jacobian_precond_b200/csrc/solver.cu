@@ -37,6 +37,56 @@ static thread_local std::string g_err;
         }                                                                                          \
     } while (0)
 
+// NCCL is bound lazily with dlopen: single-GPU users never load it, and a process that already
+// carries a (possibly newer) libnccl.so.2 -- e.g. the one bundled with PyTorch -- keeps using
+// that copy instead of getting a second, conflicting one.
+#include <dlfcn.h>
+namespace {
+struct NcclApi {
+    void* handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    bool ok = false;
+};
+NcclApi g_nccl;
+bool nccl_load() {
+    if (g_nccl.ok) return true;
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) return false;
+    g_nccl.handle = h;
+#define NKP_SYM(field, name) *(void**)(&g_nccl.field) = dlsym(h, name); if (!g_nccl.field) return false;
+    NKP_SYM(GetUniqueId, "ncclGetUniqueId")
+    NKP_SYM(CommInitRank, "ncclCommInitRank")
+    NKP_SYM(CommDestroy, "ncclCommDestroy")
+    NKP_SYM(GroupStart, "ncclGroupStart")
+    NKP_SYM(GroupEnd, "ncclGroupEnd")
+    NKP_SYM(Send, "ncclSend")
+    NKP_SYM(Recv, "ncclRecv")
+    NKP_SYM(Broadcast, "ncclBroadcast")
+    NKP_SYM(GetErrorString, "ncclGetErrorString")
+#undef NKP_SYM
+    g_nccl.ok = true;
+    return true;
+}
+}  // namespace
+#define ncclGetUniqueId g_nccl.GetUniqueId
+#define ncclCommInitRank g_nccl.CommInitRank
+#define ncclCommDestroy g_nccl.CommDestroy
+#define ncclGroupStart g_nccl.GroupStart
+#define ncclGroupEnd g_nccl.GroupEnd
+#define ncclSend g_nccl.Send
+#define ncclRecv g_nccl.Recv
+#define ncclBroadcast g_nccl.Broadcast
+#define ncclGetErrorString g_nccl.GetErrorString
+
 #define CKN(call)                                                                                  \
     do {                                                                                           \
         ncclResult_t e_ = (call);                                                                  \
@@ -226,6 +276,10 @@ static int create_impl(nkp_solver** out, int n, const int* rowptr, const int* co
         CK(cudaStreamCreate(&s->stream));
         for (int i = 0; i < 4; i++) CK(cudaEventCreate(&s->ev[i]));
         if (nranks > 1) {
+            if (!nccl_load()) {
+                g_err = "cannot load libnccl.so.2";
+                return NKP_ECUDA;
+            }
             ncclUniqueId id;
             static_assert(sizeof(ncclUniqueId) <= NKP_UNIQUE_ID_BYTES, "unique id size");
             memcpy(&id, unique_id, sizeof(id));
@@ -308,6 +362,10 @@ int nkp_create_dist(nkp_solver** out, int n, const int* rowptr, const int* colin
 
 int nkp_comm_unique_id(void* unique_id) {
     if (!unique_id) return NKP_EINVAL;
+    if (!nccl_load()) {
+        g_err = "cannot load libnccl.so.2";
+        return NKP_ECUDA;
+    }
     ncclUniqueId id;
     CKN(ncclGetUniqueId(&id));
     memset(unique_id, 0, NKP_UNIQUE_ID_BYTES);
