@@ -261,6 +261,8 @@ def run_own(args):
         s.factor_device(dev_vals[k].data_ptr())
         work_B.copy_(dev_B[k])
         torch.cuda.current_stream().synchronize()
+        if dist is not None:
+            dist.barrier()   # ranks leave the factorisation at different times; keep that skew out of the solve timing
         berr = s.solve_device(work_B.data_ptr(), n, NRHS)
         if it >= args.warmup:
             st = s.stats()
@@ -300,6 +302,8 @@ def run_own(args):
         t0 = time.perf_counter()
         s.factor(host_vals[k])
         s.sync()
+        if dist is not None:
+            dist.barrier()
         t1 = time.perf_counter()
         s.solve(Bh)
         t2 = time.perf_counter()
