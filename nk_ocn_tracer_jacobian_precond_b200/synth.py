@@ -161,8 +161,112 @@ def _nc():
     return netcdf_file
 
 
-def write_circ_file(path: str, grid: dict, circ: dict) -> None:
-    """POP-history-like file for gen_A's ``circ_fname`` (minimal option set)."""
+def make_full_fields(grid: dict, circ: dict, seed: int = 0) -> dict:
+    """Extra circulation-file fields for the reference's own test option set
+    (test/test_gen_A.csh:22-23: adv upwind3, hmix isop_file, vmix file):
+
+    * UTE/VTN/WTK_{POS,NEG}: positive / negative parts of the face transports
+      (src/matrix.c:1471-1558),
+    * 36 HDIF_EXPLICIT_3D_IRF_{1..4}_{1..3}_{1..3}: impulse responses of an isopycnal-style
+      diffusion operator; entry [k][j][i] of class (i',j',k') is the coefficient (1/s) of the
+      unique stencil neighbour whose indices are congruent to (i',j',k') mod (4,3,3)
+      (src/matrix.c:2233-2376) -- needs imt % 4 == 0,
+    * VDC_S, VDC_GM: vertical diffusivities (src/matrix.c:2869-2885).
+    """
+    rng = np.random.default_rng(seed + 2000)
+    km, jmt, imt = grid["km"], grid["jmt"], grid["imt"]
+    assert imt % 4 == 0, "IRF residue classes need imt % 4 == 0 (periodic seam)"
+    KMT = grid["KMT"]
+    kk = np.arange(km)[:, None, None]
+    ocean = kk < KMT[None]
+    U = np.where(circ["UVEL"] == FILL, 0.0, circ["UVEL"])
+    V = np.where(circ["VVEL"] == FILL, 0.0, circ["VVEL"])
+    W = np.where(circ["WVEL"] == FILL, 0.0, circ["WVEL"])
+    UTE, VTN = _face_transports(grid, U, V)
+    out = {}
+    landT = ~ocean
+    for name, f in (("UTE", UTE), ("VTN", VTN), ("WTK", W)):
+        out[name + "_POS"] = np.where(landT, FILL, np.maximum(f, 0.0))
+        out[name + "_NEG"] = np.where(landT, FILL, np.minimum(f, 0.0))
+    # vertical diffusivity 0.1 .. 10 cm^2/s
+    vdc = 0.1 + 9.9 * np.exp(-grid["z_t"] / 5.0e3)[:, None, None] * (0.5 + 0.5 * rng.random((km, jmt, imt)))
+    out["VDC_S"] = np.where(landT, FILL, vdc)
+    out["VDC_GM"] = np.where(landT, FILL, 0.05 * vdc)
+
+    # isopycnal-style diffusion stencil: 15 neighbours, conservative (self = -sum of the others)
+    lon = np.deg2rad(grid["TLONG"])
+    lat = np.deg2rad(grid["TLAT"])
+    kappa = 4.0e6 + 2.0e6 * (0.5 + 0.5 * np.sin(2 * lon + 0.7) * np.cos(lat))     # cm^2/s
+    sx = 1.0e-3 * np.sin(3 * lon) * np.cos(2 * lat)                                 # isopycnal slopes
+    sy = 1.0e-3 * np.cos(2 * lon + 0.4) * np.sin(3 * lat)
+    dz = grid["dz"][:, None, None]
+    dx = grid["HUS"][None]
+    dy = grid["HUW"][None]
+    ta = grid["TAREA"][None]
+    ii = np.arange(imt)
+    ip1 = np.r_[1:imt, 0]
+    im1 = np.r_[imt - 1, 0:imt - 1]
+
+    def shifted(mask, dk, dj, di):
+        """ocean mask of the neighbour (k+dk, j+dj, i+di), False outside the grid."""
+        m = np.zeros_like(mask)
+        ks = slice(max(0, -dk), km - max(0, dk))
+        kd = slice(max(0, dk), km - max(0, -dk))
+        js = slice(max(0, -dj), jmt - max(0, dj))
+        jd = slice(max(0, dj), jmt - max(0, -dj))
+        idx = ii if di == 0 else (ip1 if di == 1 else im1)
+        m[ks, js, :] = mask[kd, jd, :][:, :, idx]
+        return m
+
+    coef = {}
+    k2 = kappa[None]
+    coef[(0, 0, 1)] = k2 * grid["HTE"][None] / dx / ta
+    coef[(0, 0, -1)] = (k2 * grid["HTE"][None] / dx)[:, :, im1] / ta
+    coef[(0, 1, 0)] = k2 * grid["HTN"][None] / dy / ta
+    cs = np.zeros((1, jmt, imt))
+    cs[:, 1:, :] = (k2 * grid["HTN"][None] / dy)[:, :-1, :]
+    coef[(0, -1, 0)] = cs / ta
+    slope2 = (sx**2 + sy**2)[None]
+    dzu = np.empty((km, 1, 1)); dzu[1:] = 0.5 * (dz[1:] + dz[:-1]); dzu[0] = dz[0]
+    dzd = np.empty((km, 1, 1)); dzd[:-1] = 0.5 * (dz[1:] + dz[:-1]); dzd[-1] = dz[-1]
+    coef[(-1, 0, 0)] = k2 * slope2 / dzu / dz * np.ones((km, jmt, imt))
+    coef[(1, 0, 0)] = k2 * slope2 / dzd / dz * np.ones((km, jmt, imt))
+    for dk in (-1, 1):
+        for di in (-1, 1):
+            coef[(dk, 0, di)] = -dk * di * k2 * sx[None] / (4.0 * dx * dz) * np.ones((km, jmt, imt))
+        for dj in (-1, 1):
+            coef[(dk, dj, 0)] = -dk * dj * k2 * sy[None] / (4.0 * dy * dz) * np.ones((km, jmt, imt))
+    self_c = np.zeros((km, jmt, imt))
+    for off, c in list(coef.items()):
+        c = np.broadcast_to(c, (km, jmt, imt)) * (ocean & shifted(ocean, *off))
+        coef[off] = c
+        self_c -= c
+    coef[(0, 0, 0)] = np.where(ocean, self_c, 0.0)
+    kidx, jidx, iidx = np.meshgrid(np.arange(km), np.arange(jmt), np.arange(imt), indexing="ij")
+    for ip in range(4):
+        for jp in range(3):
+            for kp in range(3):
+                irf = np.zeros((km, jmt, imt))
+                for (dk, dj, di), c in coef.items():
+                    match = (((iidx + di) % imt) % 4 == ip) & ((jidx + dj) % 3 == jp) & ((kidx + dk) % 3 == kp)
+                    irf += np.where(match, c, 0.0)
+                out[f"HDIF_EXPLICIT_3D_IRF_{ip + 1}_{jp + 1}_{kp + 1}"] = irf
+    return out
+
+
+REFTEST_OPTS = (
+    "circ_fname {circ}\n"
+    "day_cnt 365.0\n"
+    "adv_type upwind3\n"
+    "hmix_type isop_file\n"
+    "vmix_type file\n"
+    "sink_type const_shallow 365.0 10.0e2\n"
+)
+
+
+def write_circ_file(path: str, grid: dict, circ: dict, full: dict | None = None) -> None:
+    """POP-history-like file for gen_A's ``circ_fname``; ``full`` (make_full_fields) adds the
+    fields of the reference's own test option set."""
     f = _nc()(path, "w", version=2)
     km, jmt, imt = grid["km"], grid["jmt"], grid["imt"]
     f.createDimension("nlon", imt)
@@ -184,6 +288,11 @@ def write_circ_file(path: str, grid: dict, circ: dict) -> None:
         v = f.createVariable(name, "d", ("z_t", "nlat", "nlon"))
         v[:] = circ[name]
         v._FillValue = np.float64(FILL)
+    for name, arr in (full or {}).items():
+        v = f.createVariable(name, "d", ("z_t", "nlat", "nlon"))
+        v[:] = arr
+        if not name.startswith("HDIF"):   # IRF variables get no fill masking (src/matrix.c:2259)
+            v._FillValue = np.float64(FILL)
     f.close()
 
 

@@ -29,6 +29,22 @@ def golden_rhs():
 
 
 @pytest.fixture(scope="session")
+def reftest_matrix():
+    """Operand of the reference's own test option set (upwind3 + isop_file + vmix file)."""
+    from nk_ocn_tracer_jacobian_precond_b200 import synth
+    m = synth.read_matrix_file(os.path.join(GOLDEN, "A_reftest_20x24x10.nc"))
+    m["n"] = len(m["rowptr"]) - 1
+    return m
+
+
+@pytest.fixture(scope="session")
+def reftest_rhs():
+    import numpy as np
+    d = np.load(os.path.join(GOLDEN, "rhs_x_reftest_20x24x10.npz"))
+    return {k: d[k] for k in d.files}
+
+
+@pytest.fixture(scope="session")
 def sim_lib():
     """CPU plan interpreter (oracle/libnkp_sim.so); built on demand."""
     import ctypes

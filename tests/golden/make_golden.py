@@ -7,6 +7,9 @@
   opts_20x24x10.txt  the gen_A option file used
   rhs_x_20x24x10.npz seeded right-hand sides and the oracle's solutions (scipy SuperLU +
                      pdgsrfs refinement, oracle/oracle_solve.py)
+  A_reftest_20x24x10.nc / rhs_x_reftest_20x24x10.npz
+                     the same for the reference's own test option set (upwind3 + isop_file +
+                     vmix file, test/test_gen_A.csh:22-23): 19-point rows
 """
 import os, subprocess, sys
 import numpy as np
@@ -31,6 +34,23 @@ def main():
     X, info = oracle_solve.solve(n, m["rowptr"], m["colind"], m["nzval_row_wise"], B, return_info=True)
     np.savez_compressed("rhs_x_20x24x10.npz", B=B, X=X, berr=np.array([i[0] for i in info]))
     print("golden written: n =", n, "nnz =", len(m["colind"]), "oracle berr", [i[0] for i in info])
+
+    # the reference's own test option set (test/test_gen_A.csh:22-23): upwind3 + isop_file + vmix file.
+    # The 2 MB circulation file is not committed; it is regenerated from the seed.
+    import tempfile
+    with tempfile.TemporaryDirectory() as td:
+        full = synth.make_full_fields(g, c, seed=1)
+        circ = os.path.join(td, "circ_full.nc")
+        synth.write_circ_file(circ, g, c, full)
+        opts = os.path.join(td, "opts.txt")
+        open(opts, "w").write(synth.REFTEST_OPTS.format(circ=circ))
+        subprocess.check_call([os.path.join(ROOT, "oracle/_ref/gen_A"), "-o", opts, os.path.join(HERE, "A_reftest_20x24x10.nc")])
+    m = synth.read_matrix_file("A_reftest_20x24x10.nc")
+    n = len(m["rowptr"]) - 1
+    B = np.asfortranarray(np.random.default_rng(321).standard_normal((n, 2)))
+    X, info = oracle_solve.solve(n, m["rowptr"], m["colind"], m["nzval_row_wise"], B, return_info=True)
+    np.savez_compressed("rhs_x_reftest_20x24x10.npz", B=B, X=X, berr=np.array([i[0] for i in info]))
+    print("golden (reference test options) written: n =", n, "nnz =", len(m["colind"]), "oracle berr", [i[0] for i in info])
 
 if __name__ == "__main__":
     main()

@@ -53,6 +53,23 @@ def test_golden_vectors(golden_matrix, golden_rhs):
     s.close()
 
 
+def test_golden_vectors_reference_test_options(reftest_matrix, reftest_rhs):
+    """Operand written by gen_A with the reference's own test options (upwind3 + isop_file +
+    vmix file, test/test_gen_A.csh:22-23)."""
+    c = _golden_case(reftest_matrix)
+    s = _solver(c)
+    s.factor(c["nzval"])
+    X = np.asfortranarray(reftest_rhs["B"].copy())
+    berr = s.solve(X)
+    A = _A(c)
+    rel = np.linalg.norm(X - reftest_rhs["X"], axis=0) / np.linalg.norm(reftest_rhs["X"], axis=0)
+    assert rel.max() <= SOL_TOL, rel
+    res = np.linalg.norm(A @ X - reftest_rhs["B"], axis=0) / np.linalg.norm(reftest_rhs["B"], axis=0)
+    assert res.max() <= RES_TOL
+    assert berr.max() <= 8 * oracle_solve.EPS
+    s.close()
+
+
 def test_batched_rhs_equals_single_rhs(golden_matrix):
     """KAT-4: the reference loops nrhs=1 solves over tracers (src/solve_ABglobal.c:370);
     the batched nrhs=8 solve must give the same answers."""

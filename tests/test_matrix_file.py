@@ -167,3 +167,29 @@ def test_nc3_reads_scipy_written_file(tmp_path):
     assert lib.nc_inq_dimlen(ncid, did, ctypes.byref(ln)) == 0 and ln.value == 4
     assert lib.nc_close(ncid) == 0
     assert lib.nc_open(str(tmp_path / "missing.nc").encode(), 0, ctypes.byref(ncid)) != 0
+
+
+def test_reftest_golden_known_answers(reftest_matrix):
+    """The reference's own test options (test/test_gen_A.csh:22-23): upwind3 + isop_file rows have
+    up to 21 entries (src/matrix.c:621-650), sorted, diagonal present, zeros stripped."""
+    m = reftest_matrix
+    n, rp, ci, nz = m["n"], m["rowptr"], m["colind"], m["nzval_row_wise"]
+    assert rp[-1] == len(nz) and np.all(nz != 0.0)
+    lens = np.diff(rp)
+    assert 7 < lens.max() <= 21
+    for r in range(n):
+        cols = ci[rp[r]:rp[r + 1]]
+        assert np.all(np.diff(cols) > 0) and r in cols
+
+
+@pytest.mark.skipif(not os.path.exists(GEN_A), reason="oracle/_ref/gen_A not built")
+def test_reference_gen_A_reproduces_reftest_golden(tmp_path, reftest_matrix):
+    c = synth_case(20, 24, 10, seed=1)
+    full = synth.make_full_fields(c["grid"], c["circ"], seed=1)
+    circ = tmp_path / "circ_full.nc"
+    synth.write_circ_file(str(circ), c["grid"], c["circ"], full)
+    (tmp_path / "opts.txt").write_text(synth.REFTEST_OPTS.format(circ=str(circ)))
+    subprocess.check_call([GEN_A, "-o", str(tmp_path / "opts.txt"), str(tmp_path / "A.nc")])
+    a = synth.read_matrix_file(str(tmp_path / "A.nc"))
+    for k in ("nzval_row_wise", "colind", "rowptr"):
+        assert np.array_equal(a[k], reftest_matrix[k]), k

@@ -108,3 +108,16 @@ def test_analysis_reports_fill_and_flops(sim_lib):
     assert nnz_lu >= len(c["nzval"])
     assert heap >= nnz_lu
     assert flops > 0 and nlevels >= 5 and maxfront < c["n"]
+
+
+def test_plan_interpreter_on_reference_test_options(sim_lib, reftest_matrix, reftest_rhs):
+    """19-point rows with +-2 reach (upwind3) and diagonal (k+-1,i+-1) couplings (isop): the
+    graph-derived separators must still separate, and the answer must match the oracle."""
+    m = reftest_matrix
+    coords = (m["tracer_state_ind_to_i"], m["tracer_state_ind_to_j"], m["tracer_state_ind_to_k"])
+    X, stats, perm = run_sim(sim_lib, m["n"], m["rowptr"], m["colind"], m["nzval_row_wise"], coords, reftest_rhs["B"],
+                             nb=64, leaf=64)
+    rel = np.linalg.norm(X - reftest_rhs["X"], axis=0) / np.linalg.norm(reftest_rhs["X"], axis=0)
+    assert rel.max() <= 1e-8, rel
+    Xo = oracle_solve.solve(m["n"], m["rowptr"], m["colind"], m["nzval_row_wise"], reftest_rhs["B"])
+    assert np.allclose(Xo, reftest_rhs["X"], rtol=1e-11, atol=0)
