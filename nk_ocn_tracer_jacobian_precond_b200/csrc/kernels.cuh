@@ -590,13 +590,14 @@ __device__ __forceinline__ void st_release_gpu(int* p, int v) {
 }
 
 template <int NR>
-__global__ void __launch_bounds__(256) k_fwd_big(const BigFront* __restrict__ bfs, const BigItem* __restrict__ items,
+__global__ void __launch_bounds__(256, 2) k_fwd_big(const BigFront* __restrict__ bfs, const BigItem* __restrict__ items,
                                                  int nitems, const SolveChild* __restrict__ children,
                                                  const int* __restrict__ rel, const double* __restrict__ heap,
                                                  double* __restrict__ W, double* __restrict__ y, int n,
                                                  int* __restrict__ flags, int epoch) {
-    __shared__ double buf[64 * 65];   // reduction scratch, then the diagonal block
+    __shared__ double buf[64 * 65];   // staged y of a batch, reduction scratch, then the diagonal block
     __shared__ double ys[64 * NR];
+    __shared__ int s_nbat;
     const int tid = threadIdx.x, row = tid & 63, cg = tid >> 6;
     for (int it = blockIdx.x; it < nitems; it += gridDim.x) {
         const BigItem item = items[it];
@@ -656,21 +657,41 @@ __global__ void __launch_bounds__(256) k_fwd_big(const BigFront* __restrict__ bf
             }
         };
         if (kmax > 0) loadL(0);
-        for (int k = 0; k < kmax; k++) {
-            if (tid == 0)
-                while (ld_acquire_gpu(&flags[bf.flag0 + k]) != epoch) __nanosleep(32);
+        // Pivot blocks are consumed in batches of FB when their solutions are already published
+        // (flags of one front are set in increasing order, so the last flag of the batch
+        // suffices); close to the wavefront the loop falls back to single blocks.
+        constexpr int FB = 4;
+        int k = 0;
+        while (k < kmax) {
+            if (tid == 0) {
+                int nbat = 1;
+                if (k + FB <= kmax && ld_acquire_gpu(&flags[bf.flag0 + k + FB - 1]) == epoch) nbat = FB;
+                else
+                    while (ld_acquire_gpu(&flags[bf.flag0 + k]) != epoch) __nanosleep(32);
+                s_nbat = nbat;
+            }
             __syncthreads();
-            const int kb = min(64, s - 64 * k);
-            for (int e = tid; e < 64 * NR; e += 256) {
-                int p = e & 63, c = e >> 6;
-                ys[e] = p < kb ? __ldcg(&y[bf.first + 64 * k + p + (int64_t)c * n]) : 0.0;
+            const int nbat = s_nbat;
+            for (int e = tid; e < nbat * 64 * NR; e += 256) {
+                int b = e / (64 * NR), rem = e - b * 64 * NR;
+                int p = rem & 63, c = rem >> 6;
+                int kk = k + b;
+                buf[e] = p < min(64, s - 64 * kk) ? __ldcg(&y[bf.first + 64 * kk + p + (int64_t)c * n]) : 0.0;
             }
             __syncthreads();
 #pragma unroll
-            for (int pp = 0; pp < 16; pp++)
+            for (int b = 0; b < FB; b++) {
+                if (b < nbat) {
+                    if (b > 0) loadL(k + b);
+                    const double* yb = buf + b * 64 * NR;
 #pragma unroll
-                for (int c = 0; c < NR; c++) acc[c] += lreg[pp] * ys[cg * 16 + pp + 64 * c];
-            if (k + 1 < kmax) loadL(k + 1);
+                    for (int pp = 0; pp < 16; pp++)
+#pragma unroll
+                        for (int c = 0; c < NR; c++) acc[c] += lreg[pp] * yb[cg * 16 + pp + 64 * c];
+                }
+            }
+            k += nbat;
+            if (k < kmax) loadL(k);
             __syncthreads();
         }
         // reduce the four column groups
@@ -749,7 +770,7 @@ __global__ void __launch_bounds__(256) k_fwd_big(const BigFront* __restrict__ bf
 }
 
 template <int NR>
-__global__ void __launch_bounds__(256) k_bwd_big(const BigFront* __restrict__ bfs, const BigItem* __restrict__ items,
+__global__ void __launch_bounds__(256, 2) k_bwd_big(const BigFront* __restrict__ bfs, const BigItem* __restrict__ items,
                                                  int nitems, const int* __restrict__ bidx,
                                                  const double* __restrict__ heap, double* __restrict__ y, int n,
                                                  int* __restrict__ flags, int epoch) {
@@ -792,20 +813,34 @@ __global__ void __launch_bounds__(256) k_bwd_big(const BigFront* __restrict__ bf
                 int p = hi * 16 + pp;
                 treg[pp] = (lo < na && p < kb) ? UT[a0 + lo + (int64_t)(c0 + p) * m] : 0.0;
             }
+            // x of this row block: boundary rows are final (solution of an ancestor) and can be
+            // fetched together with the tile; pivot rows only after their panel has published
+            constexpr int XR = (64 * NR + 255) / 256;
+            double xreg[XR];
+            auto load_x = [&]() {
+#pragma unroll
+                for (int q = 0; q < XR; q++) {
+                    int e = tid + q * 256;
+                    int a = e & 63, c = e >> 6;
+                    double xv = 0.0;
+                    if (e < 64 * NR && a < na) {
+                        int g = waitk < 0 ? bi[a0 - s + a] : bf.first + a0 + a;
+                        xv = __ldcg(&y[g + (int64_t)c * n]);
+                    }
+                    xreg[q] = xv;
+                }
+            };
+            if (waitk < 0) load_x();
             if (waitk >= 0 && tid == 0)
                 while (ld_acquire_gpu(&flags[bf.flag0 + waitk]) != epoch) __nanosleep(32);
             __syncthreads();
+            if (waitk >= 0) load_x();
 #pragma unroll
             for (int pp = 0; pp < 16; pp++) tile[lo + 65 * (hi * 16 + pp)] = treg[pp];
-            for (int e = tid; e < 64 * NR; e += 256) {
-                int a = e & 63, c = e >> 6;
-                double xv = 0.0;
-                if (a < na) {
-                    // boundary rows: final solution of an ancestor; pivot rows: published by a later panel
-                    int g = waitk < 0 ? bi[a0 - s + a] : bf.first + a0 + a;
-                    xv = __ldcg(&y[g + (int64_t)c * n]);
-                }
-                xs[e] = xv;
+#pragma unroll
+            for (int q = 0; q < XR; q++) {
+                int e = tid + q * 256;
+                if (e < 64 * NR) xs[e] = xreg[q];
             }
             __syncthreads();
             // thread (column lo, row group hi)
