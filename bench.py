@@ -367,6 +367,7 @@ def run_own(args):
             },
             "solve_s": solve_s, "solves_per_sec": NRHS / solve_s, "refine_steps": float(np.mean(refine)),
             "relres_max": relres, "solution_err_max": solerr, "berr_max": float(np.max(berr)),
+            "tiny_pivots_replaced": int(st["tiny_pivots"]),
             "roofline": roofline, "roofline_solve": roofline_solve, "cpu_baseline": cb,
             "e2e": {"value": e2e_factor, "unit": "s", "h2d_bytes_per_step": 8 * nnz + 8 * n * NRHS,
                     "d2h_bytes_per_step": 8 * n * NRHS, "solve_s": e2e_solve, "solves_per_sec": NRHS / e2e_solve},
