@@ -145,15 +145,25 @@ __global__ void __launch_bounds__(256) k_extend_add(const AddTask* __restrict__ 
     const double* Cc = heap + tk.Coff;
     int a = ti * ADD_TILE + (threadIdx.x & 31);
     int ra = a < tk.rc ? rl[a] : 0;
-    for (int jj = threadIdx.x >> 5; jj < ADD_TILE; jj += 8) {
-        int b = tj * ADD_TILE + jj;
+    // 4 entries per thread: all addresses and loads first, then the stores (distinct targets)
+    int64_t d[4];
+    double v[4], o[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        int b = tj * ADD_TILE + (threadIdx.x >> 5) + 8 * q;
+        d[q] = -1;
         if (a < tk.rc && b < tk.rc) {
             int rb = rl[b];
-            double v = Cc[a + (int64_t)b * tk.rc];
-            int64_t d = d_front_entry(ra, rb, tk.sp, tk.mp, nb, tk.Loff, tk.UToff, tk.F22off);
-            heap[d] += v;
+            v[q] = Cc[a + (int64_t)b * tk.rc];
+            d[q] = d_front_entry(ra, rb, tk.sp, tk.mp, nb, tk.Loff, tk.UToff, tk.F22off);
         }
     }
+#pragma unroll
+    for (int q = 0; q < 4; q++)
+        if (d[q] >= 0) o[q] = heap[d[q]];
+#pragma unroll
+    for (int q = 0; q < 4; q++)
+        if (d[q] >= 0) heap[d[q]] = o[q] + v[q];
 }
 
 // ------------------------------------------------------------------------------------------
@@ -184,14 +194,24 @@ __global__ void __launch_bounds__(256) k_diag(const DiagTask* __restrict__ tasks
             if (threadIdx.x == 0) atomicAdd(n_replaced, 1);
         }
         double l = 0.0;
-        if (i > k && i < kb) {
+        const int j0 = seg * 16;
+        if (i > k && i < kb && j0 + 15 > k) {
             l = D[i + k * LDS] / p;
-            const int j0 = seg * 16;
+            // stage both operands in registers first: the compiler cannot prove that the stores
+            // below do not alias the loads of the next iteration and would serialise them
+            double own[16], piv[16];
+#pragma unroll
+            for (int jj = 0; jj < 16; jj++) {
+                own[jj] = D[i + (j0 + jj) * LDS];
+                piv[jj] = D[k + (j0 + jj) * LDS];
+            }
 #pragma unroll
             for (int jj = 0; jj < 16; jj++) {
                 int j = j0 + jj;
-                if (j > k && j < kb) D[i + j * LDS] -= l * D[k + j * LDS];
+                if (j > k && j < kb) D[i + j * LDS] = own[jj] - l * piv[jj];
             }
+        } else if (i > k && i < kb) {
+            l = D[i + k * LDS] / p;
         }
         __syncthreads();
         // column k is dead for the elimination now: store the multipliers / the (replaced) pivot
@@ -216,6 +236,24 @@ __global__ void __launch_bounds__(256) k_diag(const DiagTask* __restrict__ tasks
 // ------------------------------------------------------------------------------------------
 
 constexpr int TRSM_ROWS = 128;
+
+// one row of X * T = B, KB columns held in registers (columns >= kb are padding: T is identity there)
+template <int KB>
+__device__ __forceinline__ void trsm_row(double* X, int ld, int kb, const double* T) {
+    double x[KB];
+#pragma unroll
+    for (int j = 0; j < KB; j++) x[j] = j < kb ? X[(int64_t)j * ld] : 0.0;
+#pragma unroll
+    for (int j = 0; j < KB; j++) {
+        double acc = x[j];
+#pragma unroll
+        for (int p = 0; p < j; p++) acc -= x[p] * T[p + j * NBMAX];
+        x[j] = acc * T[j + j * NBMAX];
+    }
+#pragma unroll
+    for (int j = 0; j < KB; j++)
+        if (j < kb) X[(int64_t)j * ld] = x[j];
+}
 
 __global__ void __launch_bounds__(TRSM_ROWS) k_trsm(const TrsmTask* __restrict__ tasks, int ntasks,
                                                    double* __restrict__ heap) {
@@ -242,19 +280,8 @@ __global__ void __launch_bounds__(TRSM_ROWS) k_trsm(const TrsmTask* __restrict__
     int row = (blockIdx.x - tk.cta0) * TRSM_ROWS + threadIdx.x;
     if (row >= tk.nrows) return;
     double* X = heap + tk.Xoff + row;
-    double x[NBMAX];
-#pragma unroll
-    for (int j = 0; j < NBMAX; j++) x[j] = j < kb ? X[(int64_t)j * ld] : 0.0;
-#pragma unroll
-    for (int j = 0; j < NBMAX; j++) {
-        double acc = x[j];
-#pragma unroll
-        for (int p = 0; p < j; p++) acc -= x[p] * T[p + j * NBMAX];
-        x[j] = acc * T[j + j * NBMAX];
-    }
-#pragma unroll
-    for (int j = 0; j < NBMAX; j++)
-        if (j < kb) X[(int64_t)j * ld] = x[j];
+    if (kb <= 32) trsm_row<32>(X, ld, kb, T);   // partial last blocks (e.g. the 32 of a 96-pivot leaf)
+    else trsm_row<NBMAX>(X, ld, kb, T);
 }
 
 // ------------------------------------------------------------------------------------------
