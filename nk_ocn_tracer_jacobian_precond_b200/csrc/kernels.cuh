@@ -56,6 +56,10 @@ __device__ __forceinline__ void cp_async8(void* smem, const void* gmem, bool pre
     int sz = pred ? 8 : 0;
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(s), "l"(gmem), "r"(sz));
 }
+// same with a precomputed shared-space address and source size (8 = copy, 0 = zero-fill)
+__device__ __forceinline__ void cp_async8_s(unsigned saddr, const void* gmem, int sz) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(saddr), "l"(gmem), "r"(sz));
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::); }
 
@@ -290,20 +294,50 @@ __global__ void __launch_bounds__(TRSM_ROWS) k_trsm(const TrsmTask* __restrict__
 // ------------------------------------------------------------------------------------------
 
 constexpr int G_TM = 128, G_TN = 64;
-constexpr int G_KC = 32;          // K chunk of the cp.async ring (2 stages)
+constexpr int G_KC = 16;          // K chunk of one pipeline stage
+constexpr int G_ST = 4;           // stages of the cp.async ring (prefetch distance 3 chunks)
 constexpr int G_LDA = G_TM + 4;   // == 4 (mod 16): conflict-free 8-byte fragment loads
 constexpr int G_LDB = G_TN + 4;
 constexpr int G_LDC = G_TM + 2;   // == 2 (mod 16): conflict-free accumulator staging
 constexpr int G_STAGE = G_KC * (G_LDA + G_LDB);   // doubles per stage
-constexpr int G_SMEM = 2 * G_STAGE * 8;
-static_assert(G_TN * G_LDC <= 2 * G_STAGE, "accumulator staging must fit in the ring");
+constexpr int G_SMEM = G_ST * G_STAGE * 8;
+static_assert(G_TN * G_LDC <= G_ST * G_STAGE, "accumulator staging must fit in the ring");
 
-__device__ __forceinline__ void cp_async_wait_1() { asm volatile("cp.async.wait_group 1;\n" ::); }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p)); }
+
+// mbarrier helpers (shared::cta): the ring is a producer/consumer pipeline without CTA-wide
+// barriers -- "full" completes when the cp.async copies of all 256 threads have landed,
+// "empty" when all 256 threads have finished reading the stage.
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_cp_async_arrive(uint64_t* bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+    const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    unsigned done = 0;
+    // try_wait suspends for a hardware-defined time before returning false, so this is not a hot
+    // spin; the iteration cap turns a protocol bug into a trapped kernel instead of a hung GPU
+    for (unsigned spins = 0; !done; spins++) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}\n"
+            : "=r"(done)
+            : "r"(a), "r"(parity)
+            : "memory");
+        if (spins > (1u << 26)) __trap();
+    }
+}
 
 __global__ void __launch_bounds__(256, 2) k_gemm(const GemmTask* __restrict__ tasks, int ntasks,
                                                  double* __restrict__ heap, int nb) {
     extern __shared__ __align__(16) double smem[];
+    __shared__ uint64_t full_bar[G_ST], empty_bar[G_ST];
     int t = find_task(tasks, ntasks, (int)blockIdx.x, [](const GemmTask& x) { return x.tile0; });
     const GemmTask tk = tasks[t];
     int local = blockIdx.x - tk.tile0;
@@ -318,25 +352,55 @@ __global__ void __launch_bounds__(256, 2) k_gemm(const GemmTask* __restrict__ ta
     double* C = heap + tk.Coff + m0 + (int64_t)n0 * tk.ldc;
     const int nchunks = (K + G_KC - 1) / G_KC;
 
-    // stage one K chunk of A (128 x 32) and B (64 x 32), zero-filling out-of-range elements
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int q = 0; q < G_ST; q++) {
+            mbar_init(&full_bar[q], 256);
+            mbar_init(&empty_bar[q], 256);
+        }
+    }
+    __syncthreads();
+
+    // stage one K chunk of A (128 x 16) and B (64 x 16), zero-filling out-of-range elements.
+    // Every thread copies a fixed row of 8 (A) + 4 (B) columns: addresses advance by constant strides.
+    const int ia = threadIdx.x & (G_TM - 1), ka0 = threadIdx.x >> 7;   // A: row, first column (0..1), step 2
+    const int ib = threadIdx.x & (G_TN - 1), kb0 = threadIdx.x >> 6;   // B: row, first column (0..3), step 4
+    const bool aok = ia < mrem, bok = ib < nrem;
+    const double* pa0 = A + (aok ? ia : 0) + (int64_t)ka0 * tk.lda;
+    const double* pb0 = B + (bok ? ib : 0) + (int64_t)kb0 * tk.ldb;
+    const int64_t sa = 2 * (int64_t)tk.lda, sb = 4 * (int64_t)tk.ldb;
     auto issue = [&](int ch) {
-        double* As = smem + (ch & 1) * G_STAGE;   // As[k * G_LDA + m]
+        const int stg = ch % G_ST;
+        double* As = smem + stg * G_STAGE;        // As[k * G_LDA + m]
         double* Bs = As + G_KC * G_LDA;           // Bs[k * G_LDB + n]
         const int kbase = ch * G_KC;
-        for (int e = threadIdx.x; e < G_KC * G_TM; e += 256) {
-            int i = e % G_TM, kk = e / G_TM, k = kbase + kk;
-            bool ok = (i < mrem) && (k < K);
-            cp_async8(&As[kk * G_LDA + i], ok ? (A + i + (int64_t)k * tk.lda) : A, ok);
+        const double* pa = pa0 + (int64_t)kbase * tk.lda;
+        const double* pb = pb0 + (int64_t)kbase * tk.ldb;
+        const unsigned da = (unsigned)__cvta_generic_to_shared(As + ka0 * G_LDA + ia);
+        const unsigned db = (unsigned)__cvta_generic_to_shared(Bs + kb0 * G_LDB + ib);
+        if (kbase + G_KC <= K) {
+            const int sza = aok ? 8 : 0, szb = bok ? 8 : 0;
+#pragma unroll
+            for (int q = 0; q < G_KC / 2; q++) cp_async8_s(da + q * 2 * G_LDA * 8, pa + q * sa, sza);
+#pragma unroll
+            for (int q = 0; q < G_KC / 4; q++) cp_async8_s(db + q * 4 * G_LDB * 8, pb + q * sb, szb);
+        } else {
+#pragma unroll
+            for (int q = 0; q < G_KC / 2; q++) {
+                bool ok = aok && (kbase + ka0 + 2 * q < K);
+                cp_async8_s(da + q * 2 * G_LDA * 8, ok ? pa + q * sa : A, ok ? 8 : 0);
+            }
+#pragma unroll
+            for (int q = 0; q < G_KC / 4; q++) {
+                bool ok = bok && (kbase + kb0 + 4 * q < K);
+                cp_async8_s(db + q * 4 * G_LDB * 8, ok ? pb + q * sb : B, ok ? 8 : 0);
+            }
         }
-        for (int e = threadIdx.x; e < G_KC * G_TN; e += 256) {
-            int i = e % G_TN, kk = e / G_TN, k = kbase + kk;
-            bool ok = (i < nrem) && (k < K);
-            cp_async8(&Bs[kk * G_LDB + i], ok ? (B + i + (int64_t)k * tk.ldb) : B, ok);
-        }
-        cp_async_commit();
+        mbar_cp_async_arrive(&full_bar[stg]);
     };
-    issue(0);
-    if (nchunks > 1) issue(1);
+#pragma unroll
+    for (int q = 0; q < G_ST - 1; q++)
+        if (q < nchunks) issue(q);
     // pull the C tile towards L2 for the epilogue: 512 lines of 128 B, 2 per thread
     for (int e = threadIdx.x; e < G_TN * 8; e += 256) {
         int j = e >> 3, seg = e & 7;
@@ -353,29 +417,36 @@ __global__ void __launch_bounds__(256, 2) k_gemm(const GemmTask* __restrict__ ta
         for (int b = 0; b < 4; b++) acc[a][b][0] = acc[a][b][1] = 0.0;
 
     for (int ch = 0; ch < nchunks; ch++) {
-        if (ch + 1 < nchunks) cp_async_wait_1();
-        else cp_async_wait_all();
-        __syncthreads();
-        const double* As = smem + (ch & 1) * G_STAGE;
+        const int stg = ch % G_ST;
+        mbar_wait(&full_bar[stg], (ch / G_ST) & 1);
+        // refill the stage that chunk ch-1 used, once every thread has finished reading it
+        const int nxt = ch + G_ST - 1;
+        if (nxt < nchunks) {
+            if (nxt >= G_ST) mbar_wait(&empty_bar[nxt % G_ST], (nxt / G_ST - 1) & 1);
+            issue(nxt);
+        }
+        const double* As = smem + stg * G_STAGE;
         const double* Bs = As + G_KC * G_LDA;
         const int ksteps = min(G_KC, K - ch * G_KC + 3) >> 2;
-#pragma unroll 4
-        for (int ks = 0; ks < ksteps; ks++) {
-            const double* ap = As + (ks * 4 + lc) * G_LDA + wm + lr;
-            const double* bp = Bs + (ks * 4 + lc) * G_LDB + wn + lr;
-            double af[4], bf[4];
 #pragma unroll
-            for (int a = 0; a < 4; a++) af[a] = ap[a * 8];
+        for (int ks = 0; ks < G_KC / 4; ks++) {
+            if (ks < ksteps) {
+                const double* ap = As + (ks * 4 + lc) * G_LDA + wm + lr;
+                const double* bp = Bs + (ks * 4 + lc) * G_LDB + wn + lr;
+                double af[4], bf[4];
 #pragma unroll
-            for (int b = 0; b < 4; b++) bf[b] = bp[b * 8];
+                for (int a = 0; a < 4; a++) af[a] = ap[a * 8];
 #pragma unroll
-            for (int a = 0; a < 4; a++)
+                for (int b = 0; b < 4; b++) bf[b] = bp[b * 8];
 #pragma unroll
-                for (int b = 0; b < 4; b++) dmma884(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
+                for (int a = 0; a < 4; a++)
+#pragma unroll
+                    for (int b = 0; b < 4; b++) dmma884(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
+            }
         }
-        __syncthreads();
-        if (ch + 2 < nchunks) issue(ch + 2);
+        mbar_arrive(&empty_bar[stg]);
     }
+    __syncthreads();
     // stage the product through shared memory so that the read-modify-write of C is coalesced
     double* Cs = smem;   // Cs[n * G_LDC + m]
 #pragma unroll
