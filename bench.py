@@ -292,6 +292,18 @@ def run_own(args):
         if it >= 3:
             sweep_t.append(s.stats()["t_sweeps"])
 
+    # residual SpMV r = b - A x (refinement): device time with torch events around the library call
+    dx = torch.randn(NRHS, n, dtype=torch.float64, device=dev)
+    dr = torch.empty_like(dx)
+    spmv_t = []
+    for it in range(3 + 5):
+        s.sync()
+        t0 = time.perf_counter()
+        s.residual_device(dx.data_ptr(), dev_B[0].data_ptr(), dr.data_ptr(), NRHS)
+        s.sync()
+        if it >= 3:
+            spmv_t.append(time.perf_counter() - t0)
+
     # ---------------- end-to-end arm (host buffers through the C ABI) ------------------------
     e2e_f, e2e_s = [], []
     Bh = np.empty_like(host_B[0])
@@ -348,6 +360,13 @@ def run_own(args):
             "peak_source": peaks["_hbm_src"], "traffic": None, "sweep_pair_ms": sweep_s * 1e3,
             "alg_bytes_per_sweep_pair": st["solve_bytes"],
         }
+        spmv_s = float(np.min(spmv_t))
+        spmv_bytes = NRHS * (12.0 * nnz + 4.0 * (n + 1) + 24.0 * n)   # BASELINE.md section 4, per right-hand side
+        roofline_spmv = {
+            "kernel": "k_residual (r = b - A x, %d rhs; host-timed launch+sync)" % NRHS, "bound": "hbm",
+            "achieved": spmv_bytes / spmv_s * 1e-9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+            "frac": spmv_bytes / spmv_s * 1e-9 / peaks["hbm_gbs"], "ms": spmv_s * 1e3, "traffic": None,
+        }
         cb = cpu_baseline(st["factor_flops"])
         line = {
             "metric": "numeric_factor_time_s", "value": factor_s, "unit": "s", "n_gpus": world, "steps": args.steps,
@@ -368,7 +387,7 @@ def run_own(args):
             "solve_s": solve_s, "solves_per_sec": NRHS / solve_s, "refine_steps": float(np.mean(refine)),
             "relres_max": relres, "solution_err_max": solerr, "berr_max": float(np.max(berr)),
             "tiny_pivots_replaced": int(st["tiny_pivots"]),
-            "roofline": roofline, "roofline_solve": roofline_solve, "cpu_baseline": cb,
+            "roofline": roofline, "roofline_solve": roofline_solve, "roofline_spmv": roofline_spmv, "cpu_baseline": cb,
             "e2e": {"value": e2e_factor, "unit": "s", "h2d_bytes_per_step": 8 * nnz + 8 * n * NRHS,
                     "d2h_bytes_per_step": 8 * n * NRHS, "solve_s": e2e_solve, "solves_per_sec": NRHS / e2e_solve},
             "gpu_launches": int(launches), "clocks": clocks,

@@ -241,32 +241,25 @@ __global__ void __launch_bounds__(256) k_diag(const DiagTask* __restrict__ tasks
 
 constexpr int TRSM_ROWS = 128;
 
-// one row of X * T = B, KB columns held in registers (columns >= kb are padding: T is identity there)
-template <int KB>
-__device__ __forceinline__ void trsm_row(double* X, int ld, int kb, const double* T) {
-    double x[KB];
-#pragma unroll
-    for (int j = 0; j < KB; j++) x[j] = j < kb ? X[(int64_t)j * ld] : 0.0;
-#pragma unroll
-    for (int j = 0; j < KB; j++) {
-        double acc = x[j];
-#pragma unroll
-        for (int p = 0; p < j; p++) acc -= x[p] * T[p + j * NBMAX];
-        x[j] = acc * T[j + j * NBMAX];
-    }
-#pragma unroll
-    for (int j = 0; j < KB; j++)
-        if (j < kb) X[(int64_t)j * ld] = x[j];
-}
+// X * T = B on a 128-row slab with 256 threads: thread r (< 128) solves columns 0..31 of row r,
+// thread 128 + r solves columns 32..63 of the same row after a rank-32 update with the first
+// half (exchanged through shared memory).  Each thread keeps only 32 columns in registers, so
+// twice as many warps are resident as with one thread per full row and the rank-32 update is
+// 32 independent FMA chains.
+constexpr int TRSM_THREADS = 256;
+constexpr int TRSM_XLD = 33;
+constexpr int TRSM_SMEM = (NBMAX * NBMAX + TRSM_ROWS * TRSM_XLD) * 8;
 
-__global__ void __launch_bounds__(TRSM_ROWS) k_trsm(const TrsmTask* __restrict__ tasks, int ntasks,
-                                                   double* __restrict__ heap) {
-    __shared__ double T[NBMAX * NBMAX];   // T[p + j*NBMAX], p <= j ; diagonal holds 1/T_jj
+__global__ void __launch_bounds__(TRSM_THREADS, 2) k_trsm(const TrsmTask* __restrict__ tasks, int ntasks,
+                                                          double* __restrict__ heap) {
+    extern __shared__ __align__(16) double tsm[];
+    double* T = tsm;                       // T[p + j*NBMAX], p <= j ; diagonal holds 1/T_jj
+    double* xs = tsm + NBMAX * NBMAX;      // xs[r * TRSM_XLD + p]: first half of the solution
     int t = find_task(tasks, ntasks, (int)blockIdx.x, [](const TrsmTask& x) { return x.cta0; });
     const TrsmTask tk = tasks[t];
     const int kb = tk.kb, ld = tk.ld;
     const double* G = heap + tk.Toff;
-    for (int e = threadIdx.x; e < NBMAX * NBMAX; e += blockDim.x) {
+    for (int e = threadIdx.x; e < NBMAX * NBMAX; e += TRSM_THREADS) {
         int p = e % NBMAX, j = e / NBMAX;
         double v = 0.0;
         if (p < kb && j < kb) {
@@ -280,12 +273,58 @@ __global__ void __launch_bounds__(TRSM_ROWS) k_trsm(const TrsmTask* __restrict__
         } else if (p == j) v = 1.0;
         T[e] = v;
     }
-    __syncthreads();
-    int row = (blockIdx.x - tk.cta0) * TRSM_ROWS + threadIdx.x;
-    if (row >= tk.nrows) return;
+    const int half = threadIdx.x >> 7;                 // 0: columns 0..31, 1: columns 32..63
+    const int r = threadIdx.x & (TRSM_ROWS - 1);
+    const int row = (blockIdx.x - tk.cta0) * TRSM_ROWS + r;
+    const bool active = row < tk.nrows && (half == 0 || kb > 32);
     double* X = heap + tk.Xoff + row;
-    if (kb <= 32) trsm_row<32>(X, ld, kb, T);   // partial last blocks (e.g. the 32 of a 96-pivot leaf)
-    else trsm_row<NBMAX>(X, ld, kb, T);
+    const int c0 = half * 32;
+    double x[32];
+#pragma unroll
+    for (int j = 0; j < 32; j++) x[j] = (active && c0 + j < kb) ? X[(int64_t)(c0 + j) * ld] : 0.0;
+    __syncthreads();
+    if (half == 0) {
+#pragma unroll
+        for (int j = 0; j < 32; j++) {
+            double a0 = x[j], a1 = 0.0;
+#pragma unroll
+            for (int p = 0; p < j; p++) {
+                const double tt = x[p] * T[p + j * NBMAX];
+                if (p & 1) a1 -= tt;
+                else a0 -= tt;
+            }
+            x[j] = (a0 + a1) * T[j + j * NBMAX];
+        }
+#pragma unroll
+        for (int j = 0; j < 32; j++) xs[r * TRSM_XLD + j] = x[j];
+        if (active)
+#pragma unroll
+            for (int j = 0; j < 32; j++)
+                if (j < kb) X[(int64_t)j * ld] = x[j];
+    }
+    __syncthreads();
+    if (half == 1 && active) {
+        // rank-32 update with the first half, then the second 32 x 32 triangle
+        for (int p = 0; p < 32; p++) {
+            const double xp = xs[r * TRSM_XLD + p];
+#pragma unroll
+            for (int j = 0; j < 32; j++) x[j] -= xp * T[p + (32 + j) * NBMAX];
+        }
+#pragma unroll
+        for (int j = 0; j < 32; j++) {
+            double a0 = x[j], a1 = 0.0;
+#pragma unroll
+            for (int p = 0; p < j; p++) {
+                const double tt = x[p] * T[32 + p + (32 + j) * NBMAX];
+                if (p & 1) a1 -= tt;
+                else a0 -= tt;
+            }
+            x[j] = (a0 + a1) * T[32 + j + (32 + j) * NBMAX];
+        }
+#pragma unroll
+        for (int j = 0; j < 32; j++)
+            if (32 + j < kb) X[(int64_t)(32 + j) * ld] = x[j];
+    }
 }
 
 // ------------------------------------------------------------------------------------------

@@ -335,6 +335,7 @@ static int create_impl(nkp_solver** out, int n, const int* rowptr, const int* co
         s->pinned_bytes = sizeof(double) * std::max<size_t>((size_t)s->nnz, (size_t)n * MAX_NR);
         CK(cudaMallocHost((void**)&s->h_pinned, s->pinned_bytes));
         CK(cudaFuncSetAttribute(k_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM));
+        CK(cudaFuncSetAttribute(k_trsm, cudaFuncAttributeMaxDynamicSharedMemorySize, TRSM_SMEM));
         // the scatter map and the heap can be large: release the host copies
         std::vector<int64_t>().swap(P.scatter);
         return 0;
@@ -448,7 +449,7 @@ static int do_factor(nkp_solver* s) {
             }
             int ntr = L.trsm_begin[step + 1] - L.trsm_begin[step];
             if (ntr > 0 && L.trsm_ctas[step] > 0) {
-                k_trsm<<<L.trsm_ctas[step], TRSM_ROWS, 0, st>>>(s->d_trsm + L.trsm_begin[step], ntr, s->heap);
+                k_trsm<<<L.trsm_ctas[step], TRSM_THREADS, TRSM_SMEM, st>>>(s->d_trsm + L.trsm_begin[step], ntr, s->heap);
                 s->launches++;
                 prof_mark(s, KC_TRSM);
             }

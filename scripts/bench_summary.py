@@ -4,3 +4,5 @@ print({k: d[k] for k in ("value", "solve_s", "solves_per_sec", "refine_steps", "
 r = d["roofline"]; print("gemm TF/s", round(r["achieved"], 2), "frac", round(r["frac"], 3), "share", round(r["share_of_factor_time"], 3), "overall TF/s", round(r["factor_overall_tflops"], 2), r["factor_breakdown_s"])
 r = d["roofline_solve"]; print("sweep GB/s", round(r["achieved"], 1), "frac", round(r["frac"], 3), "sweep_pair_ms", round(r["sweep_pair_ms"], 3))
 print("e2e", d["e2e"])
+if "roofline_spmv" in d:
+    r = d["roofline_spmv"]; print("spmv GB/s", round(r["achieved"], 1), "frac", round(r["frac"], 3), "ms", round(r["ms"], 3))
