@@ -367,6 +367,15 @@ def run_own(args):
             "achieved": spmv_bytes / spmv_s * 1e-9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
             "frac": spmv_bytes / spmv_s * 1e-9 / peaks["hbm_gbs"], "ms": spmv_s * 1e3, "traffic": None,
         }
+        # DRAM traffic per launch from the committed ncu capture of this workload (null if none)
+        tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+        if os.path.exists(tpath) and world == 1:
+            tj = json.load(open(tpath))
+            if wl in tj:
+                roofline["traffic"] = tj[wl].get("k_gemm_bytes_per_launch")
+                roofline["traffic_source"] = tj["source"]
+                roofline_solve["traffic"] = tj[wl].get("sweep_pair_bytes")
+                roofline_spmv["traffic"] = tj[wl].get("k_residual_bytes_per_launch")
         cb = cpu_baseline(st["factor_flops"])
         line = {
             "metric": "numeric_factor_time_s", "value": factor_s, "unit": "s", "n_gpus": world, "steps": args.steps,
