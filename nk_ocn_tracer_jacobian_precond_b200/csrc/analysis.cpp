@@ -398,6 +398,7 @@ int analyse(int n, const int* rowptr, const int* colind, const int* const coords
             std::sort(cand.begin(), cand.end());
             f.r = (int)cand.size();
             f.m = f.s + f.r;
+            f.ld = f.m + (f.m & 1);
             f.bidx_off = (int64_t)plan.bidx.size();
             plan.bidx.insert(plan.bidx.end(), cand.begin(), cand.end());
             boff[t + 1] = (int64_t)plan.bidx.size();
@@ -525,9 +526,9 @@ int analyse(int n, const int* rowptr, const int* colind, const int* const coords
         plan.flops_local += fl[t];
         plan.nnz_lu_local += (int64_t)f.s * f.s + 2 * (int64_t)f.s * f.r;
         f.Loff = off;
-        off = align_up(off + (int64_t)f.m * f.s, AL);
+        off = align_up(off + (int64_t)f.ld * f.s, AL);
         f.UToff = off;
-        off = align_up(off + (int64_t)f.m * f.s, AL);
+        off = align_up(off + (int64_t)f.ld * f.s, AL);
     }
     plan.factor_len = off;
     plan.flops = flops;
@@ -616,7 +617,7 @@ int analyse(int n, const int* rowptr, const int* colind, const int* const coords
                 };
                 int a = local(pi), b = local(pj);
                 if (a < 0 || b < 0) return -7;
-                plan.scatter[p] = front_entry(a, b, f.s, f.m, nb, f.Loff, f.UToff, f.F22off);
+                plan.scatter[p] = front_entry(a, b, f.s, f.m, f.ld, nb, f.Loff, f.UToff, f.F22off);
             }
         }
     }
@@ -652,7 +653,7 @@ int analyse(int n, const int* rowptr, const int* colind, const int* const coords
                     a.mp = fp.m;
                     a.tile0 = tile0;
                     a.tiles_m = (fc.r + opt.add_tile - 1) / opt.add_tile;
-                    a.pad = 0;
+                    a.ldp = fp.ld;
                     tile0 += a.tiles_m * a.tiles_m;
                     plan.add_tasks.push_back(a);
                 }
@@ -677,20 +678,20 @@ int analyse(int n, const int* rowptr, const int* colind, const int* const coords
                 if (k0 >= f.s) continue;
                 int kb = std::min(nb, f.s - k0);
                 int k1 = k0 + kb;
-                int64_t Dblk = f.Loff + k0 + (int64_t)k0 * f.m;
+                int64_t Dblk = f.Loff + k0 + (int64_t)k0 * f.ld;
                 DiagTask d;
                 d.Doff = Dblk;
-                d.UTDoff = f.UToff + k0 + (int64_t)k0 * f.m;
-                d.ld = f.m;
+                d.UTDoff = f.UToff + k0 + (int64_t)k0 * f.ld;
+                d.ld = f.ld;
                 d.kb = kb;
                 plan.diag_tasks.push_back(d);
                 int below = f.m - k1;
                 if (below > 0) {
                     for (int which = 0; which < 2; which++) {
                         TrsmTask tt;
-                        tt.Xoff = (which == 0 ? f.Loff : f.UToff) + k1 + (int64_t)k0 * f.m;
+                        tt.Xoff = (which == 0 ? f.Loff : f.UToff) + k1 + (int64_t)k0 * f.ld;
                         tt.Toff = Dblk;
-                        tt.ld = f.m;
+                        tt.ld = f.ld;
                         tt.nrows = below;
                         tt.kb = kb;
                         tt.unit = which;
@@ -737,13 +738,13 @@ int analyse(int n, const int* rowptr, const int* colind, const int* const coords
                             }
                         plan.gemm_flops += 2.0 * K * area;
                     };
-                    const int64_t ld = f.m;
+                    const int64_t ld = f.ld;
                     if (k1 < ke) {
                         // narrow: block columns / rows [k1, ke) of the outer block, all rows below
                         int64_t Lpan = f.Loff + k1 + (int64_t)k0 * ld;    // L[k1.., k0:k1]
                         int64_t UTpan = f.UToff + k1 + (int64_t)k0 * ld;  // U^T[k1.., k0:k1]
-                        push_gemm(Lpan, UTpan, f.Loff + k1 + (int64_t)k1 * ld, below, ke - k1, kb, f.m, f.m, f.m, 1);
-                        push_gemm(UTpan, Lpan, f.UToff + k1 + (int64_t)k1 * ld, below, ke - k1, kb, f.m, f.m, f.m, 2);
+                        push_gemm(Lpan, UTpan, f.Loff + k1 + (int64_t)k1 * ld, below, ke - k1, kb, f.ld, f.ld, f.ld, 1);
+                        push_gemm(UTpan, Lpan, f.UToff + k1 + (int64_t)k1 * ld, below, ke - k1, kb, f.ld, f.ld, f.ld, 2);
                     } else {
                         // wide: k1 == ke, the outer block [ko0, ke) is completely factored
                         const int K = ke - ko0;
@@ -752,13 +753,13 @@ int analyse(int n, const int* rowptr, const int* colind, const int* const coords
                         int64_t Lpan = f.Loff + ke + (int64_t)ko0 * ld;    // L[ke.., ko0:ke]
                         int64_t UTpan = f.UToff + ke + (int64_t)ko0 * ld;  // U^T[ke.., ko0:ke]
                         if (trail_s > 0) {
-                            push_gemm(Lpan, UTpan, f.Loff + ke + (int64_t)ke * ld, rest, trail_s, K, f.m, f.m, f.m, 1);
-                            push_gemm(UTpan, Lpan, f.UToff + ke + (int64_t)ke * ld, rest, trail_s, K, f.m, f.m, f.m, 2);
+                            push_gemm(Lpan, UTpan, f.Loff + ke + (int64_t)ke * ld, rest, trail_s, K, f.ld, f.ld, f.ld, 1);
+                            push_gemm(UTpan, Lpan, f.UToff + ke + (int64_t)ke * ld, rest, trail_s, K, f.ld, f.ld, f.ld, 2);
                         }
                         if (f.r > 0) {
                             int64_t Lb = f.Loff + f.s + (int64_t)ko0 * ld;
                             int64_t UTb = f.UToff + f.s + (int64_t)ko0 * ld;
-                            push_gemm(Lb, UTb, f.F22off, f.r, f.r, K, f.m, f.m, f.r, 0);
+                            push_gemm(Lb, UTb, f.F22off, f.r, f.r, K, f.ld, f.ld, f.r, 0);
                         }
                     }
                 }
@@ -788,8 +789,9 @@ int analyse(int n, const int* rowptr, const int* colind, const int* const coords
             st.s = f.s;
             st.r = f.r;
             st.m = f.m;
+            st.ld = f.ld;
             st.nchild = f.nchild;
-            st.pad = 0;
+            st.big = 0;
             for (int c : nodes[t].children) {
                 const Front& fc = plan.fronts[c];
                 SolveChild sc;
@@ -805,9 +807,19 @@ int analyse(int n, const int* rowptr, const int* colind, const int* const coords
         // split into single-CTA fronts and big (multi-CTA dataflow) fronts
         L.small_begin = (int)plan.solve_small.size();
         L.big_begin = (int)plan.big_fronts.size();
+        int64_t part_slots = 0;
         for (int q = L.solve_begin; q < L.solve_end; q++) {
-            const SolveTask& st = plan.solve_tasks[q];
+            SolveTask& st = plan.solve_tasks[q];
             if ((int64_t)st.m * st.s >= opt.big_entries && st.s >= 64) {
+                st.big = 1;
+                for (int k0 = 0; k0 < st.s; k0 += 64) {
+                    DiagTask d;
+                    d.Doff = st.Loff + k0 + (int64_t)k0 * st.ld;
+                    d.UTDoff = st.UToff + k0 + (int64_t)k0 * st.ld;
+                    d.ld = st.ld;
+                    d.kb = std::min(64, st.s - k0);
+                    plan.inv_tasks.push_back(d);
+                }
                 BigFront bf;
                 bf.Loff = st.Loff;
                 bf.UToff = st.UToff;
@@ -822,6 +834,10 @@ int analyse(int n, const int* rowptr, const int* colind, const int* const coords
                 bf.flag0 = plan.n_big_flags;
                 bf.nchild = st.nchild;
                 bf.child_list = st.child_list;
+                bf.nchunk = ((st.r + 63) / 64 + BWD_CHUNK - 1) / BWD_CHUNK;
+                bf.part_off = part_slots;
+                bf.ld = st.ld;
+                part_slots += (int64_t)bf.npiv * bf.nchunk;
                 plan.n_big_flags += bf.npiv;
                 plan.big_fronts.push_back(bf);
             } else {
@@ -849,6 +865,14 @@ int analyse(int n, const int* rowptr, const int* colind, const int* const coords
         }
         L.fwd_item_end = (int)plan.big_fwd_items.size();
         L.bwd_item_end = (int)plan.big_bwd_items.size();
+        // rectangular (boundary) part of the backward sweep: independent (panel, row chunk) items
+        plan.bwd_part_slots = std::max(plan.bwd_part_slots, part_slots);
+        L.rect_item_begin = (int)plan.big_rect_items.size();
+        for (int b = L.big_begin; b < L.big_end; b++) {
+            const BigFront& bf = plan.big_fronts[b];
+            for (int q = 0; q < bf.npiv * bf.nchunk; q++) plan.big_rect_items.push_back(BigItem{b, q});
+        }
+        L.rect_item_end = (int)plan.big_rect_items.size();
     }
     plan.t_plan = now_s() - t0;
 
@@ -858,6 +882,22 @@ int analyse(int n, const int* rowptr, const int* colind, const int* const coords
                 "heap=%.2f GB flops=%.3e  t(order,symb,plan)=%.2f,%.2f,%.2f s\n",
                 n, (long long)plan.nnz, nf, plan.nlevels, plan.max_front, (long long)plan.nnz_lu,
                 plan.nnz_lu * 8e-9, plan.heap_len * 8e-9, plan.flops, plan.t_order, plan.t_symbolic, plan.t_plan);
+    }
+    if (opt.verbose >= 2) {
+        // per level: fronts, big fronts, largest pivot count / front size, factor bytes (L + U^T panels)
+        for (int l = 0; l < plan.nlevels; l++) {
+            const LevelPlan& L = plan.levels[l];
+            int maxs = 0, maxm = 0;
+            double bytes = 0;
+            for (int t : L.mine) {
+                const Front& f = plan.fronts[t];
+                maxs = std::max(maxs, f.s);
+                maxm = std::max(maxm, f.m);
+                bytes += 8.0 * ((double)f.s * f.s + 2.0 * (double)f.r * f.s);
+            }
+            fprintf(stderr, "[nkp] level %2d: fronts %6d big %5d max_s %6d max_m %6d factor bytes %8.3f GB\n", l,
+                    (int)L.mine.size(), L.big_end - L.big_begin, maxs, maxm, bytes * 1e-9);
+        }
     }
     return 0;
 }

@@ -36,13 +36,13 @@ __device__ __forceinline__ int find_task(const T* tasks, int n, int idx, F key) 
     return lo;
 }
 
-__device__ __forceinline__ int64_t d_front_entry(int a, int b, int s, int m, int nb,
+__device__ __forceinline__ int64_t d_front_entry(int a, int b, int s, int m, int ld, int nb,
                                                  int64_t Loff, int64_t UToff, int64_t F22off) {
     if (b < s) {
-        if (a >= s || a / nb >= b / nb) return Loff + a + (int64_t)b * m;
-        return UToff + b + (int64_t)a * m;
+        if (a >= s || a / nb >= b / nb) return Loff + a + (int64_t)b * ld;
+        return UToff + b + (int64_t)a * ld;
     }
-    if (a < s) return UToff + b + (int64_t)a * m;
+    if (a < s) return UToff + b + (int64_t)a * ld;
     return F22off + (a - s) + (int64_t)(b - s) * (m - s);
 }
 
@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(256) k_extend_add(const AddTask* __restrict__ 
         if (a < tk.rc && b < tk.rc) {
             int rb = rl[b];
             v[q] = Cc[a + (int64_t)b * tk.rc];
-            d[q] = d_front_entry(ra, rb, tk.sp, tk.mp, nb, tk.Loff, tk.UToff, tk.F22off);
+            d[q] = d_front_entry(ra, rb, tk.sp, tk.mp, tk.ldp, nb, tk.Loff, tk.UToff, tk.F22off);
         }
     }
 #pragma unroll
@@ -561,7 +561,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS) k_fwd(const SolveTask* __restri
     __shared__ double tri[32 * 33];
     __shared__ double yb[32 * NR];
     const SolveTask tk = tasks[blockIdx.x];
-    const int s = tk.s, m = tk.m;
+    const int s = tk.s, m = tk.m, ld = tk.ld;
     double* w = W + tk.woff * nrtot;
     const double* L = heap + tk.Loff;
     // 1. load pivots' rhs, clear boundary part
@@ -587,7 +587,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS) k_fwd(const SolveTask* __restri
         const int kb = min(32, s - k0);
         for (int e = threadIdx.x; e < 32 * 32; e += SOLVE_THREADS) {
             int a = e & 31, p = e >> 5;
-            tri[a + p * 33] = (a < kb && p < kb && a > p) ? L[k0 + a + (int64_t)(k0 + p) * m] : 0.0;
+            tri[a + p * 33] = (a < kb && p < kb && a > p) ? L[k0 + a + (int64_t)(k0 + p) * ld] : 0.0;
         }
         __syncthreads();
         if (threadIdx.x < 32) {
@@ -615,9 +615,9 @@ __global__ void __launch_bounds__(SOLVE_THREADS) k_fwd(const SolveTask* __restri
             double acc[NR];
 #pragma unroll
             for (int c = 0; c < NR; c++) acc[c] = 0.0;
-            const double* Lp = L + a + (int64_t)k0 * m;
+            const double* Lp = L + a + (int64_t)k0 * ld;
             for (int p = 0; p < kb; p++) {
-                double l = Lp[(int64_t)p * m];
+                double l = Lp[(int64_t)p * ld];
 #pragma unroll
                 for (int c = 0; c < NR; c++) acc[c] += l * yb[p + 32 * c];
             }
@@ -640,7 +640,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS) k_bwd(const SolveTask* __restri
     __shared__ double tri[32 * 33];
     __shared__ double z[32 * NR];
     const SolveTask tk = tasks[blockIdx.x];
-    const int s = tk.s, m = tk.m;
+    const int s = tk.s, m = tk.m, ld = tk.ld;
     double* w = W + tk.woff * nrtot;
     const double* UT = heap + tk.UToff;
     const int* bi = bidx + tk.bidx_off;
@@ -661,7 +661,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS) k_bwd(const SolveTask* __restri
             double acc[NR];
 #pragma unroll
             for (int c = 0; c < NR; c++) acc[c] = 0.0;
-            const double* Up = UT + (int64_t)(k0 + p) * m;
+            const double* Up = UT + (int64_t)(k0 + p) * ld;
             for (int a = k1 + lane; a < m; a += 32) {
                 double u = Up[a];
 #pragma unroll
@@ -676,7 +676,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS) k_bwd(const SolveTask* __restri
         }
         for (int e = threadIdx.x; e < 32 * 32; e += SOLVE_THREADS) {
             int a = e & 31, p = e >> 5;   // tri[a + p*33] = UT[k0+a, k0+p] = U(p, a), a >= p
-            tri[a + p * 33] = (a < kb && p < kb && a >= p) ? UT[k0 + a + (int64_t)(k0 + p) * m] : 0.0;
+            tri[a + p * 33] = (a < kb && p < kb && a >= p) ? UT[k0 + a + (int64_t)(k0 + p) * ld] : 0.0;
         }
         __syncthreads();
         // (ii) back substitution in the 32 x 32 triangle (one warp): lane p owns x[p]
@@ -708,360 +708,415 @@ __global__ void __launch_bounds__(SOLVE_THREADS) k_bwd(const SolveTask* __restri
 }
 
 // ------------------------------------------------------------------------------------------
-// big fronts: many CTAs per front, flag-driven dataflow (launched cooperatively so that all
-// CTAs are co-resident; a CTA only ever waits on work items that precede its own in the
-// item list, which some running CTA is processing or has processed).
-//   forward : item = 64-row slab i.   w_i -= sum_{k<i} L[i,k] y_k ; pivot slabs then solve
-//             their 64x64 diagonal block and publish y_i (flag i).
-//   backward: item = 64-column pivot panel i, swept from the last panel down.
-//             z_i = y_i - sum_{rows below} UT[rows, i]^T x_rows ; x_i = U_ii^-1 z_i (flag i).
+// big fronts: many CTAs per front, counter-driven dataflow (launched cooperatively so that all
+// CTAs are co-resident; a CTA only ever waits on work items that precede its own in the item
+// list, which some running CTA is processing or has processed).
+//
+//   forward : item = 64-row slab i of L.        v_i = b_i - sum_{k<i} L[i,k] y_k ;  y_i = L_ii^-1 v_i
+//   backward: item = 64-column pivot panel i of U^T, swept from the last panel down.
+//             z_i = y_i - sum_{row blocks below} UT[rows, i]^T x_rows ;  x_i = U_ii^-1 z_i
+//
+// Both are streams of 64 x 64 tiles contracted with 64 x nrhs blocks of the running solution, and
+// both run on the FP64 tensor cores (DMMA m8n8k4, N = 8 right-hand sides): a warp owns 8 of the 64
+// contraction indices of every tile (columns of L / rows of U^T), fetches that 8 x 64 sub-tile
+// with cp.async into a warp-private shared-memory ring (no CTA barrier in the stream loop) and
+// keeps a 64 x 8 partial product in 16 registers; the eight partials are added once per item.
+// The diagonal blocks are stored INVERTED (k_invert_diag, after the factorisation), so the
+// triangular solve at the end of an item is one more 64 x 64 x 8 product instead of a 64-step
+// substitution: the dependency chain of a front has npiv links of a few microseconds each.
+// Progress is published through one 64-bit counter per front and direction: (epoch << 32 | blocks
+// done); the blocks of a front complete in order, so a consumer far behind the wavefront learns
+// about many finished blocks with one poll.
 // ------------------------------------------------------------------------------------------
 
-__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
-    int v;
-    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release_gpu(int* p, int v) {
-    asm volatile("st.release.gpu.global.s32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
+constexpr int SW_LD = 68;                   // column stride of a staged tile: == 4 (mod 16) -> conflict-free fragment
+                                            // loads in both directions, and room for 64 + 2 rows (alignment shift)
+constexpr int SW_ST = 3;                    // ring stages
+constexpr int SW_TILE = 64 * SW_LD;         // doubles per stage: tile[col * SW_LD + (row - aligned first row)]
+constexpr int SW_SMEM = SW_ST * SW_TILE * 8;   // dynamic shared memory per CTA (bytes): 2 CTAs per SM
+static_assert(SW_ST * SW_TILE >= 8 * 64 * 8, "the ring doubles as the buffer of the eight 64 x 8 partial sums");
+
+__device__ __forceinline__ void cp_async16_s(unsigned saddr, const void* gmem, int sz) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(saddr), "l"(gmem), "r"(sz));
 }
 
-template <int NR>
-__global__ void __launch_bounds__(256, 2) k_fwd_big(const BigFront* __restrict__ bfs, const BigItem* __restrict__ items,
-                                                 int nitems, const SolveChild* __restrict__ children,
-                                                 const int* __restrict__ rel, const double* __restrict__ heap,
-                                                 double* __restrict__ W, double* __restrict__ y, int n,
-                                                 int* __restrict__ flags, int epoch) {
-    __shared__ double buf[64 * 65];   // staged y of a batch, reduction scratch, then the diagonal block
-    __shared__ double ys[64 * NR];
-    __shared__ int s_nbat;
-    const int tid = threadIdx.x, row = tid & 63, cg = tid >> 6;
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];\n" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.gpu.global.u64 [%0], %1;\n" ::"l"(p), "l"(v) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
+
+// x boundary values of the big fronts of one level -> their work vectors (backward sweep):
+// w[s + a, c] = y[bidx[a], c].  grid (fronts, row chunks)
+__global__ void __launch_bounds__(256) k_gather_bnd(const BigFront* __restrict__ bfs, const int* __restrict__ bidx,
+                                                    const double* __restrict__ y, double* __restrict__ W, int n,
+                                                    int nr, int nrtot) {
+    const BigFront bf = bfs[blockIdx.x];
+    const int a = blockIdx.y * 256 + threadIdx.x;
+    if (a >= bf.r) return;
+    const int g = bidx[bf.bidx_off + a];
+    double* w = W + bf.woff * nrtot + bf.s + a;
+    for (int c = 0; c < nr; c++) w[(int64_t)c * bf.m] = y[g + (int64_t)c * n];
+}
+
+// MODE 0: forward sweep (slab items).
+// MODE 1: backward sweep, triangular part (panel items, pivot row blocks only); starts from
+//         y_i minus the partial products of the rectangular part.
+// MODE 2: backward sweep, rectangular part: item = (panel, chunk of BWD_CHUNK boundary row blocks);
+//         all inputs are known when the level starts, so these items are independent and equally
+//         sized; each stores its 64 x 8 partial product in a scratch slot (summed in a fixed order
+//         by the MODE 1 item of the panel: deterministic).
+enum { SWEEP_FWD = 0, SWEEP_BWD_TRI = 1, SWEEP_BWD_RECT = 2 };
+
+template <int MODE>
+__global__ void __launch_bounds__(256, 2) k_sweep_big(const BigFront* __restrict__ bfs, const BigItem* __restrict__ items,
+                                                      int nitems, const SolveChild* __restrict__ children,
+                                                      const int* __restrict__ rel, const double* __restrict__ heap,
+                                                      double* W, double* y, double* part, int n, int nr, int nrtot,
+                                                      unsigned long long* cnt, unsigned epoch) {
+    constexpr bool FWD = MODE == SWEEP_FWD;
+    constexpr bool RECT = MODE == SWEEP_BWD_RECT;
+    extern __shared__ __align__(16) double ring[];
+    __shared__ double bv[64 * 8];   // item start values b_i / y_i, then v_i / z_i : [entry * 8 + rhs]
+    __shared__ uint64_t full_bar[SW_ST], empty_bar[SW_ST];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, lr = lane >> 2, lc = lane & 3;
+    const unsigned ring_s = (unsigned)__cvta_generic_to_shared(ring);
+    if (tid == 0) {
+#pragma unroll
+        for (int q = 0; q < SW_ST; q++) {
+            mbar_init(&full_bar[q], 256);
+            mbar_init(&empty_bar[q], 256);
+        }
+    }
+    __syncthreads();
+    unsigned gbase = 0;   // tiles streamed by this CTA before the current item (ring position / barrier phase)
     for (int it = blockIdx.x; it < nitems; it += gridDim.x) {
         const BigItem item = items[it];
         const BigFront bf = bfs[item.front];
-        const int i = item.idx, s = bf.s, m = bf.m;
-        const bool pivot = i < bf.npiv;
-        const int r0 = pivot ? 64 * i : s + 64 * (i - bf.npiv);
-        const int nrow = min(64, (pivot ? s : m) - r0);
-        const int kmax = pivot ? i : bf.npiv;
-        const double* L = heap + bf.Loff;
-        double* w = W + bf.woff * NR;
-        double acc[NR];
+        const int s = bf.s, m = bf.m, ld = bf.ld;
+        const double* F = heap + (FWD ? bf.Loff : bf.UToff);
+        double* w = W + bf.woff * nrtot;
+        const unsigned long long* mycnt = cnt + item.front;
+        bool pivot = true;
+        int i = item.idx, r0, nrow, ntiles, tile0 = 0;
+        if (FWD) {
+            pivot = i < bf.npiv;
+            r0 = pivot ? 64 * i : s + 64 * (i - bf.npiv);
+            nrow = min(64, (pivot ? s : m) - r0);
+            ntiles = pivot ? i : bf.npiv;
+        } else if (RECT) {
+            const int chunk = item.idx % bf.nchunk;
+            i = item.idx / bf.nchunk;
+            tile0 = chunk * BWD_CHUNK;                       // first boundary row block of the chunk
+            ntiles = min(BWD_CHUNK, ((bf.r + 63) >> 6) - tile0);
+            r0 = 64 * i;
+            nrow = min(64, s - r0);
+        } else {
+            r0 = 64 * i;
+            nrow = min(64, s - r0);
+            ntiles = bf.npiv - 1 - i;
+        }
+        // ---- start values of the 64 out entries (kept in shared memory until the end of the item)
+        if (!RECT && tid < 64) {
+            double base[8];
 #pragma unroll
-        for (int c = 0; c < NR; c++) acc[c] = 0.0;
-        double lreg[16], treg[16];
-        if (pivot) {
+            for (int c = 0; c < 8; c++) base[c] = 0.0;
+            if (tid < nrow) {
+                if (pivot)
 #pragma unroll
-            for (int pp = 0; pp < 16; pp++) {
-                int p = cg * 16 + pp;
-                treg[pp] = (row < nrow && p < nrow && row > p) ? L[r0 + row + (int64_t)(r0 + p) * m] : 0.0;
+                    for (int c = 0; c < 8; c++)
+                        if (c < nr) base[c] = y[bf.first + r0 + tid + (int64_t)c * n];
+                if (FWD) {
+                    // children's update vectors (fixed order: deterministic).  rel[] of a child is
+                    // ascending, so the entry mapping to row r0+tid is found by bisection.
+                    const int target = r0 + tid;
+                    for (int ch = 0; ch < bf.nchild; ch++) {
+                        const SolveChild sc = children[bf.child_list + ch];
+                        const int* rl = rel + sc.rel_off;
+                        int lo = 0, hi = sc.r;
+                        while (lo < hi) {
+                            int mid = (lo + hi) >> 1;
+                            if (rl[mid] < target) lo = mid + 1;
+                            else hi = mid;
+                        }
+                        if (lo < sc.r && rl[lo] == target) {
+                            const int mc = sc.s + sc.r;
+                            const double* wc = W + sc.woff * nrtot + sc.s;
+#pragma unroll
+                            for (int c = 0; c < 8; c++)
+                                if (c < nr) base[c] += wc[lo + (int64_t)c * mc];
+                        }
+                    }
+                } else {
+                    // partial products of the rectangular part, chunk by chunk
+                    const double* pp = part + ((bf.part_off + (int64_t)i * bf.nchunk) * 64 + tid) * 8;
+                    for (int ch = 0; ch < bf.nchunk; ch++) {
+#pragma unroll
+                        for (int c = 0; c < 8; c++) base[c] -= pp[c];
+                        pp += 512;
+                    }
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < 8; c++) bv[tid * 8 + c] = base[c];
+        }
+        // ---- fragments of the inverted diagonal block for the final product: entry (p, q) with
+        //      p = 8 warp + lr (out), q = 4 ks + lc (contraction)
+        double ainv[16];
+        if (!RECT && pivot) {
+            const int p = 8 * warp + lr;
+#pragma unroll
+            for (int ks = 0; ks < 16; ks++) {
+                const int q = 4 * ks + lc;
+                double v = (p == q) ? 1.0 : 0.0;
+                if (p < nrow && q < nrow) {
+                    if (FWD) {
+                        if (p > q) v = F[r0 + p + (int64_t)(r0 + q) * ld];            // L_ii^-1 (unit lower)
+                    } else {
+                        v = q >= p ? F[r0 + q + (int64_t)(r0 + p) * ld] : 0.0;        // U_ii^-1 (upper), stored transposed
+                    }
+                }
+                ainv[ks] = v;
             }
         }
-        // initial value of this slab's rows: the pivots' right-hand side plus the children's
-        // update vectors (children in fixed order: deterministic).  rel[] of a child is
-        // ascending, so the entry mapping to row r0+tid is found by bisection.
-        double base[NR];
-#pragma unroll
-        for (int c = 0; c < NR; c++) base[c] = 0.0;
-        if (tid < nrow) {
-            if (pivot)
-#pragma unroll
-                for (int c = 0; c < NR; c++) base[c] = y[bf.first + r0 + tid + (int64_t)c * n];
-            const int target = r0 + tid;
-            for (int ch = 0; ch < bf.nchild; ch++) {
-                const SolveChild sc = children[bf.child_list + ch];
-                const int* rl = rel + sc.rel_off;
-                int lo = 0, hi = sc.r;
-                while (lo < hi) {
-                    int mid = (lo + hi) >> 1;
-                    if (rl[mid] < target) lo = mid + 1;
-                    else hi = mid;
+        // ---- tile stream.  Tile t covers rows [R0, R0 + nrows) x columns [C0, C0 + ncols) of F:
+        //        forward : R0 = r0 (out rows),          C0 = 64 t (contraction)
+        //        backward: R0 = row block (contraction), C0 = r0   (out columns)
+        auto tile_geom = [&](int t, int& R0, int& nrows, int& C0, int& ncols) {
+            if (FWD) {
+                R0 = r0;
+                nrows = nrow;
+                C0 = 64 * t;
+                ncols = min(64, s - C0);
+            } else {
+                if (RECT) {
+                    R0 = s + 64 * (tile0 + t);
+                    nrows = min(64, m - R0);
+                } else {
+                    R0 = 64 * (bf.npiv - 1 - t);
+                    nrows = min(64, s - R0);
                 }
-                if (lo < sc.r && rl[lo] == target) {
-                    const int mc = sc.s + sc.r;
-                    const double* wc = W + sc.woff * NR + sc.s;
-#pragma unroll
-                    for (int c = 0; c < NR; c++) base[c] += wc[lo + (int64_t)c * mc];
-                }
-            }
-        }
-        auto loadL = [&](int k) {
-            const int kb = min(64, s - 64 * k);
-#pragma unroll
-            for (int pp = 0; pp < 16; pp++) {
-                int p = cg * 16 + pp;
-                lreg[pp] = (row < nrow && p < kb) ? L[r0 + row + (int64_t)(64 * k + p) * m] : 0.0;
+                C0 = r0;
+                ncols = nrow;
             }
         };
-        if (kmax > 0) loadL(0);
-        // Pivot blocks are consumed in batches of FB when their solutions are already published
-        // (flags of one front are set in increasing order, so the last flag of the batch
-        // suffices); close to the wavefront the loop falls back to single blocks.
-        constexpr int FB = 4;
-        int k = 0;
-        while (k < kmax) {
-            if (tid == 0) {
-                int nbat = 1;
-                if (k + FB <= kmax && ld_acquire_gpu(&flags[bf.flag0 + k + FB - 1]) == epoch) nbat = FB;
-                else
-                    while (ld_acquire_gpu(&flags[bf.flag0 + k]) != epoch) __nanosleep(32);
-                s_nbat = nbat;
+        // The whole CTA stages the tile with 16-byte cp.async: a warp copies 512 contiguous bytes of
+        // one column per instruction.  Columns start 16-byte aligned (even ld), so the copy starts at
+        // the even row Ra <= R0 and the fragment loads skip `R0 - Ra` (0 or 1) rows.
+        auto issue = [&](int t) {
+            const unsigned g = gbase + (unsigned)t;
+            const int stg = g % SW_ST;
+            if (g >= SW_ST) mbar_wait(&empty_bar[stg], (g / SW_ST - 1) & 1);
+            int R0, nrows, C0, ncols;
+            tile_geom(t, R0, nrows, C0, ncols);
+            const int Ra = R0 & ~1;
+            const int nval = (R0 - Ra) + nrows;     // rows [Ra, Ra + nval) are wanted (the first may be a dummy)
+            const unsigned st = ring_s + (unsigned)(stg * SW_TILE * 8);
+            const int cr = tid & 31, cg = tid >> 5;
+            const int szr = 2 * cr + 1 < nval ? 16 : (2 * cr < nval ? 8 : 0);
+            const double* src = F + Ra + 2 * cr + (int64_t)(C0 + cg) * ld;
+            const unsigned dst = st + (unsigned)((cg * SW_LD + 2 * cr) * 8);
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const int sz = cg + 8 * j < ncols ? szr : 0;
+                cp_async16_s(dst + (unsigned)(8 * j * SW_LD * 8), sz ? src + (int64_t)(8 * j) * ld : F, sz);
             }
-            __syncthreads();
-            const int nbat = s_nbat;
-            for (int e = tid; e < nbat * 64 * NR; e += 256) {
-                int b = e / (64 * NR), rem = e - b * 64 * NR;
-                int p = rem & 63, c = rem >> 6;
-                int kk = k + b;
-                buf[e] = p < min(64, s - 64 * kk) ? __ldcg(&y[bf.first + 64 * kk + p + (int64_t)c * n]) : 0.0;
+            if (nval > 64 && tid < 64) {   // 33rd chunk of every column (odd first row)
+                const int sz = tid < ncols ? (65 < nval ? 16 : 8) : 0;
+                cp_async16_s(st + (unsigned)((tid * SW_LD + 64) * 8), sz ? F + Ra + 64 + (int64_t)(C0 + tid) * ld : F, sz);
             }
-            __syncthreads();
+            mbar_cp_async_arrive(&full_bar[stg]);
+        };
+        // B fragments of tile t: entry (q, rhs) with q = 8 warp + 4 ks + lc, rhs = lr
+        auto load_b = [&](int t, double* b) {
+            int R0, nrows, C0, ncols;
+            tile_geom(t, R0, nrows, C0, ncols);
 #pragma unroll
-            for (int b = 0; b < FB; b++) {
-                if (b < nbat) {
-                    if (b > 0) loadL(k + b);
-                    const double* yb = buf + b * 64 * NR;
+            for (int ks = 0; ks < 2; ks++) {
+                const int q = 8 * warp + 4 * ks + lc;
+                double v = 0.0;
+                if (FWD) {
+                    if (lr < nr && q < ncols) v = __ldcg(&y[bf.first + C0 + q + (int64_t)lr * n]);
+                } else if (lr < nr && q < nrows) {
+                    v = RECT ? __ldcg(&w[R0 + q + (int64_t)lr * m]) : __ldcg(&y[bf.first + R0 + q + (int64_t)lr * n]);
+                }
+                b[ks] = v;
+            }
+        };
+        // number of published blocks of this front (forward: y_0..; backward: x_{npiv-1}, ...)
+        auto poll = [&]() -> int {
+            unsigned long long v = 0;
+            if (lane == 0) v = ld_acquire_u64(mycnt);
+            v = __shfl_sync(0xffffffffu, v, 0);
+            return (unsigned)(v >> 32) == epoch ? (int)(unsigned)(v & 0xffffffffu) : 0;
+        };
+        double acc[8][2];
 #pragma unroll
-                    for (int pp = 0; pp < 16; pp++)
+        for (int g = 0; g < 8; g++) acc[g][0] = acc[g][1] = 0.0;
 #pragma unroll
-                        for (int c = 0; c < NR; c++) acc[c] += lreg[pp] * yb[cg * 16 + pp + 64 * c];
+        for (int q = 0; q < SW_ST - 1; q++)
+            if (q < ntiles) issue(q);
+        int ready = RECT ? (1 << 30) : 0;   // tile t needs `ready > t`
+        bool have_next = false;
+        double bn[2] = {0.0, 0.0};
+        for (int t = 0; t < ntiles; t++) {
+            double b[2];
+            if (have_next) {
+                b[0] = bn[0];
+                b[1] = bn[1];
+            } else {
+                if (ready <= t) {
+                    ready = poll();
+                    // the iteration cap turns a protocol bug into a trapped kernel instead of a hung GPU
+                    for (unsigned spins = 0; ready <= t; spins++) {
+                        __nanosleep(20);
+                        ready = poll();
+                        if (spins > (1u << 24)) __trap();
+                    }
+                }
+                load_b(t, b);
+            }
+            // prefetch the fragments of the next tile when its block is already published
+            have_next = false;
+            if (t + 1 < ntiles) {
+                if (ready <= t + 1) ready = poll();
+                if (ready > t + 1) {
+                    load_b(t + 1, bn);
+                    have_next = true;
                 }
             }
-            k += nbat;
-            if (k < kmax) loadL(k);
-            __syncthreads();
-        }
-        // reduce the four column groups
+            const unsigned g = gbase + (unsigned)t;
+            const int stg = g % SW_ST;
+            mbar_wait(&full_bar[stg], (g / SW_ST) & 1);
+            if (t + SW_ST - 1 < ntiles) issue(t + SW_ST - 1);
+            int R0, nrows, C0, ncols;
+            tile_geom(t, R0, nrows, C0, ncols);
+            const double* st = ring + stg * SW_TILE + (R0 & 1);
 #pragma unroll
-        for (int c = 0; c < NR; c++) buf[(cg * 64 + row) * NR + c] = acc[c];
-        __syncthreads();
-        double val[NR];
-        if (tid < 64) {
+            for (int ks = 0; ks < 2; ks++) {
+                const int kq = 8 * warp + 4 * ks + lc;   // contraction index inside the tile
+                double af[8];
 #pragma unroll
-            for (int c = 0; c < NR; c++) {
-                double sum = buf[(0 * 64 + tid) * NR + c] + buf[(1 * 64 + tid) * NR + c] + buf[(2 * 64 + tid) * NR + c] +
-                             buf[(3 * 64 + tid) * NR + c];
-                val[c] = tid < nrow ? base[c] - sum : 0.0;
+                for (int g2 = 0; g2 < 8; g2++)
+                    af[g2] = FWD ? st[kq * SW_LD + 8 * g2 + lr] : st[(8 * g2 + lr) * SW_LD + kq];
+#pragma unroll
+                for (int g2 = 0; g2 < 8; g2++) dmma884(acc[g2][0], acc[g2][1], af[g2], b[ks]);
             }
+            mbar_arrive(&empty_bar[stg]);
         }
-        if (!pivot) {
-            if (tid < nrow)
+        gbase += (unsigned)ntiles;
+        __syncthreads();   // every warp has finished reading the ring
+        // ---- add the eight partial products (staged in the idle ring)
+        double* myred = ring + warp * 512;
 #pragma unroll
-                for (int c = 0; c < NR; c++) w[r0 + tid + (int64_t)c * m] = val[c];
-            __syncthreads();
-            continue;
+        for (int g = 0; g < 8; g++) {
+            myred[(8 * g + lr) * 8 + 2 * lc] = acc[g][0];
+            myred[(8 * g + lr) * 8 + 2 * lc + 1] = acc[g][1];
         }
         __syncthreads();
 #pragma unroll
-        for (int pp = 0; pp < 16; pp++) buf[row + 65 * (cg * 16 + pp)] = treg[pp];
-        if (tid < 64)
+        for (int h = 0; h < 2; h++) {
+            const int e = tid + 256 * h;
+            double sum = 0.0;
 #pragma unroll
-            for (int c = 0; c < NR; c++) ys[tid + 64 * c] = val[c];
-        __syncthreads();
-        if (tid < 32) {   // rows 0..31
-            double v[NR];
-#pragma unroll
-            for (int c = 0; c < NR; c++) v[c] = ys[tid + 64 * c];
-            for (int p = 0; p < 32; p++) {
-                double l = buf[tid + 65 * p];
-#pragma unroll
-                for (int c = 0; c < NR; c++) {
-                    double yp = __shfl_sync(0xffffffffu, v[c], p);
-                    v[c] -= l * yp;
+            for (int q = 0; q < 8; q++) sum += ring[q * 512 + e];
+            if (RECT) {
+                part[(bf.part_off + item.idx) * 512 + e] = sum;
+            } else {
+                const double v = bv[e] - sum;
+                if (pivot) bv[e] = v;
+                else {
+                    const int a = e >> 3, c = e & 7;
+                    if (a < nrow && c < nr) w[r0 + a + (int64_t)c * m] = v;
                 }
             }
-#pragma unroll
-            for (int c = 0; c < NR; c++) ys[tid + 64 * c] = v[c];
         }
         __syncthreads();
-        if (tid >= 32 && tid < 64) {   // rows 32..63
-            const int a = tid;
-            double v[NR];
+        if (RECT || !pivot) continue;
+        // ---- out = D_ii^-1 v : warp computes entries 8 warp .. 8 warp + 7
+        double c4[4][2];
 #pragma unroll
-            for (int c = 0; c < NR; c++) v[c] = ys[a + 64 * c];
-            for (int p = 0; p < 32; p++) {
-                double l = buf[a + 65 * p];
+        for (int q = 0; q < 4; q++) c4[q][0] = c4[q][1] = 0.0;
 #pragma unroll
-                for (int c = 0; c < NR; c++) v[c] -= l * ys[p + 64 * c];
-            }
-            for (int p = 0; p < 32; p++) {
-                double l = buf[a + 65 * (32 + p)];
-#pragma unroll
-                for (int c = 0; c < NR; c++) {
-                    double yp = __shfl_sync(0xffffffffu, v[c], p);
-                    v[c] -= l * yp;
-                }
-            }
-#pragma unroll
-            for (int c = 0; c < NR; c++) ys[a + 64 * c] = v[c];
-        }
-        __syncthreads();
-        for (int e = tid; e < 64 * NR; e += 256) {
-            int a = e & 63, c = e >> 6;
-            if (a < nrow) y[bf.first + r0 + a + (int64_t)c * n] = ys[e];
+        for (int ks = 0; ks < 16; ks++) dmma884(c4[ks & 3][0], c4[ks & 3][1], ainv[ks], bv[(4 * ks + lc) * 8 + lr]);
+        const double o0 = (c4[0][0] + c4[1][0]) + (c4[2][0] + c4[3][0]);
+        const double o1 = (c4[0][1] + c4[1][1]) + (c4[2][1] + c4[3][1]);
+        const int p = 8 * warp + lr;
+        if (p < nrow) {
+            if (2 * lc < nr) y[bf.first + r0 + p + (int64_t)(2 * lc) * n] = o0;
+            if (2 * lc + 1 < nr) y[bf.first + r0 + p + (int64_t)(2 * lc + 1) * n] = o1;
         }
         __threadfence();
         __syncthreads();
-        if (tid == 0) st_release_gpu(&flags[bf.flag0 + i], epoch);
+        if (tid == 0)
+            st_release_u64(cnt + item.front, ((unsigned long long)epoch << 32) | (unsigned)(FWD ? i + 1 : bf.npiv - i));
     }
 }
 
-template <int NR>
-__global__ void __launch_bounds__(256, 2) k_bwd_big(const BigFront* __restrict__ bfs, const BigItem* __restrict__ items,
-                                                 int nitems, const int* __restrict__ bidx,
-                                                 const double* __restrict__ heap, double* __restrict__ y, int n,
-                                                 int* __restrict__ flags, int epoch) {
-    __shared__ double tile[64 * 65];
-    __shared__ double xs[64 * NR];
-    const int tid = threadIdx.x, lo = tid & 63, hi = tid >> 6;
-    for (int it = blockIdx.x; it < nitems; it += gridDim.x) {
-        const BigItem item = items[it];
-        const BigFront bf = bfs[item.front];
-        const int i = item.idx, s = bf.s, m = bf.m;
-        const int c0 = 64 * i;
-        const int kb = min(64, s - c0);
-        const double* UT = heap + bf.UToff;
-        const int* bi = bidx + bf.bidx_off;
-        double acc[NR];
-#pragma unroll
-        for (int c = 0; c < NR; c++) acc[c] = 0.0;
-        double dreg[16], treg[16];
-        // diagonal block UT[c0+a, c0+p] = U(p,a), a >= p
-#pragma unroll
-        for (int pp = 0; pp < 16; pp++) {
-            int p = hi * 16 + pp;
-            dreg[pp] = (lo < kb && p < kb && lo >= p) ? UT[c0 + lo + (int64_t)(c0 + p) * m] : 0.0;
-        }
-        const int nbb = (bf.r + 63) / 64;
-        const int nblk = nbb + (bf.npiv - 1 - i);
-        for (int b = 0; b < nblk; b++) {
-            int a0, na, waitk;
-            if (b < nbb) {
-                a0 = s + 64 * b;
-                na = min(64, m - a0);
-                waitk = -1;
-            } else {
-                waitk = bf.npiv - 1 - (b - nbb);
-                a0 = 64 * waitk;
-                na = min(64, s - a0);
-            }
-#pragma unroll
-            for (int pp = 0; pp < 16; pp++) {
-                int p = hi * 16 + pp;
-                treg[pp] = (lo < na && p < kb) ? UT[a0 + lo + (int64_t)(c0 + p) * m] : 0.0;
-            }
-            // x of this row block: boundary rows are final (solution of an ancestor) and can be
-            // fetched together with the tile; pivot rows only after their panel has published
-            constexpr int XR = (64 * NR + 255) / 256;
-            double xreg[XR];
-            auto load_x = [&]() {
-#pragma unroll
-                for (int q = 0; q < XR; q++) {
-                    int e = tid + q * 256;
-                    int a = e & 63, c = e >> 6;
-                    double xv = 0.0;
-                    if (e < 64 * NR && a < na) {
-                        int g = waitk < 0 ? bi[a0 - s + a] : bf.first + a0 + a;
-                        xv = __ldcg(&y[g + (int64_t)c * n]);
-                    }
-                    xreg[q] = xv;
+// In-place inversion of the 64 x 64 diagonal blocks of the big fronts, after the factorisation:
+// strictly lower part of the Larr block <- strictly lower part of L_kk^-1 (unit diagonal implied),
+// lower part of the UTarr block <- (U_kk^-1)^T.  grid (blocks, 2): y = 0 inverts L_kk, y = 1 U_kk;
+// 64 threads, one column of the inverse each.
+constexpr int INV_SMEM = 2 * 64 * 65 * 8;
+
+__global__ void __launch_bounds__(64) k_invert_diag(const DiagTask* __restrict__ tasks, double* __restrict__ heap) {
+    extern __shared__ __align__(16) double ism[];
+    double* T = ism;             // the triangle
+    double* X = ism + 64 * 65;   // its inverse
+    const DiagTask tk = tasks[blockIdx.x];
+    const int kb = tk.kb, ld = tk.ld;
+    const bool lower = blockIdx.y == 0;
+    double* G = heap + (lower ? tk.Doff : tk.UTDoff);
+    for (int e = threadIdx.x; e < 64 * 64; e += 64) {
+        int a = e & 63, b = e >> 6;
+        // lower: T[a + 65 b] = L(a,b), a > b.   upper: T[a + 65 b] = U(b,a), a >= b (as stored)
+        bool ok = a < kb && b < kb && (lower ? a > b : a >= b);
+        T[a + 65 * b] = ok ? G[a + (int64_t)b * ld] : 0.0;
+    }
+    __syncthreads();
+    const int j = threadIdx.x;
+    if (j < kb) {
+        if (lower) {
+            X[j + 65 * j] = 1.0;
+            for (int i2 = j + 1; i2 < kb; i2++) {
+                double a0 = 0.0, a1 = 0.0;
+                for (int p = j; p < i2; p++) {
+                    double t = T[i2 + 65 * p] * X[p + 65 * j];
+                    if (p & 1) a1 += t;
+                    else a0 += t;
                 }
-            };
-            if (waitk < 0) load_x();
-            if (waitk >= 0 && tid == 0)
-                while (ld_acquire_gpu(&flags[bf.flag0 + waitk]) != epoch) __nanosleep(32);
-            __syncthreads();
-            if (waitk >= 0) load_x();
-#pragma unroll
-            for (int pp = 0; pp < 16; pp++) tile[lo + 65 * (hi * 16 + pp)] = treg[pp];
-#pragma unroll
-            for (int q = 0; q < XR; q++) {
-                int e = tid + q * 256;
-                if (e < 64 * NR) xs[e] = xreg[q];
+                X[i2 + 65 * j] = -(a0 + a1);
             }
-            __syncthreads();
-            // thread (column lo, row group hi)
-#pragma unroll
-            for (int rr = 0; rr < 16; rr++) {
-                int a = hi * 16 + rr;
-                double u = tile[a + 65 * lo];
-#pragma unroll
-                for (int c = 0; c < NR; c++) acc[c] += u * xs[a + 64 * c];
-            }
-        }
-        __syncthreads();
-#pragma unroll
-        for (int c = 0; c < NR; c++) tile[(hi * 64 + lo) * NR + c] = acc[c];
-        __syncthreads();
-        double z[NR];
-        if (tid < 64) {
-#pragma unroll
-            for (int c = 0; c < NR; c++) {
-                double sum = tile[(0 * 64 + tid) * NR + c] + tile[(1 * 64 + tid) * NR + c] + tile[(2 * 64 + tid) * NR + c] +
-                             tile[(3 * 64 + tid) * NR + c];
-                z[c] = tid < kb ? y[bf.first + c0 + tid + (int64_t)c * n] - sum : 0.0;
-            }
-        }
-        __syncthreads();
-#pragma unroll
-        for (int pp = 0; pp < 16; pp++) tile[lo + 65 * (hi * 16 + pp)] = dreg[pp];   // tile[a + 65 p] = U(p, a)
-        if (tid < 64)
-#pragma unroll
-            for (int c = 0; c < NR; c++) xs[tid + 64 * c] = z[c];
-        __syncthreads();
-        if (tid >= 32 && tid < 64) {   // unknowns 32..63 first
-            const int p = tid, lane = tid - 32;
-            double v[NR];
-#pragma unroll
-            for (int c = 0; c < NR; c++) v[c] = xs[p + 64 * c];
-            const double d = tile[p + 65 * p];
-            const double dinv = p < kb ? 1.0 / d : 0.0;
-            for (int q = 63; q >= 32; q--) {
-                double u = tile[q + 65 * p];
-#pragma unroll
-                for (int c = 0; c < NR; c++) {
-                    if (p == q) v[c] *= dinv;
-                    double xq = __shfl_sync(0xffffffffu, v[c], q - 32);
-                    if (p < q) v[c] -= u * xq;
+        } else {
+            X[j + 65 * j] = 1.0 / T[j + 65 * j];
+            for (int i2 = j - 1; i2 >= 0; i2--) {
+                double a0 = 0.0, a1 = 0.0;
+                for (int p = i2 + 1; p <= j; p++) {
+                    double t = T[p + 65 * i2] * X[p + 65 * j];   // U(i2,p) V(p,j)
+                    if (p & 1) a1 += t;
+                    else a0 += t;
                 }
+                X[i2 + 65 * j] = -(a0 + a1) / T[i2 + 65 * i2];
             }
-            (void)lane;
-#pragma unroll
-            for (int c = 0; c < NR; c++) xs[p + 64 * c] = v[c];
         }
-        __syncthreads();
-        if (tid < 32) {
-            const int p = tid;
-            double v[NR];
-#pragma unroll
-            for (int c = 0; c < NR; c++) v[c] = xs[p + 64 * c];
-            for (int q = 32; q < 64; q++) {
-                double u = tile[q + 65 * p];
-#pragma unroll
-                for (int c = 0; c < NR; c++) v[c] -= u * xs[q + 64 * c];
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < 64 * 64; e += 64) {
+        int a = e & 63, b = e >> 6;
+        if (a < kb && b < kb) {
+            if (lower) {
+                if (a > b) G[a + (int64_t)b * ld] = X[a + 65 * b];
+            } else if (a >= b) {
+                G[a + (int64_t)b * ld] = X[b + 65 * a];   // (U^-1)(b,a), stored transposed
             }
-            const double d = tile[p + 65 * p];
-            const double dinv = p < kb ? 1.0 / d : 0.0;
-            for (int q = 31; q >= 0; q--) {
-                double u = tile[q + 65 * p];
-#pragma unroll
-                for (int c = 0; c < NR; c++) {
-                    if (p == q) v[c] *= dinv;
-                    double xq = __shfl_sync(0xffffffffu, v[c], q);
-                    if (p < q) v[c] -= u * xq;
-                }
-            }
-#pragma unroll
-            for (int c = 0; c < NR; c++) xs[p + 64 * c] = v[c];
         }
-        __syncthreads();
-        for (int e = tid; e < 64 * NR; e += 256) {
-            int a = e & 63, c = e >> 6;
-            if (a < kb) y[bf.first + c0 + a + (int64_t)c * n] = xs[e];
-        }
-        __threadfence();
-        __syncthreads();
-        if (tid == 0) st_release_gpu(&flags[bf.flag0 + i], epoch);
     }
 }
 

@@ -8,11 +8,11 @@
 // multifrontal LU + triangular solves + refinement on the GPU.
 //
 // Storage layout of one front t (s pivots, r boundary rows/cols, m = s + r):
-//   Larr  : m x s column-major (ld = m).  Holds every entry (a,b) of the front with
+//   Larr  : m x s column-major (ld = m rounded up to even, so every column starts 16-byte aligned).  Holds every entry (a,b) of the front with
 //           b < s and (a >= s or blk(a) >= blk(b)), i.e. the block-lower part
 //           including the full nb x nb diagonal blocks.  After factorisation:
 //           L (unit lower) below the diagonal blocks, packed LU in the diagonal blocks.
-//   UTarr : m x s column-major (ld = m).  Holds U TRANSPOSED: entry (a,b) of the front
+//   UTarr : m x s column-major (same ld).  Holds U TRANSPOSED: entry (a,b) of the front
 //           with a < s and (b >= s or blk(b) > blk(a)) is stored at UTarr[b + a*m].
 //           After factorisation the diagonal blocks additionally receive U_kk^T, so the
 //           backward solve reads UTarr only.
@@ -32,6 +32,7 @@ struct Front {
     int s = 0;           // number of pivots
     int r = 0;           // boundary size
     int m = 0;           // s + r
+    int ld = 0;          // leading dimension of Larr / UTarr: m rounded up to even (16-byte aligned columns)
     int parent = -1;
     int level = 0;       // depth from the root (roots are level 0)
     int child_rank = 0;  // position among the parent's children (extend-add pass)
@@ -87,7 +88,7 @@ struct AddTask {    // extend-add a child's update matrix into its parent front
     int sp, mp;     // parent pivots / size
     int tile0;
     int tiles_m;
-    int pad;
+    int ldp;        // leading dimension of the parent's Larr / UTarr
 };
 
 struct SolveTask {  // one front in a forward / backward sweep
@@ -98,7 +99,8 @@ struct SolveTask {  // one front in a forward / backward sweep
     int64_t child_list;   // offset into Plan::solve_children
     int first, s, r, m;
     int nchild;
-    int pad;
+    int ld;               // leading dimension of Larr / UTarr
+    int big;              // 1: swept by the multi-CTA dataflow kernels (diagonal blocks are stored inverted)
 };
 
 struct SolveChild {
@@ -116,7 +118,12 @@ struct BigFront {
     int flag0;   // first flag of this front (one per pivot block)
     int nchild;
     int64_t child_list;  // into Plan::solve_children
+    int64_t part_off;    // backward sweep: first 64 x 8 partial-product slot of this front (level scratch)
+    int nchunk;          // backward sweep: chunks of BWD_CHUNK boundary row blocks per pivot panel
+    int ld;              // leading dimension of Larr / UTarr (even)
 };
+
+constexpr int BWD_CHUNK = 16;   // 64-row blocks of the boundary per item of the rectangular part
 
 struct BigItem {
     int front;   // index into Plan::big_fronts
@@ -151,6 +158,7 @@ struct LevelPlan {
     int big_begin = 0, big_end = 0;      // into Plan::big_fronts
     int fwd_item_begin = 0, fwd_item_end = 0;  // into Plan::big_fwd_items
     int bwd_item_begin = 0, bwd_item_end = 0;  // into Plan::big_bwd_items
+    int rect_item_begin = 0, rect_item_end = 0;  // into Plan::big_rect_items (idx = panel * nchunk + chunk)
 };
 
 struct Options {
@@ -187,7 +195,9 @@ struct Plan {
     std::vector<SolveChild> solve_children;
     std::vector<SolveTask> solve_small;   // the non-big subset, grouped by level like solve_tasks
     std::vector<BigFront> big_fronts;
-    std::vector<BigItem> big_fwd_items, big_bwd_items;
+    std::vector<BigItem> big_fwd_items, big_bwd_items, big_rect_items;
+    int64_t bwd_part_slots = 0;           // 64 x 8 partial-product slots needed by the largest level
+    std::vector<DiagTask> inv_tasks;      // diagonal blocks of the big fronts: inverted in place after the factorisation
     int n_big_flags = 0;
     int64_t factor_len = 0;    // doubles in the factor arena  [0, factor_len)
     int64_t pool_len[2] = {0, 0};  // update-matrix pools follow the arena
@@ -218,13 +228,13 @@ int analyse(int n, const int* rowptr, const int* colind, const int* const coords
 inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
 
 // where does entry (a,b) of a front live?  returns heap offset
-inline int64_t front_entry(int a, int b, int s, int m, int nb,
+inline int64_t front_entry(int a, int b, int s, int m, int ld, int nb,
                            int64_t Loff, int64_t UToff, int64_t F22off) {
     if (b < s) {
-        if (a >= s || a / nb >= b / nb) return Loff + a + (int64_t)b * m;
-        return UToff + b + (int64_t)a * m;
+        if (a >= s || a / nb >= b / nb) return Loff + a + (int64_t)b * ld;
+        return UToff + b + (int64_t)a * ld;
     }
-    if (a < s) return UToff + b + (int64_t)a * m;
+    if (a < s) return UToff + b + (int64_t)a * ld;
     return F22off + (a - s) + (int64_t)(b - s) * (m - s);
 }
 

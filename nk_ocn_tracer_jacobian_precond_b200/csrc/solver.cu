@@ -129,7 +129,10 @@ struct nkp_solver {
     BigFront* d_big = nullptr;
     BigItem* d_fwd_items = nullptr;
     BigItem* d_bwd_items = nullptr;
-    int* d_flags = nullptr;     // [0, nflags): forward, [nflags, 2 nflags): backward
+    BigItem* d_rect_items = nullptr;
+    double* d_part = nullptr;   // 64 x 8 partial products of the backward sweep's rectangular part
+    unsigned long long* d_cnt = nullptr;  // progress counters of the big fronts: [0, nbig) forward, [nbig, 2 nbig) backward
+    DiagTask* d_inv = nullptr;            // diagonal blocks inverted after the factorisation
     int epoch = 0;
     int coop_ctas = 0;          // co-resident CTAs for the dataflow sweeps
     ncclComm_t comm = nullptr;  // multi-GPU only
@@ -306,15 +309,22 @@ static int create_impl(nkp_solver** out, int n, const int* rowptr, const int* co
         if (upload(&s->d_big, P.big_fronts)) return NKP_ECUDA;
         if (upload(&s->d_fwd_items, P.big_fwd_items)) return NKP_ECUDA;
         if (upload(&s->d_bwd_items, P.big_bwd_items)) return NKP_ECUDA;
-        CK(cudaMalloc((void**)&s->d_flags, sizeof(int) * (size_t)(2 * P.n_big_flags + 2)));
-        CK(cudaMemset(s->d_flags, 0, sizeof(int) * (size_t)(2 * P.n_big_flags + 2)));
+        if (upload(&s->d_rect_items, P.big_rect_items)) return NKP_ECUDA;
+        CK(cudaMalloc((void**)&s->d_part, sizeof(double) * 512 * (size_t)std::max<int64_t>(P.bwd_part_slots, 1)));
+        if (upload(&s->d_inv, P.inv_tasks)) return NKP_ECUDA;
+        CK(cudaMalloc((void**)&s->d_cnt, sizeof(unsigned long long) * (2 * P.big_fronts.size() + 2)));
+        CK(cudaMemset(s->d_cnt, 0, sizeof(unsigned long long) * (2 * P.big_fronts.size() + 2)));
         {
             cudaDeviceProp prop;
             CK(cudaGetDeviceProperties(&prop, o.device));
             int occ = 0, minocc = 1 << 30;
-            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_fwd_big<8>, 256, 0));
+            CK(cudaFuncSetAttribute(k_sweep_big<SWEEP_FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, SW_SMEM));
+            CK(cudaFuncSetAttribute(k_sweep_big<SWEEP_BWD_TRI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SW_SMEM));
+            CK(cudaFuncSetAttribute(k_sweep_big<SWEEP_BWD_RECT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SW_SMEM));
+            CK(cudaFuncSetAttribute(k_invert_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, INV_SMEM));
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sweep_big<SWEEP_FWD>, 256, SW_SMEM));
             minocc = std::min(minocc, occ);
-            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_bwd_big<8>, 256, 0));
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sweep_big<SWEEP_BWD_TRI>, 256, SW_SMEM));
             minocc = std::min(minocc, occ);
             if (!prop.cooperativeLaunch || minocc < 1) {
                 g_err = "device cannot run the cooperative dataflow sweeps";
@@ -461,6 +471,12 @@ static int do_factor(nkp_solver* s) {
             }
         }
     }
+    // the dataflow sweeps use inverted diagonal blocks (part of the factorisation time)
+    if (!P.inv_tasks.empty()) {
+        k_invert_diag<<<dim3((unsigned)P.inv_tasks.size(), 2), 64, INV_SMEM, st>>>(s->d_inv, s->heap);
+        s->launches++;
+        prof_mark(s, KC_DIAG);
+    }
     CK(cudaEventRecord(s->ev[2], st));
     CK(cudaGetLastError());
     int nrepl = 0;
@@ -529,8 +545,10 @@ static int sweeps(nkp_solver* s) {
         tname.push_back(b);
     };
     mark("start", -1, 0);
-    int* flags_f = s->d_flags;
-    int* flags_b = s->d_flags + P.n_big_flags;
+    unsigned long long* cnt_f = s->d_cnt;
+    unsigned long long* cnt_b = s->d_cnt + P.big_fronts.size();
+    unsigned uepoch = (unsigned)epoch;
+    int nr = NR, nrtot = NR;
     const double* heap = s->heap;
     for (int l = P.nlevels - 1; l >= 0; l--) {
         const LevelPlan& L = P.levels[l];
@@ -567,10 +585,11 @@ static int sweeps(nkp_solver* s) {
             const int* rel = s->d_rel;
             double* W = s->d_W;
             double* y = s->d_y;
-            void* args[] = {(void*)&bfs, (void*)&items, (void*)&nitems, (void*)&ch,      (void*)&rel,  (void*)&heap,
-                            (void*)&W,   (void*)&y,     (void*)&n,      (void*)&flags_f, (void*)&epoch};
+            double* part = s->d_part;
+            void* args[] = {(void*)&bfs, (void*)&items, (void*)&nitems, (void*)&ch, (void*)&rel,   (void*)&heap,  (void*)&W,
+                            (void*)&y,   (void*)&part,  (void*)&n,      (void*)&nr, (void*)&nrtot, (void*)&cnt_f, (void*)&uepoch};
             int grid = std::min(nitems, s->coop_ctas);
-            CK(cudaLaunchCooperativeKernel((void*)k_fwd_big<NR>, dim3(grid), dim3(256), args, 0, st));
+            CK(cudaLaunchCooperativeKernel((void*)k_sweep_big<SWEEP_FWD>, dim3(grid), dim3(256), args, SW_SMEM, st));
             s->launches++;
             mark("fwd big", l, nitems);
         }
@@ -588,12 +607,32 @@ static int sweeps(nkp_solver* s) {
         if (nitems > 0) {
             const BigFront* bfs = s->d_big;
             const BigItem* items = s->d_bwd_items + L.bwd_item_begin;
-            const int* bidx = s->d_bidx;
+            const SolveChild* ch = s->d_children;
+            const int* rel = s->d_rel;
+            double* W = s->d_W;
             double* y = s->d_y;
-            void* args[] = {(void*)&bfs, (void*)&items, (void*)&nitems, (void*)&bidx, (void*)&heap,
-                            (void*)&y,   (void*)&n,     (void*)&flags_b, (void*)&epoch};
+            // boundary values of the level's big fronts -> their work vectors
+            int maxr = 0;
+            for (int b = L.big_begin; b < L.big_end; b++) maxr = std::max(maxr, P.big_fronts[b].r);
+            if (maxr > 0) {
+                k_gather_bnd<<<dim3(L.big_end - L.big_begin, (maxr + 255) / 256), 256, 0, st>>>(
+                    s->d_big + L.big_begin, s->d_bidx, s->d_y, s->d_W, n, nr, nrtot);
+                s->launches++;
+            }
+            double* part = s->d_part;
+            int nrect = L.rect_item_end - L.rect_item_begin;
+            if (nrect > 0) {
+                // rectangular part: independent items, plain launch
+                k_sweep_big<SWEEP_BWD_RECT><<<std::min(nrect, 8 * s->coop_ctas), 256, SW_SMEM, st>>>(
+                    s->d_big, s->d_rect_items + L.rect_item_begin, nrect, ch, rel, heap, W, y, part, n, nr, nrtot, cnt_b,
+                    uepoch);
+                s->launches++;
+                mark("bwd rect", l, nrect);
+            }
+            void* args[] = {(void*)&bfs, (void*)&items, (void*)&nitems, (void*)&ch, (void*)&rel,   (void*)&heap,  (void*)&W,
+                            (void*)&y,   (void*)&part,  (void*)&n,      (void*)&nr, (void*)&nrtot, (void*)&cnt_b, (void*)&uepoch};
             int grid = std::min(nitems, s->coop_ctas);
-            CK(cudaLaunchCooperativeKernel((void*)k_bwd_big<NR>, dim3(grid), dim3(256), args, 0, st));
+            CK(cudaLaunchCooperativeKernel((void*)k_sweep_big<SWEEP_BWD_TRI>, dim3(grid), dim3(256), args, SW_SMEM, st));
             s->launches++;
             mark("bwd big", l, nitems);
         }
@@ -857,7 +896,7 @@ void nkp_destroy(nkp_solver* s) {
                     s->d_bidx, s->d_rel,    s->d_R,      s->d_C,      s->d_diag, s->d_trsm,    s->d_gemm,
                     s->d_add,  s->d_solve,  s->d_children, s->d_W,    s->d_y,    s->d_r,       s->d_x,
                     s->d_xb,   s->d_berr,   s->d_nrepl,  s->d_small,  s->d_big,  s->d_fwd_items, s->d_bwd_items,
-                    s->d_flags};
+                    s->d_cnt,  s->d_inv,    s->d_rect_items, s->d_part};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (s->h_pinned) cudaFreeHost(s->h_pinned);

@@ -99,9 +99,40 @@ void sim_add(double* H, const AddTask& t, const int* rel, int nb) {
     const int* rl = rel + t.rel_off;
     for (int b = 0; b < t.rc; b++)
         for (int a = 0; a < t.rc; a++) {
-            int64_t dst = front_entry(rl[a], rl[b], t.sp, t.mp, nb, t.Loff, t.UToff, t.F22off);
+            int64_t dst = front_entry(rl[a], rl[b], t.sp, t.mp, t.ldp, nb, t.Loff, t.UToff, t.F22off);
             H[dst] += C[a + (int64_t)b * t.rc];
         }
+}
+
+// In-place inversion of the nb x nb diagonal blocks of the fronts swept by the multi-CTA dataflow
+// kernels (k_invert_diag): the strictly lower part of the Larr diagonal block receives the strictly
+// lower part of L_kk^-1 (unit diagonal implied), the lower part of the UTarr diagonal block
+// receives (U_kk^-1)^T.
+void sim_invert_diag(double* H, const DiagTask& t) {
+    int ld = t.ld, kb = t.kb;
+    double* D = H + t.Doff;
+    double* UD = H + t.UTDoff;
+    std::vector<double> X((size_t)kb * kb, 0.0), V((size_t)kb * kb, 0.0);
+    for (int j = 0; j < kb; j++) {   // column j of L^-1
+        X[j + (size_t)j * kb] = 1.0;
+        for (int i = j + 1; i < kb; i++) {
+            double acc = 0;
+            for (int p = j; p < i; p++) acc += D[i + (int64_t)p * ld] * X[p + (size_t)j * kb];
+            X[i + (size_t)j * kb] = -acc;
+        }
+    }
+    for (int j = 0; j < kb; j++) {   // column j of U^-1 (upper), U(p,q) = UD[q + p*ld]
+        V[j + (size_t)j * kb] = 1.0 / UD[j + (int64_t)j * ld];
+        for (int i = j - 1; i >= 0; i--) {
+            double acc = 0;
+            for (int p = i + 1; p <= j; p++) acc += UD[p + (int64_t)i * ld] * V[p + (size_t)j * kb];
+            V[i + (size_t)j * kb] = -acc / UD[i + (int64_t)i * ld];
+        }
+    }
+    for (int j = 0; j < kb; j++)
+        for (int i = j + 1; i < kb; i++) D[i + (int64_t)j * ld] = X[i + (size_t)j * kb];
+    for (int b = 0; b < kb; b++)
+        for (int a = b; a < kb; a++) UD[a + (int64_t)b * ld] = V[b + (size_t)a * kb];
 }
 
 }  // namespace
@@ -124,7 +155,7 @@ int nkp_sim_run_dist(int n, const int* rowptr, const int* colind, const double* 
     if (getenv("NKP_OUTER")) opt.outer = atoi(getenv("NKP_OUTER"));
     if (getenv("NKP_SIM_TM")) opt.tm = atoi(getenv("NKP_SIM_TM"));
     if (getenv("NKP_SIM_TN")) opt.tn = atoi(getenv("NKP_SIM_TN"));
-    opt.verbose = getenv("NKP_SIM_VERBOSE") ? 1 : 0;
+    opt.verbose = getenv("NKP_SIM_VERBOSE") ? atoi(getenv("NKP_SIM_VERBOSE")) : 0;
     opt.nranks = nranks;
     const int* coords[3] = {ci, cj, ck};
     std::vector<Plan> plans(nranks);
@@ -207,6 +238,15 @@ int nkp_sim_run_dist(int n, const int* rowptr, const int* colind, const double* 
         }
     }
     if (stats_out) stats_out[6] = nrepl;
+    // the fronts swept by the dataflow kernels keep their diagonal blocks inverted (k_invert_diag)
+    const bool invdiag = !getenv("NKP_SIM_NO_INVDIAG");
+    if (invdiag)
+        for (int r = 0; r < nranks; r++) {
+            Plan& P = plans[r];
+            double* H = heaps[r].data();
+#pragma omp parallel for schedule(dynamic)
+            for (size_t q = 0; q < P.inv_tasks.size(); q++) sim_invert_diag(H, P.inv_tasks[q]);
+        }
     if (nrhs <= 0) return 0;
 
     // ---- solves: y = permuted rhs (replicated); forward deepest -> root, backward root -> deepest
@@ -265,9 +305,27 @@ int nkp_sim_run_dist(int n, const int* rowptr, const int* colind, const double* 
                         for (int a = 0; a < sc.r; a++) w[rl[a]] += wc[a];
                     }
                     const double* Lr = H + t.Loff;
-                    for (int p = 0; p < t.s; p++) {
-                        double yp = w[p];
-                        for (int a = p + 1; a < t.m; a++) w[a] -= Lr[a + (int64_t)p * t.m] * yp;
+                    if (t.big && invdiag) {
+                        // block forward substitution with inverted 64 x 64 diagonal blocks (k_fwd_big)
+                        double tmp[64];
+                        for (int k0 = 0; k0 < t.s; k0 += 64) {
+                            int kb = std::min(64, t.s - k0);
+                            for (int a = 0; a < kb; a++) {
+                                double acc = w[k0 + a];
+                                for (int p = 0; p < a; p++) acc += Lr[k0 + a + (int64_t)(k0 + p) * t.ld] * w[k0 + p];
+                                tmp[a] = acc;
+                            }
+                            for (int a = 0; a < kb; a++) w[k0 + a] = tmp[a];
+                            for (int p = 0; p < kb; p++) {
+                                double yp = w[k0 + p];
+                                for (int a = k0 + kb; a < t.m; a++) w[a] -= Lr[a + (int64_t)(k0 + p) * t.ld] * yp;
+                            }
+                        }
+                    } else {
+                        for (int p = 0; p < t.s; p++) {
+                            double yp = w[p];
+                            for (int a = p + 1; a < t.m; a++) w[a] -= Lr[a + (int64_t)p * t.ld] * yp;
+                        }
                     }
                     for (int a = 0; a < t.s; a++) y[t.first + a] = w[a];
                 }
@@ -287,11 +345,30 @@ int nkp_sim_run_dist(int n, const int* rowptr, const int* colind, const double* 
                     const int* bi = P.bidx.data() + t.bidx_off;
                     for (int a = 0; a < t.r; a++) w[t.s + a] = y[bi[a]];
                     const double* UT = H + t.UToff;
-                    for (int p = t.s - 1; p >= 0; p--) {
-                        double z = y[t.first + p];
-                        for (int a = p + 1; a < t.m; a++) z -= UT[a + (int64_t)p * t.m] * w[a];
-                        w[p] = z / UT[p + (int64_t)p * t.m];
-                        y[t.first + p] = w[p];
+                    if (t.big && invdiag) {
+                        // block back substitution, diagonal blocks hold (U_kk^-1)^T (k_bwd_big)
+                        double z[64];
+                        for (int k0 = (t.s - 1) / 64 * 64; k0 >= 0; k0 -= 64) {
+                            int kb = std::min(64, t.s - k0);
+                            for (int p = 0; p < kb; p++) {
+                                double acc = y[t.first + k0 + p];
+                                for (int a = k0 + kb; a < t.m; a++) acc -= UT[a + (int64_t)(k0 + p) * t.ld] * w[a];
+                                z[p] = acc;
+                            }
+                            for (int p = 0; p < kb; p++) {
+                                double acc = 0;   // x_p = sum_{q >= p} Uinv(p,q) z_q, Uinv(p,q) = UT[k0+q + (k0+p) m]
+                                for (int q2 = p; q2 < kb; q2++) acc += UT[k0 + q2 + (int64_t)(k0 + p) * t.ld] * z[q2];
+                                w[k0 + p] = acc;
+                                y[t.first + k0 + p] = acc;
+                            }
+                        }
+                    } else {
+                        for (int p = t.s - 1; p >= 0; p--) {
+                            double z = y[t.first + p];
+                            for (int a = p + 1; a < t.m; a++) z -= UT[a + (int64_t)p * t.ld] * w[a];
+                            w[p] = z / UT[p + (int64_t)p * t.ld];
+                            y[t.first + p] = w[p];
+                        }
                     }
                 }
             }
