@@ -810,16 +810,17 @@ int analyse(int n, const int* rowptr, const int* colind, const int* const coords
         int64_t part_slots = 0;
         for (int q = L.solve_begin; q < L.solve_end; q++) {
             SolveTask& st = plan.solve_tasks[q];
+            // every front keeps its 64 x 64 diagonal blocks inverted for the sweeps
+            for (int k0 = 0; k0 < st.s; k0 += 64) {
+                DiagTask d;
+                d.Doff = st.Loff + k0 + (int64_t)k0 * st.ld;
+                d.UTDoff = st.UToff + k0 + (int64_t)k0 * st.ld;
+                d.ld = st.ld;
+                d.kb = std::min(64, st.s - k0);
+                plan.inv_tasks.push_back(d);
+            }
             if ((int64_t)st.m * st.s >= opt.big_entries && st.s >= 64) {
                 st.big = 1;
-                for (int k0 = 0; k0 < st.s; k0 += 64) {
-                    DiagTask d;
-                    d.Doff = st.Loff + k0 + (int64_t)k0 * st.ld;
-                    d.UTDoff = st.UToff + k0 + (int64_t)k0 * st.ld;
-                    d.ld = st.ld;
-                    d.kb = std::min(64, st.s - k0);
-                    plan.inv_tasks.push_back(d);
-                }
                 BigFront bf;
                 bf.Loff = st.Loff;
                 bf.UToff = st.UToff;
@@ -837,6 +838,15 @@ int analyse(int n, const int* rowptr, const int* colind, const int* const coords
                 bf.nchunk = ((st.r + 63) / 64 + BWD_CHUNK - 1) / BWD_CHUNK;
                 bf.part_off = part_slots;
                 bf.ld = st.ld;
+                bf.clo_off = (int64_t)plan.child_lo.size();
+                for (int c = 0; c < st.nchild; c++) {
+                    const SolveChild& sc = plan.solve_children[st.child_list + c];
+                    const int* rb = plan.rel.data() + sc.rel_off;
+                    for (int j = 0; j < bf.nslab; j++) {
+                        int row0 = j < bf.npiv ? 64 * j : st.s + 64 * (j - bf.npiv);
+                        plan.child_lo.push_back((int)(std::lower_bound(rb, rb + sc.r, row0) - rb));
+                    }
+                }
                 part_slots += (int64_t)bf.npiv * bf.nchunk;
                 plan.n_big_flags += bf.npiv;
                 plan.big_fronts.push_back(bf);

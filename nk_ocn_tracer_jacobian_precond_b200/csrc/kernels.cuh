@@ -546,164 +546,210 @@ __global__ void k_permute_out(int n, int nrhs, const int* __restrict__ perm, con
 }
 
 // ------------------------------------------------------------------------------------------
-// triangular sweeps: one CTA per front, NR right-hand sides at a time
-// W (work vectors) layout: front t, rhs c  ->  W[(woff_t) * NRtot + c * m_t + a]
+// triangular sweeps of the small fronts: ONE WARP per front, no barriers.
+// W (work vectors) layout: front t, rhs c  ->  W[woff_t * nrtot + c * m_t + a]
+//
+// The arithmetic is the same block algorithm as for the big fronts (inverted 64 x 64 diagonal
+// blocks, everything as DMMA m8n8k4 products with the right-hand sides as the N = 8 dimension),
+// but a warp walks its whole front alone: the A fragments come straight from global memory into
+// registers (32 independent loads in flight per lane), the work vector lives in global memory
+// (L2 resident), and results move from the accumulator layout to the B-fragment layout with
+// warp shuffles.  With 8 fronts per CTA and no shared memory, thousands of fronts are in flight.
 // ------------------------------------------------------------------------------------------
 
-constexpr int SOLVE_THREADS = 256;
+constexpr int SMALL_WARPS = 8;
 
-template <int NR>
-__global__ void __launch_bounds__(SOLVE_THREADS) k_fwd(const SolveTask* __restrict__ tasks,
-                                                       const SolveChild* __restrict__ children,
-                                                       const int* __restrict__ rel,
-                                                       const double* __restrict__ heap, double* __restrict__ W,
-                                                       double* __restrict__ y, int n, int nrtot) {
-    __shared__ double tri[32 * 33];
-    __shared__ double yb[32 * NR];
-    const SolveTask tk = tasks[blockIdx.x];
+// accumulator layout (row 8g + lr, rhs 2 lc + {0,1}) -> B fragment of k-step ks: (k = 4 ks + lc, rhs = lr)
+__device__ __forceinline__ double acc_to_bfrag(const double (&acc)[8][2], int ks, int lr, int lc) {
+    const int q = 4 * ks + lc;
+    const int src = ((q & 7) << 2) | (lr >> 1);
+    const double v0 = __shfl_sync(0xffffffffu, acc[ks >> 1][0], src);
+    const double v1 = __shfl_sync(0xffffffffu, acc[ks >> 1][1], src);
+    return (lr & 1) ? v1 : v0;
+}
+
+__global__ void __launch_bounds__(32 * SMALL_WARPS, 2) k_fwd_small(const SolveTask* __restrict__ tasks, int ntasks,
+                                                                const SolveChild* __restrict__ children,
+                                                                const int* __restrict__ rel,
+                                                                const double* __restrict__ heap, double* W, double* y,
+                                                                int n, int nr, int nrtot) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, lr = lane >> 2, lc = lane & 3;
+    const int t = blockIdx.x * SMALL_WARPS + warp;
+    if (t >= ntasks) return;
+    const SolveTask tk = tasks[t];
     const int s = tk.s, m = tk.m, ld = tk.ld;
     double* w = W + tk.woff * nrtot;
     const double* L = heap + tk.Loff;
-    // 1. load pivots' rhs, clear boundary part
-    for (int a = threadIdx.x; a < m; a += SOLVE_THREADS)
-#pragma unroll
-        for (int c = 0; c < NR; c++) w[a + (int64_t)c * m] = a < s ? y[tk.first + a + (int64_t)c * n] : 0.0;
-    __syncthreads();
-    // 2. add the children's update vectors (children in fixed order: deterministic)
+    // 1. pivots' right-hand side, zero boundary part
+    for (int a = lane; a < m; a += 32)
+        for (int c = 0; c < nr; c++) w[a + (int64_t)c * m] = a < s ? y[tk.first + a + (int64_t)c * n] : 0.0;
+    __syncwarp();
+    // 2. children's update vectors (fixed order: deterministic)
     for (int ch = 0; ch < tk.nchild; ch++) {
         const SolveChild sc = children[tk.child_list + ch];
         const int mc = sc.s + sc.r;
         const double* wc = W + sc.woff * nrtot + sc.s;
         const int* rl = rel + sc.rel_off;
-        for (int a = threadIdx.x; a < sc.r; a += SOLVE_THREADS) {
-            int d = rl[a];
-#pragma unroll
-            for (int c = 0; c < NR; c++) w[d + (int64_t)c * m] += wc[a + (int64_t)c * mc];
+        for (int a = lane; a < sc.r; a += 32) {
+            const int d = rl[a];
+            for (int c = 0; c < nr; c++) w[d + (int64_t)c * m] += wc[a + (int64_t)c * mc];
         }
-        __syncthreads();
+        __syncwarp();
     }
-    // 3. blocked forward substitution with L (unit lower), 32 columns at a time
-    for (int k0 = 0; k0 < s; k0 += 32) {
-        const int kb = min(32, s - k0);
-        for (int e = threadIdx.x; e < 32 * 32; e += SOLVE_THREADS) {
-            int a = e & 31, p = e >> 5;
-            tri[a + p * 33] = (a < kb && p < kb && a > p) ? L[k0 + a + (int64_t)(k0 + p) * ld] : 0.0;
+    // 3. block forward substitution
+    for (int c0 = 0; c0 < s; c0 += 64) {
+        const int kb = min(64, s - c0);
+        // y_i = L_ii^-1 v_i
+        double acc[8][2];
+        {
+            double bf[16];
+#pragma unroll
+            for (int ks = 0; ks < 16; ks++) {
+                const int q = 4 * ks + lc;
+                bf[ks] = (q < kb && lr < nr) ? __ldcg(&w[c0 + q + (int64_t)lr * m]) : 0.0;
+            }
+#pragma unroll
+            for (int g = 0; g < 8; g++) {
+                acc[g][0] = acc[g][1] = 0.0;
+                const int p = 8 * g + lr;
+                double af[16];
+#pragma unroll
+                for (int ks = 0; ks < 16; ks++) {
+                    const int q = 4 * ks + lc;
+                    double v = p == q ? 1.0 : 0.0;
+                    if (ks <= 2 * g + 1 && p < kb && q < p) v = L[c0 + p + (int64_t)(c0 + q) * ld];
+                    af[ks] = v;
+                }
+#pragma unroll
+                for (int ks = 0; ks < 16; ks++)
+                    if (ks <= 2 * g + 1) dmma884(acc[g][0], acc[g][1], af[ks], bf[ks]);
+            }
         }
-        __syncthreads();
-        if (threadIdx.x < 32) {
-            const int a = threadIdx.x;
-            double v[NR];
 #pragma unroll
-            for (int c = 0; c < NR; c++) v[c] = a < kb ? w[k0 + a + (int64_t)c * m] : 0.0;
-            for (int p = 0; p < kb; p++) {
-                double l = tri[a + p * 33];
+        for (int g = 0; g < 8; g++) {
+            const int p = 8 * g + lr;
+            if (p < kb) {
+                if (2 * lc < nr) y[tk.first + c0 + p + (int64_t)(2 * lc) * n] = acc[g][0];
+                if (2 * lc + 1 < nr) y[tk.first + c0 + p + (int64_t)(2 * lc + 1) * n] = acc[g][1];
+            }
+        }
+        // rows below: w -= L[rows, block] y_i
+        double bneg[16];
 #pragma unroll
-                for (int c = 0; c < NR; c++) {
-                    double yp = __shfl_sync(0xffffffffu, v[c], p);
-                    v[c] -= l * yp;
+        for (int ks = 0; ks < 16; ks++) bneg[ks] = -acc_to_bfrag(acc, ks, lr, lc);
+        const int R0 = c0 + kb;
+        const int ksn = (kb + 3) >> 2;
+        for (int rb = R0; rb < m; rb += 16) {
+            double cc[2][2], af[2][16];
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int R = rb + 8 * h + lr;
+                const bool rok = R < m;
+                cc[h][0] = (rok && 2 * lc < nr) ? __ldcg(&w[R + (int64_t)(2 * lc) * m]) : 0.0;
+                cc[h][1] = (rok && 2 * lc + 1 < nr) ? __ldcg(&w[R + (int64_t)(2 * lc + 1) * m]) : 0.0;
+#pragma unroll
+                for (int ks = 0; ks < 16; ks++) {
+                    const int q = 4 * ks + lc;
+                    af[h][ks] = (rok && q < kb) ? L[R + (int64_t)(c0 + q) * ld] : 0.0;
                 }
             }
 #pragma unroll
-            for (int c = 0; c < NR; c++) {
-                yb[a + 32 * c] = v[c];
-                if (a < kb) w[k0 + a + (int64_t)c * m] = v[c];
+            for (int h = 0; h < 2; h++) {
+#pragma unroll
+                for (int ks = 0; ks < 16; ks++)
+                    if (ks < ksn) dmma884(cc[h][0], cc[h][1], af[h][ks], bneg[ks]);
+                const int R = rb + 8 * h + lr;
+                if (R < m) {
+                    if (2 * lc < nr) w[R + (int64_t)(2 * lc) * m] = cc[h][0];
+                    if (2 * lc + 1 < nr) w[R + (int64_t)(2 * lc + 1) * m] = cc[h][1];
+                }
             }
         }
-        __syncthreads();
-        const int k1 = k0 + kb;
-        for (int a = k1 + threadIdx.x; a < m; a += SOLVE_THREADS) {
-            double acc[NR];
-#pragma unroll
-            for (int c = 0; c < NR; c++) acc[c] = 0.0;
-            const double* Lp = L + a + (int64_t)k0 * ld;
-            for (int p = 0; p < kb; p++) {
-                double l = Lp[(int64_t)p * ld];
-#pragma unroll
-                for (int c = 0; c < NR; c++) acc[c] += l * yb[p + 32 * c];
-            }
-#pragma unroll
-            for (int c = 0; c < NR; c++) w[a + (int64_t)c * m] -= acc[c];
-        }
-        __syncthreads();
+        __syncwarp();
     }
-    // 4. publish the pivots' part
-    for (int a = threadIdx.x; a < s; a += SOLVE_THREADS)
-#pragma unroll
-        for (int c = 0; c < NR; c++) y[tk.first + a + (int64_t)c * n] = w[a + (int64_t)c * m];
 }
 
-template <int NR>
-__global__ void __launch_bounds__(SOLVE_THREADS) k_bwd(const SolveTask* __restrict__ tasks,
-                                                       const int* __restrict__ bidx,
-                                                       const double* __restrict__ heap, double* __restrict__ W,
-                                                       double* __restrict__ y, int n, int nrtot) {
-    __shared__ double tri[32 * 33];
-    __shared__ double z[32 * NR];
-    const SolveTask tk = tasks[blockIdx.x];
+__global__ void __launch_bounds__(32 * SMALL_WARPS, 2) k_bwd_small(const SolveTask* __restrict__ tasks, int ntasks,
+                                                                const int* __restrict__ bidx,
+                                                                const double* __restrict__ heap, double* W, double* y,
+                                                                int n, int nr, int nrtot) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, lr = lane >> 2, lc = lane & 3;
+    const int t = blockIdx.x * SMALL_WARPS + warp;
+    if (t >= ntasks) return;
+    const SolveTask tk = tasks[t];
     const int s = tk.s, m = tk.m, ld = tk.ld;
     double* w = W + tk.woff * nrtot;
     const double* UT = heap + tk.UToff;
     const int* bi = bidx + tk.bidx_off;
-    for (int a = threadIdx.x; a < tk.r; a += SOLVE_THREADS) {
-        int g = bi[a];
-#pragma unroll
-        for (int c = 0; c < NR; c++) w[s + a + (int64_t)c * m] = y[g + (int64_t)c * n];
+    // 1. boundary values (solutions of ancestors)
+    for (int a = lane; a < tk.r; a += 32) {
+        const int g = bi[a];
+        for (int c = 0; c < nr; c++) w[s + a + (int64_t)c * m] = y[g + (int64_t)c * n];
     }
-    __syncthreads();
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int nblk = (s + 31) / 32;
-    for (int blk = nblk - 1; blk >= 0; blk--) {
-        const int k0 = blk * 32;
-        const int kb = min(32, s - k0);
-        const int k1 = k0 + kb;
-        // (i) z[p] = y[p] - sum_{a >= k1} UT[a,p] * w[a]   (one warp per column)
-        for (int p = warp; p < kb; p += SOLVE_THREADS / 32) {
-            double acc[NR];
+    __syncwarp();
+    // 2. block back substitution, last pivot block first
+    for (int c0 = (s - 1) / 64 * 64; c0 >= 0; c0 -= 64) {
+        const int kb = min(64, s - c0);
+        const int R0 = c0 + kb;
+        // z_i = y_i - UT[rows below, block]^T x_rows : out = 64 columns (8 groups), contraction over rows
+        double acc[8][2];
 #pragma unroll
-            for (int c = 0; c < NR; c++) acc[c] = 0.0;
-            const double* Up = UT + (int64_t)(k0 + p) * ld;
-            for (int a = k1 + lane; a < m; a += 32) {
-                double u = Up[a];
+        for (int g = 0; g < 8; g++) acc[g][0] = acc[g][1] = 0.0;
+        for (int rb = R0; rb < m; rb += 16) {
+            double bf[4], af[4][8];
 #pragma unroll
-                for (int c = 0; c < NR; c++) acc[c] += u * w[a + (int64_t)c * m];
+            for (int kk = 0; kk < 4; kk++) {
+                const int R = rb + 4 * kk + lc;
+                const bool rok = R < m;
+                bf[kk] = (rok && lr < nr) ? __ldcg(&w[R + (int64_t)lr * m]) : 0.0;
+#pragma unroll
+                for (int g = 0; g < 8; g++) af[kk][g] = (rok && 8 * g + lr < kb) ? UT[R + (int64_t)(c0 + 8 * g + lr) * ld] : 0.0;
             }
 #pragma unroll
-            for (int c = 0; c < NR; c++) {
-                double v = acc[c];
-                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-                if (lane == 0) z[p + 32 * c] = y[tk.first + k0 + p + (int64_t)c * n] - v;
+            for (int kk = 0; kk < 4; kk++)
+#pragma unroll
+                for (int g = 0; g < 8; g++) dmma884(acc[g][0], acc[g][1], af[kk][g], bf[kk]);
+        }
+#pragma unroll
+        for (int g = 0; g < 8; g++) {
+            const int p = 8 * g + lr;
+            const bool ok = p < kb;
+            const double y0 = (ok && 2 * lc < nr) ? y[tk.first + c0 + p + (int64_t)(2 * lc) * n] : 0.0;
+            const double y1 = (ok && 2 * lc + 1 < nr) ? y[tk.first + c0 + p + (int64_t)(2 * lc + 1) * n] : 0.0;
+            acc[g][0] = y0 - acc[g][0];
+            acc[g][1] = y1 - acc[g][1];
+        }
+        // x_i = U_ii^-1 z_i   (U_ii^-1 upper, stored transposed: UT[c0 + q + (c0 + p) ld] = Uinv(p, q), q >= p)
+        double zf[16];
+#pragma unroll
+        for (int ks = 0; ks < 16; ks++) zf[ks] = acc_to_bfrag(acc, ks, lr, lc);
+#pragma unroll
+        for (int g = 0; g < 8; g++) {
+            const int p = 8 * g + lr;
+            double x0 = 0.0, x1 = 0.0;
+            double af[16];
+#pragma unroll
+            for (int ks = 0; ks < 16; ks++) {
+                const int q = 4 * ks + lc;
+                double v = p == q ? 1.0 : 0.0;
+                if (ks >= 2 * g && p < kb && q < kb) v = q >= p ? UT[c0 + q + (int64_t)(c0 + p) * ld] : 0.0;
+                af[ks] = v;
             }
-        }
-        for (int e = threadIdx.x; e < 32 * 32; e += SOLVE_THREADS) {
-            int a = e & 31, p = e >> 5;   // tri[a + p*33] = UT[k0+a, k0+p] = U(p, a), a >= p
-            tri[a + p * 33] = (a < kb && p < kb && a >= p) ? UT[k0 + a + (int64_t)(k0 + p) * ld] : 0.0;
-        }
-        __syncthreads();
-        // (ii) back substitution in the 32 x 32 triangle (one warp): lane p owns x[p]
-        if (threadIdx.x < 32) {
-            const int p = threadIdx.x;
-            double v[NR];
 #pragma unroll
-            for (int c = 0; c < NR; c++) v[c] = p < kb ? z[p + 32 * c] : 0.0;
-            double dinv = p < kb ? 1.0 / tri[p + p * 33] : 0.0;
-            for (int q = kb - 1; q >= 0; q--) {
-                // finalize x[q], then eliminate it from rows p < q
-                double u = tri[q + p * 33];   // U(p, q) for p <= q
-#pragma unroll
-                for (int c = 0; c < NR; c++) {
-                    if (p == q) v[c] *= dinv;
-                    double xq = __shfl_sync(0xffffffffu, v[c], q);
-                    if (p < q) v[c] -= u * xq;
+            for (int ks = 0; ks < 16; ks++)
+                if (ks >= 2 * g) dmma884(x0, x1, af[ks], zf[ks]);
+            if (p < kb) {
+                if (2 * lc < nr) {
+                    y[tk.first + c0 + p + (int64_t)(2 * lc) * n] = x0;
+                    w[c0 + p + (int64_t)(2 * lc) * m] = x0;
+                }
+                if (2 * lc + 1 < nr) {
+                    y[tk.first + c0 + p + (int64_t)(2 * lc + 1) * n] = x1;
+                    w[c0 + p + (int64_t)(2 * lc + 1) * m] = x1;
                 }
             }
-#pragma unroll
-            for (int c = 0; c < NR; c++)
-                if (p < kb) {
-                    w[k0 + p + (int64_t)c * m] = v[c];
-                    y[tk.first + k0 + p + (int64_t)c * n] = v[c];
-                }
         }
-        __syncthreads();
+        __syncwarp();
     }
 }
 
@@ -778,9 +824,9 @@ enum { SWEEP_FWD = 0, SWEEP_BWD_TRI = 1, SWEEP_BWD_RECT = 2 };
 template <int MODE>
 __global__ void __launch_bounds__(256, 2) k_sweep_big(const BigFront* __restrict__ bfs, const BigItem* __restrict__ items,
                                                       int nitems, const SolveChild* __restrict__ children,
-                                                      const int* __restrict__ rel, const double* __restrict__ heap,
-                                                      double* W, double* y, double* part, int n, int nr, int nrtot,
-                                                      unsigned long long* cnt, unsigned epoch) {
+                                                      const int* __restrict__ rel, const int* __restrict__ clo,
+                                                      const double* __restrict__ heap, double* W, double* y, double* part,
+                                                      int n, int nr, int nrtot, unsigned long long* cnt, unsigned epoch) {
     constexpr bool FWD = MODE == SWEEP_FWD;
     constexpr bool RECT = MODE == SWEEP_BWD_RECT;
     extern __shared__ __align__(16) double ring[];
@@ -833,28 +879,7 @@ __global__ void __launch_bounds__(256, 2) k_sweep_big(const BigFront* __restrict
 #pragma unroll
                     for (int c = 0; c < 8; c++)
                         if (c < nr) base[c] = y[bf.first + r0 + tid + (int64_t)c * n];
-                if (FWD) {
-                    // children's update vectors (fixed order: deterministic).  rel[] of a child is
-                    // ascending, so the entry mapping to row r0+tid is found by bisection.
-                    const int target = r0 + tid;
-                    for (int ch = 0; ch < bf.nchild; ch++) {
-                        const SolveChild sc = children[bf.child_list + ch];
-                        const int* rl = rel + sc.rel_off;
-                        int lo = 0, hi = sc.r;
-                        while (lo < hi) {
-                            int mid = (lo + hi) >> 1;
-                            if (rl[mid] < target) lo = mid + 1;
-                            else hi = mid;
-                        }
-                        if (lo < sc.r && rl[lo] == target) {
-                            const int mc = sc.s + sc.r;
-                            const double* wc = W + sc.woff * nrtot + sc.s;
-#pragma unroll
-                            for (int c = 0; c < 8; c++)
-                                if (c < nr) base[c] += wc[lo + (int64_t)c * mc];
-                        }
-                    }
-                } else {
+                if (!FWD) {
                     // partial products of the rectangular part, chunk by chunk
                     const double* pp = part + ((bf.part_off + (int64_t)i * bf.nchunk) * 64 + tid) * 8;
                     for (int ch = 0; ch < bf.nchunk; ch++) {
@@ -866,6 +891,28 @@ __global__ void __launch_bounds__(256, 2) k_sweep_big(const BigFront* __restrict
             }
 #pragma unroll
             for (int c = 0; c < 8; c++) bv[tid * 8 + c] = base[c];
+        }
+        if (FWD && bf.nchild > 0) {
+            // children's update vectors (fixed order: deterministic).  rel[] of a child is ascending,
+            // so the entries that map into this slab are the run starting at the precomputed
+            // child_lo[child][slab]; thread k looks at the k-th entry of the run.
+            for (int ch = 0; ch < bf.nchild; ch++) {
+                __syncthreads();
+                if (tid < 64) {
+                    const SolveChild sc = children[bf.child_list + ch];
+                    const int e = clo[bf.clo_off + (int64_t)ch * bf.nslab + item.idx] + tid;
+                    if (e < sc.r) {
+                        const int row = rel[sc.rel_off + e] - r0;
+                        if (row < nrow) {
+                            const int mc = sc.s + sc.r;
+                            const double* wc = W + sc.woff * nrtot + sc.s + e;
+#pragma unroll
+                            for (int c = 0; c < 8; c++)
+                                if (c < nr) bv[row * 8 + c] += wc[(int64_t)c * mc];
+                        }
+                    }
+                }
+            }
         }
         // ---- fragments of the inverted diagonal block for the final product: entry (p, q) with
         //      p = 8 warp + lr (out), q = 4 ks + lc (contraction)

@@ -121,6 +121,8 @@ struct BigFront {
     int64_t part_off;    // backward sweep: first 64 x 8 partial-product slot of this front (level scratch)
     int nchunk;          // backward sweep: chunks of BWD_CHUNK boundary row blocks per pivot panel
     int ld;              // leading dimension of Larr / UTarr (even)
+    int64_t clo_off;     // forward sweep: into Plan::child_lo, [child * nslab + slab] = first entry of the child's
+                         // rel[] list that maps to a row >= the slab's first row
 };
 
 constexpr int BWD_CHUNK = 16;   // 64-row blocks of the boundary per item of the rectangular part
@@ -197,6 +199,7 @@ struct Plan {
     std::vector<BigFront> big_fronts;
     std::vector<BigItem> big_fwd_items, big_bwd_items, big_rect_items;
     int64_t bwd_part_slots = 0;           // 64 x 8 partial-product slots needed by the largest level
+    std::vector<int> child_lo;            // see BigFront::clo_off
     std::vector<DiagTask> inv_tasks;      // diagonal blocks of the big fronts: inverted in place after the factorisation
     int n_big_flags = 0;
     int64_t factor_len = 0;    // doubles in the factor arena  [0, factor_len)

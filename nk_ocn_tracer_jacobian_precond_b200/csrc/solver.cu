@@ -117,6 +117,7 @@ struct nkp_solver {
     int* d_perm = nullptr;
     int* d_bidx = nullptr;
     int* d_rel = nullptr;
+    int* d_clo = nullptr;
     double* d_R = nullptr;
     double* d_C = nullptr;
     DiagTask* d_diag = nullptr;
@@ -299,6 +300,7 @@ static int create_impl(nkp_solver** out, int n, const int* rowptr, const int* co
         if (upload(&s->d_perm, P.perm)) return NKP_ECUDA;
         if (upload(&s->d_bidx, P.bidx)) return NKP_ECUDA;
         if (upload(&s->d_rel, P.rel)) return NKP_ECUDA;
+        if (upload(&s->d_clo, P.child_lo)) return NKP_ECUDA;
         if (upload(&s->d_diag, P.diag_tasks)) return NKP_ECUDA;
         if (upload(&s->d_trsm, P.trsm_tasks)) return NKP_ECUDA;
         if (upload(&s->d_gemm, P.gemm_tasks)) return NKP_ECUDA;
@@ -572,8 +574,8 @@ static int sweeps(nkp_solver* s) {
         }
         int nsmall = L.small_end - L.small_begin;
         if (nsmall > 0) {
-            k_fwd<NR><<<nsmall, SOLVE_THREADS, 0, st>>>(s->d_small + L.small_begin, s->d_children, s->d_rel, s->heap,
-                                                        s->d_W, s->d_y, s->n, NR);
+            k_fwd_small<<<(nsmall + SMALL_WARPS - 1) / SMALL_WARPS, 32 * SMALL_WARPS, 0, st>>>(
+                s->d_small + L.small_begin, nsmall, s->d_children, s->d_rel, s->heap, s->d_W, s->d_y, s->n, nr, nrtot);
             s->launches++;
             mark("fwd small", l, nsmall);
         }
@@ -586,8 +588,9 @@ static int sweeps(nkp_solver* s) {
             double* W = s->d_W;
             double* y = s->d_y;
             double* part = s->d_part;
-            void* args[] = {(void*)&bfs, (void*)&items, (void*)&nitems, (void*)&ch, (void*)&rel,   (void*)&heap,  (void*)&W,
-                            (void*)&y,   (void*)&part,  (void*)&n,      (void*)&nr, (void*)&nrtot, (void*)&cnt_f, (void*)&uepoch};
+            const int* clo = s->d_clo;
+            void* args[] = {(void*)&bfs, (void*)&items, (void*)&nitems, (void*)&ch,    (void*)&rel,   (void*)&clo,   (void*)&heap, (void*)&W,
+                            (void*)&y,   (void*)&part,  (void*)&n,      (void*)&nr,    (void*)&nrtot, (void*)&cnt_f, (void*)&uepoch};
             int grid = std::min(nitems, s->coop_ctas);
             CK(cudaLaunchCooperativeKernel((void*)k_sweep_big<SWEEP_FWD>, dim3(grid), dim3(256), args, SW_SMEM, st));
             s->launches++;
@@ -598,8 +601,8 @@ static int sweeps(nkp_solver* s) {
         const LevelPlan& L = P.levels[l];
         int nsmall = L.small_end - L.small_begin;
         if (nsmall > 0) {
-            k_bwd<NR><<<nsmall, SOLVE_THREADS, 0, st>>>(s->d_small + L.small_begin, s->d_bidx, s->heap, s->d_W, s->d_y,
-                                                        s->n, NR);
+            k_bwd_small<<<(nsmall + SMALL_WARPS - 1) / SMALL_WARPS, 32 * SMALL_WARPS, 0, st>>>(
+                s->d_small + L.small_begin, nsmall, s->d_bidx, s->heap, s->d_W, s->d_y, s->n, nr, nrtot);
             s->launches++;
             mark("bwd small", l, nsmall);
         }
@@ -624,13 +627,14 @@ static int sweeps(nkp_solver* s) {
             if (nrect > 0) {
                 // rectangular part: independent items, plain launch
                 k_sweep_big<SWEEP_BWD_RECT><<<std::min(nrect, 8 * s->coop_ctas), 256, SW_SMEM, st>>>(
-                    s->d_big, s->d_rect_items + L.rect_item_begin, nrect, ch, rel, heap, W, y, part, n, nr, nrtot, cnt_b,
-                    uepoch);
+                    s->d_big, s->d_rect_items + L.rect_item_begin, nrect, ch, rel, s->d_clo, heap, W, y, part, n, nr, nrtot,
+                    cnt_b, uepoch);
                 s->launches++;
                 mark("bwd rect", l, nrect);
             }
-            void* args[] = {(void*)&bfs, (void*)&items, (void*)&nitems, (void*)&ch, (void*)&rel,   (void*)&heap,  (void*)&W,
-                            (void*)&y,   (void*)&part,  (void*)&n,      (void*)&nr, (void*)&nrtot, (void*)&cnt_b, (void*)&uepoch};
+            const int* clo = s->d_clo;
+            void* args[] = {(void*)&bfs, (void*)&items, (void*)&nitems, (void*)&ch,    (void*)&rel,   (void*)&clo,   (void*)&heap, (void*)&W,
+                            (void*)&y,   (void*)&part,  (void*)&n,      (void*)&nr,    (void*)&nrtot, (void*)&cnt_b, (void*)&uepoch};
             int grid = std::min(nitems, s->coop_ctas);
             CK(cudaLaunchCooperativeKernel((void*)k_sweep_big<SWEEP_BWD_TRI>, dim3(grid), dim3(256), args, SW_SMEM, st));
             s->launches++;
@@ -896,7 +900,7 @@ void nkp_destroy(nkp_solver* s) {
                     s->d_bidx, s->d_rel,    s->d_R,      s->d_C,      s->d_diag, s->d_trsm,    s->d_gemm,
                     s->d_add,  s->d_solve,  s->d_children, s->d_W,    s->d_y,    s->d_r,       s->d_x,
                     s->d_xb,   s->d_berr,   s->d_nrepl,  s->d_small,  s->d_big,  s->d_fwd_items, s->d_bwd_items,
-                    s->d_cnt,  s->d_inv,    s->d_rect_items, s->d_part};
+                    s->d_cnt,  s->d_inv,    s->d_rect_items, s->d_part, s->d_clo};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (s->h_pinned) cudaFreeHost(s->h_pinned);

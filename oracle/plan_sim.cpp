@@ -238,7 +238,7 @@ int nkp_sim_run_dist(int n, const int* rowptr, const int* colind, const double* 
         }
     }
     if (stats_out) stats_out[6] = nrepl;
-    // the fronts swept by the dataflow kernels keep their diagonal blocks inverted (k_invert_diag)
+    // the sweeps use inverted 64 x 64 diagonal blocks (k_invert_diag)
     const bool invdiag = !getenv("NKP_SIM_NO_INVDIAG");
     if (invdiag)
         for (int r = 0; r < nranks; r++) {
@@ -305,7 +305,7 @@ int nkp_sim_run_dist(int n, const int* rowptr, const int* colind, const double* 
                         for (int a = 0; a < sc.r; a++) w[rl[a]] += wc[a];
                     }
                     const double* Lr = H + t.Loff;
-                    if (t.big && invdiag) {
+                    if (invdiag) {
                         // block forward substitution with inverted 64 x 64 diagonal blocks (k_fwd_big)
                         double tmp[64];
                         for (int k0 = 0; k0 < t.s; k0 += 64) {
@@ -345,7 +345,7 @@ int nkp_sim_run_dist(int n, const int* rowptr, const int* colind, const double* 
                     const int* bi = P.bidx.data() + t.bidx_off;
                     for (int a = 0; a < t.r; a++) w[t.s + a] = y[bi[a]];
                     const double* UT = H + t.UToff;
-                    if (t.big && invdiag) {
+                    if (invdiag) {
                         // block back substitution, diagonal blocks hold (U_kk^-1)^T (k_bwd_big)
                         double z[64];
                         for (int k0 = (t.s - 1) / 64 * 64; k0 >= 0; k0 -= 64) {
