@@ -819,7 +819,7 @@ int analyse(int n, const int* rowptr, const int* colind, const int* const coords
                 d.kb = std::min(64, st.s - k0);
                 plan.inv_tasks.push_back(d);
             }
-            if ((int64_t)st.m * st.s >= opt.big_entries && st.s >= 64) {
+            if ((int64_t)st.m * st.s >= opt.big_entries || st.m >= opt.big_rows) {
                 st.big = 1;
                 BigFront bf;
                 bf.Loff = st.Loff;

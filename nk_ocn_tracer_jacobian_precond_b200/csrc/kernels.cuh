@@ -557,7 +557,7 @@ __global__ void k_permute_out(int n, int nrhs, const int* __restrict__ perm, con
 // warp shuffles.  With 8 fronts per CTA and no shared memory, thousands of fronts are in flight.
 // ------------------------------------------------------------------------------------------
 
-constexpr int SMALL_WARPS = 8;
+constexpr int SMALL_WARPS = 4;
 
 // accumulator layout (row 8g + lr, rhs 2 lc + {0,1}) -> B fragment of k-step ks: (k = 4 ks + lc, rhs = lr)
 __device__ __forceinline__ double acc_to_bfrag(const double (&acc)[8][2], int ks, int lr, int lc) {
@@ -568,7 +568,7 @@ __device__ __forceinline__ double acc_to_bfrag(const double (&acc)[8][2], int ks
     return (lr & 1) ? v1 : v0;
 }
 
-__global__ void __launch_bounds__(32 * SMALL_WARPS, 2) k_fwd_small(const SolveTask* __restrict__ tasks, int ntasks,
+__global__ void __launch_bounds__(32 * SMALL_WARPS, 3) k_fwd_small(const SolveTask* __restrict__ tasks, int ntasks,
                                                                 const SolveChild* __restrict__ children,
                                                                 const int* __restrict__ rel,
                                                                 const double* __restrict__ heap, double* W, double* y,
@@ -669,7 +669,7 @@ __global__ void __launch_bounds__(32 * SMALL_WARPS, 2) k_fwd_small(const SolveTa
     }
 }
 
-__global__ void __launch_bounds__(32 * SMALL_WARPS, 2) k_bwd_small(const SolveTask* __restrict__ tasks, int ntasks,
+__global__ void __launch_bounds__(32 * SMALL_WARPS, 3) k_bwd_small(const SolveTask* __restrict__ tasks, int ntasks,
                                                                 const int* __restrict__ bidx,
                                                                 const double* __restrict__ heap, double* W, double* y,
                                                                 int n, int nr, int nrtot) {

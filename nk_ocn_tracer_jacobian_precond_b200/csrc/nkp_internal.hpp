@@ -172,7 +172,8 @@ struct Options {
     int add_tile = 32;     // extend-add tile
     int period_i = 0;
     int verbose = 0;
-    int64_t big_entries = 1 << 16;  // fronts with m*s >= this use the multi-CTA dataflow sweeps
+    int64_t big_entries = 1 << 15;  // fronts with m*s >= this use the multi-CTA dataflow sweeps
+    int big_rows = 768;             // ... and so do tall fronts (few pivots, long boundary): one warp would crawl
     int rank = 0, nranks = 1;       // multi-GPU: this process' rank (one GPU per rank)
 };
 

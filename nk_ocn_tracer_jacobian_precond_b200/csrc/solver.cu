@@ -255,6 +255,7 @@ static int create_impl(nkp_solver** out, int n, const int* rowptr, const int* co
     s->rank = rank;
     s->nranks = nranks;
     if (getenv("NKP_BIG_ENTRIES")) po.big_entries = atoll(getenv("NKP_BIG_ENTRIES"));
+    if (getenv("NKP_BIG_ROWS")) po.big_rows = atoi(getenv("NKP_BIG_ROWS"));
     if (getenv("NKP_OUTER")) po.outer = std::max(1, atoi(getenv("NKP_OUTER")));
     const int* coords[3] = {ci, cj, ck};
     auto t0 = std::chrono::steady_clock::now();
