@@ -119,6 +119,22 @@ int nkp_solve(nkp_solver* s, double* B, int ldb, int nrhs, double* berr);
 /* Same with B in device memory (berr stays a host pointer). */
 int nkp_solve_device(nkp_solver* s, double* d_B, int ldb, int nrhs, double* berr);
 
+/* Tracer fields in, tracer fields out -- get_B_global + pdgssvx*(FACTORED) + put_B_global of the
+ * reference in one call (src/solve_ABglobal.c:154-208, :395, :213-267).
+ * nkp_set_tracer_maps registers the index maps of the matrix file (tracer_state_ind_to_{i,j,k},
+ * src/matrix.c:322-329; grid dimensions as read by get_grid_dims, src/grid.c:34); n of the handle must
+ * equal coupled_tracer_cnt * tracer_state_len (src/matrix.c:471).
+ * nkp_solve_fields takes `nfields` HOST pointers to 3-D double fields of km*jmt*imt values, [k][j][i]
+ * (what get_var_3d_double returns, src/file_io.c:273).  Every `coupled_tracer_cnt` consecutive fields
+ * form one right-hand side (src/solve_ABglobal.c:373-388); ALL systems are solved as one batched
+ * multi-RHS solve (the reference loops with nrhs = 1).  The ocean points of the fields are gathered
+ * and scattered by device kernels; land values are left untouched (src/solve_ABglobal.c:236-248).
+ * berr (may be NULL) receives nfields / coupled_tracer_cnt backward errors.  A field count that is not
+ * a multiple of coupled_tracer_cnt is NKP_EINVAL (fatal in the reference, src/solve_ABglobal.c:376-379). */
+int nkp_set_tracer_maps(nkp_solver* s, int tracer_state_len, int coupled_tracer_cnt, const int* ind_i,
+                        const int* ind_j, const int* ind_k, int imt, int jmt, int km);
+int nkp_solve_fields(nkp_solver* s, double* const* fields, int nfields, double* berr);
+
 /* Residual r = b - A x for the currently loaded values (device pointers, column-major
  * with leading dimension n); the refinement SpMV exposed for testing and measurement. */
 int nkp_residual_device(nkp_solver* s, const double* d_x, const double* d_b, double* d_r, int nrhs);

@@ -808,6 +808,7 @@ int analyse(int n, const int* rowptr, const int* colind, const int* const coords
         L.small_begin = (int)plan.solve_small.size();
         L.big_begin = (int)plan.big_fronts.size();
         int64_t part_slots = 0;
+        L.inv_begin = (int)plan.inv_tasks.size();
         for (int q = L.solve_begin; q < L.solve_end; q++) {
             SolveTask& st = plan.solve_tasks[q];
             // every front keeps its 64 x 64 diagonal blocks inverted for the sweeps
@@ -856,6 +857,7 @@ int analyse(int n, const int* rowptr, const int* colind, const int* const coords
         }
         L.small_end = (int)plan.solve_small.size();
         L.big_end = (int)plan.big_fronts.size();
+        L.inv_end = (int)plan.inv_tasks.size();
         L.fwd_item_begin = (int)plan.big_fwd_items.size();
         L.bwd_item_begin = (int)plan.big_bwd_items.size();
         {

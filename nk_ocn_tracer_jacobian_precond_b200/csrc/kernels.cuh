@@ -546,6 +546,37 @@ __global__ void k_permute_out(int n, int nrhs, const int* __restrict__ perm, con
 }
 
 // ------------------------------------------------------------------------------------------
+// tracer fields <-> right-hand sides (get_B_global / put_B_global of the reference,
+// src/solve_ABglobal.c:184-191 and :242-248): system `col` stacks the ocean points of `ct`
+// coupled tracer fields, B[t * tsl + s, col] = field_{col * ct + t}[cell[s]].  The scatter
+// writes only ocean points, so land values of the fields survive (src/solve_ABglobal.c:236-248).
+// ------------------------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(256) k_gather_fields(int tsl, int ct, int nfields, const int* __restrict__ cell,
+                                                       const double* __restrict__ fields, int64_t ncell,
+                                                       double* __restrict__ B, int ldb) {
+    const int sidx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (sidx >= tsl) return;
+    const int c = cell[sidx];
+    for (int f = 0; f < nfields; f++) {
+        const int col = f / ct, t = f - col * ct;
+        B[(int64_t)t * tsl + sidx + (int64_t)col * ldb] = fields[(int64_t)f * ncell + c];
+    }
+}
+
+__global__ void __launch_bounds__(256) k_scatter_fields(int tsl, int ct, int nfields, const int* __restrict__ cell,
+                                                        double* __restrict__ fields, int64_t ncell,
+                                                        const double* __restrict__ B, int ldb) {
+    const int sidx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (sidx >= tsl) return;
+    const int c = cell[sidx];
+    for (int f = 0; f < nfields; f++) {
+        const int col = f / ct, t = f - col * ct;
+        fields[(int64_t)f * ncell + c] = B[(int64_t)t * tsl + sidx + (int64_t)col * ldb];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // triangular sweeps of the small fronts: ONE WARP per front, no barriers.
 // W (work vectors) layout: front t, rhs c  ->  W[woff_t * nrtot + c * m_t + a]
 //
@@ -1107,63 +1138,51 @@ __global__ void __launch_bounds__(256, 2) k_sweep_big(const BigFront* __restrict
     }
 }
 
-// In-place inversion of the 64 x 64 diagonal blocks of the big fronts, after the factorisation:
+// In-place inversion of the 64 x 64 diagonal blocks, after the factorisation of their level:
 // strictly lower part of the Larr block <- strictly lower part of L_kk^-1 (unit diagonal implied),
-// lower part of the UTarr block <- (U_kk^-1)^T.  grid (blocks, 2): y = 0 inverts L_kk, y = 1 U_kk;
-// 64 threads, one column of the inverse each.
-constexpr int INV_SMEM = 2 * 64 * 65 * 8;
+// lower part of the UTarr block <- (U_kk^-1)^T = (U_kk^T)^-1.  Both are inverses of a LOWER
+// triangular matrix M stored in place (L_kk with unit diagonal; U_kk^T as stored), so one code path
+// serves both: grid (blocks, 2), y = 0 inverts L_kk, y = 1 U_kk^T.  64 threads; thread j computes
+// column j of M^-1 by forward substitution entirely in registers (the column is zero above row j,
+// so every thread can run the same fully unrolled loops), M is broadcast from shared memory.
+constexpr int INV_SMEM = 64 * 65 * 8;
 
 __global__ void __launch_bounds__(64) k_invert_diag(const DiagTask* __restrict__ tasks, double* __restrict__ heap) {
-    extern __shared__ __align__(16) double ism[];
-    double* T = ism;             // the triangle
-    double* X = ism + 64 * 65;   // its inverse
+    __shared__ double T[64 * 65];   // T[a + 65 b] = M(a,b), a > b ; afterwards the inverse
+    __shared__ double dinv[64];     // 1 / M(a,a)
     const DiagTask tk = tasks[blockIdx.x];
     const int kb = tk.kb, ld = tk.ld;
     const bool lower = blockIdx.y == 0;
     double* G = heap + (lower ? tk.Doff : tk.UTDoff);
-    for (int e = threadIdx.x; e < 64 * 64; e += 64) {
-        int a = e & 63, b = e >> 6;
-        // lower: T[a + 65 b] = L(a,b), a > b.   upper: T[a + 65 b] = U(b,a), a >= b (as stored)
-        bool ok = a < kb && b < kb && (lower ? a > b : a >= b);
-        T[a + 65 * b] = ok ? G[a + (int64_t)b * ld] : 0.0;
-    }
-    __syncthreads();
     const int j = threadIdx.x;
-    if (j < kb) {
-        if (lower) {
-            X[j + 65 * j] = 1.0;
-            for (int i2 = j + 1; i2 < kb; i2++) {
-                double a0 = 0.0, a1 = 0.0;
-                for (int p = j; p < i2; p++) {
-                    double t = T[i2 + 65 * p] * X[p + 65 * j];
-                    if (p & 1) a1 += t;
-                    else a0 += t;
-                }
-                X[i2 + 65 * j] = -(a0 + a1);
-            }
-        } else {
-            X[j + 65 * j] = 1.0 / T[j + 65 * j];
-            for (int i2 = j - 1; i2 >= 0; i2--) {
-                double a0 = 0.0, a1 = 0.0;
-                for (int p = i2 + 1; p <= j; p++) {
-                    double t = T[p + 65 * i2] * X[p + 65 * j];   // U(i2,p) V(p,j)
-                    if (p & 1) a1 += t;
-                    else a0 += t;
-                }
-                X[i2 + 65 * j] = -(a0 + a1) / T[i2 + 65 * i2];
-            }
-        }
+    for (int e = threadIdx.x; e < 64 * 64; e += 64) {
+        int a = e & 63, b = e >> 6;
+        T[a + 65 * b] = (a < kb && b < kb && a > b) ? G[a + (int64_t)b * ld] : 0.0;
     }
+    dinv[j] = (lower || j >= kb) ? 1.0 : 1.0 / G[j + (int64_t)j * ld];
+    __syncthreads();
+    double x[64];
+#pragma unroll
+    for (int i = 0; i < 64; i++) {
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll
+        for (int p = 0; p < i; p++) {
+            const double t = T[i + 65 * p];
+            if ((p & 3) == 0) a0 = fma(t, x[p], a0);
+            else if ((p & 3) == 1) a1 = fma(t, x[p], a1);
+            else if ((p & 3) == 2) a2 = fma(t, x[p], a2);
+            else a3 = fma(t, x[p], a3);
+        }
+        const double d = dinv[i];
+        x[i] = i == j ? d : (i > j ? -((a0 + a1) + (a2 + a3)) * d : 0.0);
+    }
+    __syncthreads();   // everybody has finished reading M
+#pragma unroll
+    for (int i = 0; i < 64; i++) T[i + 65 * j] = x[i];
     __syncthreads();
     for (int e = threadIdx.x; e < 64 * 64; e += 64) {
         int a = e & 63, b = e >> 6;
-        if (a < kb && b < kb) {
-            if (lower) {
-                if (a > b) G[a + (int64_t)b * ld] = X[a + 65 * b];
-            } else if (a >= b) {
-                G[a + (int64_t)b * ld] = X[b + 65 * a];   // (U^-1)(b,a), stored transposed
-            }
-        }
+        if (a < kb && b < kb && (lower ? a > b : a >= b)) G[a + (int64_t)b * ld] = T[a + 65 * b];
     }
 }
 

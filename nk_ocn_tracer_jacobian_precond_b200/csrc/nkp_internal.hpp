@@ -160,6 +160,7 @@ struct LevelPlan {
     int big_begin = 0, big_end = 0;      // into Plan::big_fronts
     int fwd_item_begin = 0, fwd_item_end = 0;  // into Plan::big_fwd_items
     int bwd_item_begin = 0, bwd_item_end = 0;  // into Plan::big_bwd_items
+    int inv_begin = 0, inv_end = 0;            // into Plan::inv_tasks (diagonal blocks of this level's fronts)
     int rect_item_begin = 0, rect_item_end = 0;  // into Plan::big_rect_items (idx = panel * nchunk + chunk)
 };
 

@@ -106,6 +106,8 @@ struct nkp_solver {
     int n = 0;
     int64_t nnz = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t side = nullptr;          // diagonal-block inversion of finished levels, concurrent with the levels above
+    cudaEvent_t ev_level = nullptr, ev_side = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     // device data
     double* heap = nullptr;
@@ -145,6 +147,12 @@ struct nkp_solver {
     double* d_x = nullptr;      // n x MAX_NR solution accumulator
     double* d_berr = nullptr;   // MAX_NR (+ MAX_NR sums)
     int* d_nrepl = nullptr;
+    // tracer fields (nkp_set_tracer_maps / nkp_solve_fields)
+    int tsl = 0, ct = 0;        // tracer_state_len, coupled_tracer_cnt
+    int64_t ncell = 0;          // imt * jmt * km
+    int* d_cell = nullptr;      // flat (k, j, i) cell index of every tracer-state entry
+    double* d_fields = nullptr; // MAX_NR * ct device copies of the 3-D fields
+    double* h_field = nullptr;  // pinned staging, one field
     double* h_pinned = nullptr; // pinned staging for values / rhs
     size_t pinned_bytes = 0;
     bool factored = false;
@@ -279,6 +287,9 @@ static int create_impl(nkp_solver** out, int n, const int* rowptr, const int* co
     } while (0)
     auto body = [&]() -> int {
         CK(cudaStreamCreate(&s->stream));
+        CK(cudaStreamCreateWithFlags(&s->side, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&s->ev_level, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&s->ev_side, cudaEventDisableTiming));
         for (int i = 0; i < 4; i++) CK(cudaEventCreate(&s->ev[i]));
         if (nranks > 1) {
             if (!nccl_load()) {
@@ -324,7 +335,6 @@ static int create_impl(nkp_solver** out, int n, const int* rowptr, const int* co
             CK(cudaFuncSetAttribute(k_sweep_big<SWEEP_FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, SW_SMEM));
             CK(cudaFuncSetAttribute(k_sweep_big<SWEEP_BWD_TRI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SW_SMEM));
             CK(cudaFuncSetAttribute(k_sweep_big<SWEEP_BWD_RECT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SW_SMEM));
-            CK(cudaFuncSetAttribute(k_invert_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, INV_SMEM));
             CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sweep_big<SWEEP_FWD>, 256, SW_SMEM));
             minocc = std::min(minocc, occ);
             CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sweep_big<SWEEP_BWD_TRI>, 256, SW_SMEM));
@@ -473,13 +483,19 @@ static int do_factor(nkp_solver* s) {
                 prof_mark(s, KC_GEMM);
             }
         }
+        // the sweeps use inverted 64 x 64 diagonal blocks; nothing above this level reads them, so the
+        // inversion of a finished level runs on the side stream while the main stream factors on
+        if (L.inv_end > L.inv_begin) {
+            CK(cudaEventRecord(s->ev_level, st));
+            CK(cudaStreamWaitEvent(s->side, s->ev_level, 0));
+            k_invert_diag<<<dim3((unsigned)(L.inv_end - L.inv_begin), 2), 64, 0, s->side>>>(s->d_inv + L.inv_begin,
+                                                                                                   s->heap);
+            s->launches++;
+        }
     }
-    // the dataflow sweeps use inverted diagonal blocks (part of the factorisation time)
-    if (!P.inv_tasks.empty()) {
-        k_invert_diag<<<dim3((unsigned)P.inv_tasks.size(), 2), 64, INV_SMEM, st>>>(s->d_inv, s->heap);
-        s->launches++;
-        prof_mark(s, KC_DIAG);
-    }
+    // the sweeps' inverted diagonal blocks: the main stream joins the side stream (part of the factorisation time)
+    CK(cudaEventRecord(s->ev_side, s->side));
+    CK(cudaStreamWaitEvent(st, s->ev_side, 0));
     CK(cudaEventRecord(s->ev[2], st));
     CK(cudaGetLastError());
     int nrepl = 0;
@@ -806,6 +822,90 @@ int nkp_solve(nkp_solver* s, double* B, int ldb, int nrhs, double* berr) {
     return NKP_OK;
 }
 
+int nkp_set_tracer_maps(nkp_solver* s, int tracer_state_len, int coupled_tracer_cnt, const int* ind_i, const int* ind_j,
+                        const int* ind_k, int imt, int jmt, int km) {
+    if (!s || tracer_state_len <= 0 || coupled_tracer_cnt <= 0 || !ind_i || !ind_j || !ind_k || imt <= 0 || jmt <= 0 ||
+        km <= 0 || (int64_t)tracer_state_len * coupled_tracer_cnt != s->n) {
+        g_err = "nkp_set_tracer_maps: invalid argument (n must equal coupled_tracer_cnt * tracer_state_len)";
+        return NKP_EINVAL;
+    }
+    CK(cudaSetDevice(s->opt.device));
+    std::vector<int> cell((size_t)tracer_state_len);
+    for (int q = 0; q < tracer_state_len; q++) {
+        if (ind_i[q] < 0 || ind_i[q] >= imt || ind_j[q] < 0 || ind_j[q] >= jmt || ind_k[q] < 0 || ind_k[q] >= km) {
+            g_err = "nkp_set_tracer_maps: index map entry out of range";
+            return NKP_EINVAL;
+        }
+        cell[q] = (ind_k[q] * jmt + ind_j[q]) * imt + ind_i[q];
+    }
+    if (s->d_cell) cudaFree(s->d_cell);
+    if (s->d_fields) cudaFree(s->d_fields);
+    if (s->h_field) cudaFreeHost(s->h_field);
+    s->d_cell = nullptr;
+    s->d_fields = nullptr;
+    s->h_field = nullptr;
+    s->tsl = tracer_state_len;
+    s->ct = coupled_tracer_cnt;
+    s->ncell = (int64_t)imt * jmt * km;
+    if (upload(&s->d_cell, cell)) return NKP_ECUDA;
+    CK(cudaMalloc((void**)&s->d_fields, sizeof(double) * (size_t)s->ncell * MAX_NR * s->ct));
+    CK(cudaMallocHost((void**)&s->h_field, sizeof(double) * (size_t)s->ncell));
+    return NKP_OK;
+}
+
+int nkp_solve_fields(nkp_solver* s, double* const* fields, int nfields, double* berr) {
+    if (!s || !fields || nfields < 0) {
+        g_err = "nkp_solve_fields: invalid argument";
+        return NKP_EINVAL;
+    }
+    if (!s->d_cell) {
+        g_err = "nkp_solve_fields: call nkp_set_tracer_maps first";
+        return NKP_ESTATE;
+    }
+    if (!s->factored) {
+        g_err = "nkp_solve: matrix not factored";
+        return NKP_ESTATE;
+    }
+    if (nfields % s->ct != 0) {
+        // the reference aborts when the variable list runs out inside a group (src/solve_ABglobal.c:376-379)
+        g_err = "nkp_solve_fields: number of fields is not a multiple of coupled_tracer_cnt";
+        return NKP_EINVAL;
+    }
+    CK(cudaSetDevice(s->opt.device));
+    cudaStream_t st = s->stream;
+    const int n = s->n, ct = s->ct, tsl = s->tsl;
+    const size_t fbytes = sizeof(double) * (size_t)s->ncell;
+    const int ngroups = nfields / ct;
+    int maxsteps = 0;
+    double tsum = 0;
+    for (int g0 = 0; g0 < ngroups; g0 += MAX_NR) {
+        const int ng = std::min(MAX_NR, ngroups - g0);
+        const int nf = ng * ct;
+        for (int f = 0; f < nf; f++) {
+            memcpy(s->h_field, fields[g0 * ct + f], fbytes);
+            CK(cudaMemcpyAsync(s->d_fields + (size_t)f * s->ncell, s->h_field, fbytes, cudaMemcpyHostToDevice, st));
+            CK(cudaStreamSynchronize(st));   // the staging buffer is reused
+        }
+        k_gather_fields<<<(tsl + 255) / 256, 256, 0, st>>>(tsl, ct, nf, s->d_cell, s->d_fields, s->ncell, s->d_xb, n);
+        s->launches++;
+        int rc = nkp_solve_device(s, s->d_xb, n, ng, berr ? berr + g0 : nullptr);
+        if (rc) return rc;
+        tsum += s->t_solve;
+        maxsteps = std::max(maxsteps, s->refine_steps);
+        k_scatter_fields<<<(tsl + 255) / 256, 256, 0, st>>>(tsl, ct, nf, s->d_cell, s->d_fields, s->ncell, s->d_xb, n);
+        s->launches++;
+        CK(cudaGetLastError());
+        for (int f = 0; f < nf; f++) {
+            CK(cudaMemcpyAsync(s->h_field, s->d_fields + (size_t)f * s->ncell, fbytes, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            memcpy(fields[g0 * ct + f], s->h_field, fbytes);
+        }
+    }
+    s->t_solve = tsum;
+    s->refine_steps = maxsteps;
+    return NKP_OK;
+}
+
 int nkp_residual_device(nkp_solver* s, const double* dx, const double* db, double* dr, int nrhs) {
     if (!s || !dx || !db || !dr || nrhs < 0) return NKP_EINVAL;
     if (nrhs == 0) return NKP_OK;
@@ -905,9 +1005,15 @@ void nkp_destroy(nkp_solver* s) {
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (s->h_pinned) cudaFreeHost(s->h_pinned);
+    if (s->h_field) cudaFreeHost(s->h_field);
+    if (s->d_cell) cudaFree(s->d_cell);
+    if (s->d_fields) cudaFree(s->d_fields);
     for (int i = 0; i < 4; i++)
         if (s->ev[i]) cudaEventDestroy(s->ev[i]);
     for (cudaEvent_t e : s->prof_ev) cudaEventDestroy(e);
+    if (s->ev_level) cudaEventDestroy(s->ev_level);
+    if (s->ev_side) cudaEventDestroy(s->ev_side);
+    if (s->side) cudaStreamDestroy(s->side);
     if (s->stream) cudaStreamDestroy(s->stream);
     delete s;
 }

@@ -61,6 +61,8 @@ def load_library():
     lib.nkp_factor_device.argtypes = [vp, vp]
     lib.nkp_solve.argtypes = [vp, P(C.c_double), C.c_int, C.c_int, P(C.c_double)]
     lib.nkp_solve_device.argtypes = [vp, vp, C.c_int, C.c_int, P(C.c_double)]
+    lib.nkp_set_tracer_maps.argtypes = [vp, C.c_int, C.c_int, P(C.c_int), P(C.c_int), P(C.c_int), C.c_int, C.c_int, C.c_int]
+    lib.nkp_solve_fields.argtypes = [vp, P(P(C.c_double)), C.c_int, P(C.c_double)]
     lib.nkp_residual_device.argtypes = [vp, vp, vp, vp, C.c_int]
     lib.nkp_sweeps_device.argtypes = [vp, vp, C.c_int, C.c_int]
     lib.nkp_get_perm.argtypes = [vp, P(C.c_int)]
@@ -160,6 +162,28 @@ class TracerJacobianSolver:
         berr = np.zeros(max(nrhs, 1))
         _check(self._lib.nkp_solve_device(self._h, C.c_void_p(d_ptr), ldb, nrhs,
                                           berr.ctypes.data_as(C.POINTER(C.c_double))), "nkp_solve_device")
+        return berr
+
+    def set_tracer_maps(self, ind_i, ind_j, ind_k, shape, coupled_tracer_cnt=1):
+        """Register tracer_state_ind_to_{i,j,k} (src/matrix.c:322-329) and the grid shape (imt, jmt, km)."""
+        ii, jj, kk = (np.ascontiguousarray(a, dtype=np.int32) for a in (ind_i, ind_j, ind_k))
+        imt, jmt, km = (int(v) for v in shape)
+        self._field_shape = (km, jmt, imt)
+        self._ct = int(coupled_tracer_cnt)
+        _check(self._lib.nkp_set_tracer_maps(self._h, int(ii.size), self._ct, _iptr(ii), _iptr(jj), _iptr(kk),
+                                             imt, jmt, km), "nkp_set_tracer_maps")
+
+    def solve_fields(self, fields):
+        """get_B + solve + put_B (src/solve_ABglobal.c:154-267) for a list of 3-D float64 fields
+        [k][j][i], in place; every coupled_tracer_cnt consecutive fields form one system and all systems
+        are solved as one batch.  Returns berr per system."""
+        shape = getattr(self, "_field_shape", None)
+        for f in fields:
+            assert f.dtype == np.float64 and f.flags.c_contiguous and (shape is None or f.shape == shape)
+        ptrs = (C.POINTER(C.c_double) * max(len(fields), 1))(*[f.ctypes.data_as(C.POINTER(C.c_double)) for f in fields])
+        berr = np.zeros(max(len(fields) // getattr(self, "_ct", 1), 1))
+        _check(self._lib.nkp_solve_fields(self._h, ptrs, len(fields), berr.ctypes.data_as(C.POINTER(C.c_double))),
+               "nkp_solve_fields")
         return berr
 
     def sweeps_device(self, d_ptr, ldb, nrhs):

@@ -54,3 +54,19 @@ def test_python_binding_fails_loudly_without_gpu():
     ci = np.array([0, 1], dtype=np.int32)
     with pytest.raises(solver.NkpError):
         solver.TracerJacobianSolver(2, rp, ci)
+
+
+def test_native_driver_usage_and_io_errors(tmp_path):
+    """solve_ABbatch mirrors the reference's command-line behaviour (src/solve_ABglobal.c:38-99): usage
+    errors and unreadable files exit with EXIT_FAILURE; no GPU is needed to get that far."""
+    prog = os.path.join(PKG, "solve_ABbatch")
+    if not os.path.exists(prog):
+        _build()
+    r = subprocess.run([prog, "-h"], capture_output=True, text=True)
+    assert r.returncode == 1 and "usage: jacobian_precond [-D dbg_lvl] [-n nprow[,npcol]] [-v vars] matrix_fname inout_fname" in r.stderr
+    r = subprocess.run([prog, "-D", "x", "a", "b"], capture_output=True, text=True)
+    assert r.returncode == 1 and "error parsing argument 'x' for option 'D'" in r.stderr
+    r = subprocess.run([prog, "only_one"], capture_output=True, text=True)
+    assert r.returncode == 1 and "unexpected number of arguments" in r.stderr
+    r = subprocess.run([prog, str(tmp_path / "missing.nc"), str(tmp_path / "t.nc")], capture_output=True, text=True)
+    assert r.returncode == 1 and r.stderr.startswith("(0) ")

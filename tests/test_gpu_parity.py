@@ -268,3 +268,67 @@ def test_reference_driver_cli(tmp_path, golden_matrix, prog, nflag):
     # usage error -> EXIT_FAILURE, like the reference
     bad = subprocess.run([DRV[prog], "-n", "1"], capture_output=True, text=True)
     assert bad.returncode != 0 and "usage" in bad.stderr
+
+
+# ---- tracer fields in / out (device gather + scatter) and the native C driver ------
+
+def test_solve_fields_matches_oracle_and_keeps_land(golden_matrix):
+    """nkp_solve_fields = get_B_global + solve + put_B_global (src/solve_ABglobal.c:154-267):
+    ocean points solved (all fields in one batch), land values bit-identical (KAT-7)."""
+    from nk_ocn_tracer_jacobian_precond_b200 import solver
+    m = golden_matrix
+    c = _golden_case(m)
+    s = solver.TracerJacobianSolver(c["n"], c["rowptr"], c["colind"], coords=(c["i"], c["j"], c["k"]))
+    s.factor(c["nzval"])
+    s.set_tracer_maps(c["i"], c["j"], c["k"], (20, 24, 10))
+    rng = np.random.default_rng(5)
+    orig = [rng.standard_normal((10, 24, 20)) for _ in range(11)]     # 11 > MAX_NR: two chunks
+    fields = [f.copy() for f in orig]
+    berr = s.solve_fields(fields)
+    assert berr.shape == (11,) and berr.max() <= 16 * oracle_solve.EPS
+    i, j, k = c["i"], c["j"], c["k"]
+    ocean = np.zeros((10, 24, 20), bool)
+    ocean[k, j, i] = True
+    for f0, f in zip(orig, fields):
+        assert np.array_equal(f[~ocean], f0[~ocean])
+        xo = oracle_solve.solve(c["n"], c["rowptr"], c["colind"], c["nzval"], f0[k, j, i])
+        assert np.linalg.norm(f[k, j, i] - xo) / np.linalg.norm(xo) <= SOL_TOL
+    # a field count that is not a multiple of coupled_tracer_cnt is an error (src/solve_ABglobal.c:376-379)
+    s.set_tracer_maps(c["i"], c["j"], c["k"], (20, 24, 10), coupled_tracer_cnt=1)
+    with pytest.raises(solver.NkpError):
+        s2 = solver.TracerJacobianSolver(c["n"], c["rowptr"], c["colind"])
+        s2.solve_fields([orig[0].copy()])                                 # maps not set
+    s.close()
+
+
+def test_native_batch_driver_cli(tmp_path, golden_matrix):
+    """solve_ABbatch: the reference command line (src/solve_ABglobal.c:41), all -v tracers in one
+    batched solve, same file semantics."""
+    prog = os.path.join(ROOT, "nk_ocn_tracer_jacobian_precond_b200", "solve_ABbatch")
+    assert os.path.exists(prog), "build with make -C nk_ocn_tracer_jacobian_precond_b200/csrc"
+    from nk_ocn_tracer_jacobian_precond_b200 import synth
+    m = golden_matrix
+    c = _golden_case(m)
+    g = synth.make_grid(20, 24, 10, seed=1)
+    rng = np.random.default_rng(22)
+    fields = {f"T{q}": rng.standard_normal((10, 24, 20)) for q in range(1, 4)}
+    mat = tmp_path / "A.nc"
+    shutil.copy(os.path.join(GOLDEN, "A_20x24x10.nc"), mat)
+    tr = tmp_path / "tracers.nc"
+    synth.write_tracer_file(str(tr), g, fields)
+    out = subprocess.run([prog, "-D", "1", "-n", "12,12", "-v", "T1,T2,T3", str(mat), str(tr)],
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    assert "solve info = 0" in out.stdout and all(l.startswith("(0) ") or not l for l in out.stdout.splitlines())
+    i, j, k = c["i"], c["j"], c["k"]
+    ocean = np.zeros((10, 24, 20), bool)
+    ocean[k, j, i] = True
+    for name, f in fields.items():
+        got = synth.read_tracer(str(tr), name)
+        assert np.array_equal(got[~ocean], f[~ocean])
+        xo = oracle_solve.solve(c["n"], c["rowptr"], c["colind"], c["nzval"], f[k, j, i])
+        assert np.linalg.norm(got[k, j, i] - xo) / np.linalg.norm(xo) <= SOL_TOL
+    bad = subprocess.run([prog, "-n", "1"], capture_output=True, text=True)
+    assert bad.returncode != 0 and "usage" in bad.stderr
+    missing = subprocess.run([prog, "-v", "NOPE", str(mat), str(tr)], capture_output=True, text=True)
+    assert missing.returncode != 0
