@@ -46,7 +46,11 @@ typedef struct nkp_options {
     int refine_max;      /* max refinement steps (SuperLU IterRefine=SLU_DOUBLE, ITMAX)  */
     int device;          /* CUDA device ordinal                                          */
     int verbose;         /* 0 silent, 1 phase summary on stderr                          */
-    int reserved[10];
+    int refine_rule;     /* 0: SuperLU's pdgsrfs rule -- componentwise berr <= eps or no     */
+                         /*    halving (default, what the reference gets);                    */
+                         /* 1: normwise -- stop once ||b - A x||_2 <= 1e-14 ||b||_2 for every */
+                         /*    right-hand side (or no halving); typically 2-3 steps fewer     */
+    int reserved[9];
 } nkp_options;
 
 /* Statistics in the spirit of PStatPrint (src/solve_ABglobal.c:351-360). */
@@ -149,6 +153,8 @@ int nkp_get_stats(const nkp_solver* s, nkp_stats* st);
 /* on != 0: bracket every kernel of nkp_factor* with CUDA events on the solver's stream and
  * report per-kernel-class times in nkp_stats (small overhead; off by default). */
 int nkp_set_profile(nkp_solver* s, int on);
+/* Change the refinement stopping rule of an existing handle (see nkp_options.refine_rule). */
+int nkp_set_refine_rule(nkp_solver* s, int rule);
 /* Block until all device work of this handle has finished. */
 int nkp_sync(nkp_solver* s);
 void nkp_destroy(nkp_solver* s);

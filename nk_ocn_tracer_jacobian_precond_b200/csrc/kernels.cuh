@@ -333,14 +333,22 @@ __global__ void __launch_bounds__(TRSM_THREADS, 2) k_trsm(const TrsmTask* __rest
 // ------------------------------------------------------------------------------------------
 
 constexpr int G_TM = 128, G_TN = 64;
-constexpr int G_KC = 16;          // K chunk of one pipeline stage
-constexpr int G_ST = 4;           // stages of the cp.async ring (prefetch distance 3 chunks)
+#ifndef NKP_G_KC
+#define NKP_G_KC 16
+#endif
+#ifndef NKP_G_ST
+#define NKP_G_ST 2
+#endif
+constexpr int G_KC = NKP_G_KC;    // K chunk of one pipeline stage
+constexpr int G_ST = NKP_G_ST;    // stages of the cp.async ring (prefetch distance G_ST - 1 chunks).  16 x 2 was the
+                                  // fastest of 14 measured (KC, ST) pairs at gx1v6 (3.26 s; 16 x 4: 3.63 s): the ring
+                                  // takes 51 KB per CTA instead of 102 KB and leaves the rest of the SM's 256 KB to L1
 constexpr int G_LDA = G_TM + 4;   // == 4 (mod 16): conflict-free 8-byte fragment loads
 constexpr int G_LDB = G_TN + 4;
 constexpr int G_LDC = G_TM + 2;   // == 2 (mod 16): conflict-free accumulator staging
 constexpr int G_STAGE = G_KC * (G_LDA + G_LDB);   // doubles per stage
 constexpr int G_SMEM = G_ST * G_STAGE * 8;
-static_assert(G_TN * G_LDC <= G_ST * G_STAGE, "accumulator staging must fit in the ring");
+static_assert(32 * G_LDC <= G_ST * G_STAGE, "accumulator staging (32 columns at a time) must fit in the ring");
 
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p)); }
 
@@ -486,33 +494,38 @@ __global__ void __launch_bounds__(256, 2) k_gemm(const GemmTask* __restrict__ ta
         mbar_arrive(&empty_bar[stg]);
     }
     __syncthreads();
-    // stage the product through shared memory so that the read-modify-write of C is coalesced
-    double* Cs = smem;   // Cs[n * G_LDC + m]
-#pragma unroll
-    for (int a = 0; a < 4; a++)
-#pragma unroll
-        for (int b = 0; b < 4; b++) {
-            int r = wm + a * 8 + lr;
-            int c = wn + b * 8 + 2 * lc;
-            Cs[c * G_LDC + r] = acc[a][b][0];
-            Cs[(c + 1) * G_LDC + r] = acc[a][b][1];
-        }
-    __syncthreads();
-    // all loads of C first (independent, deep memory-level parallelism), then update + store
-    constexpr int PER = 16;   // 2 passes x 16 elements per thread
+    // stage the product through shared memory so that the read-modify-write of C is coalesced;
+    // 32 columns at a time, so the staging area (and with it the ring) stays small: the less shared
+    // memory the kernel takes, the more L1 is left, which measurably helps
+    double* Cs = smem;   // Cs[n * G_LDC + m], n in [0, 32)
+    constexpr int PER = 16;   // 16 elements per thread and half
     const int i = threadIdx.x % G_TM, jb = threadIdx.x / G_TM;   // jb in {0,1}
 #pragma unroll
     for (int half = 0; half < 2; half++) {
+        if (half) __syncthreads();
+        if (wn == 32 * half) {
+#pragma unroll
+            for (int a = 0; a < 4; a++)
+#pragma unroll
+                for (int b = 0; b < 4; b++) {
+                    int r = wm + a * 8 + lr;
+                    int c = b * 8 + 2 * lc;
+                    Cs[c * G_LDC + r] = acc[a][b][0];
+                    Cs[(c + 1) * G_LDC + r] = acc[a][b][1];
+                }
+        }
+        __syncthreads();
+        // all loads of C first (independent, deep memory-level parallelism), then update + store
         double cv[PER];
 #pragma unroll
         for (int q = 0; q < PER; q++) {
-            int j = jb + 2 * (half * PER + q);
+            int j = 32 * half + jb + 2 * q;
             cv[q] = (i < mrem && j < nrem) ? C[i + (int64_t)j * tk.ldc] : 0.0;
         }
 #pragma unroll
         for (int q = 0; q < PER; q++) {
-            int j = jb + 2 * (half * PER + q);
-            if (i < mrem && j < nrem) C[i + (int64_t)j * tk.ldc] = cv[q] - Cs[j * G_LDC + i];
+            int j = 32 * half + jb + 2 * q;
+            if (i < mrem && j < nrem) C[i + (int64_t)j * tk.ldc] = cv[q] - Cs[(jb + 2 * q) * G_LDC + i];
         }
     }
 }
@@ -1142,46 +1155,76 @@ __global__ void __launch_bounds__(256, 2) k_sweep_big(const BigFront* __restrict
 // strictly lower part of the Larr block <- strictly lower part of L_kk^-1 (unit diagonal implied),
 // lower part of the UTarr block <- (U_kk^-1)^T = (U_kk^T)^-1.  Both are inverses of a LOWER
 // triangular matrix M stored in place (L_kk with unit diagonal; U_kk^T as stored), so one code path
-// serves both: grid (blocks, 2), y = 0 inverts L_kk, y = 1 U_kk^T.  64 threads; thread j computes
-// column j of M^-1 by forward substitution entirely in registers (the column is zero above row j,
-// so every thread can run the same fully unrolled loops), M is broadcast from shared memory.
-constexpr int INV_SMEM = 64 * 65 * 8;
+// serves both: grid (blocks, 2), y = 0 inverts L_kk, y = 1 U_kk^T.
+// Blocked: the eight 8 x 8 diagonal blocks are inverted by substitution, then the block size doubles
+// three times with  inv([[A, 0], [B, C]]) = [[A^-1, 0], [-C^-1 B A^-1, C^-1]]  (two small products per
+// off-diagonal block, all entries of a step in parallel): short dependency chains, small code.
+constexpr int INV_THREADS = 128;
 
-__global__ void __launch_bounds__(64) k_invert_diag(const DiagTask* __restrict__ tasks, double* __restrict__ heap) {
-    __shared__ double T[64 * 65];   // T[a + 65 b] = M(a,b), a > b ; afterwards the inverse
-    __shared__ double dinv[64];     // 1 / M(a,a)
+__global__ void __launch_bounds__(INV_THREADS) k_invert_diag(const DiagTask* __restrict__ tasks, double* __restrict__ heap) {
+    __shared__ double T[64 * 65];    // T[a + 65 b] = M(a,b), a >= b; inverted in place, block by block
+    __shared__ double Wk[32 * 32];   // B * A^-1 of the current step (all pairs)
     const DiagTask tk = tasks[blockIdx.x];
     const int kb = tk.kb, ld = tk.ld;
     const bool lower = blockIdx.y == 0;
     double* G = heap + (lower ? tk.Doff : tk.UTDoff);
-    const int j = threadIdx.x;
-    for (int e = threadIdx.x; e < 64 * 64; e += 64) {
-        int a = e & 63, b = e >> 6;
-        T[a + 65 * b] = (a < kb && b < kb && a > b) ? G[a + (int64_t)b * ld] : 0.0;
+    const int tid = threadIdx.x;
+    for (int e = tid; e < 64 * 64; e += INV_THREADS) {
+        const int a = e & 63, b = e >> 6;
+        double v = 0.0;
+        if (a == b) v = (lower || a >= kb) ? 1.0 : G[a + (int64_t)a * ld];
+        else if (a > b && a < kb) v = G[a + (int64_t)b * ld];
+        T[a + 65 * b] = v;
     }
-    dinv[j] = (lower || j >= kb) ? 1.0 : 1.0 / G[j + (int64_t)j * ld];
     __syncthreads();
-    double x[64];
+    {   // 8 x 8 diagonal blocks: thread = (block, column); in place via registers
+        const int base = 8 * ((tid & 63) >> 3), c = tid & 7;
+        double x[8];
 #pragma unroll
-    for (int i = 0; i < 64; i++) {
-        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        for (int i = 0; i < 8; i++) {
+            double acc = i == c ? 1.0 : 0.0;
 #pragma unroll
-        for (int p = 0; p < i; p++) {
-            const double t = T[i + 65 * p];
-            if ((p & 3) == 0) a0 = fma(t, x[p], a0);
-            else if ((p & 3) == 1) a1 = fma(t, x[p], a1);
-            else if ((p & 3) == 2) a2 = fma(t, x[p], a2);
-            else a3 = fma(t, x[p], a3);
+            for (int p = 0; p < i; p++) acc -= T[base + i + 65 * (base + p)] * x[p];
+            x[i] = acc / T[base + i + 65 * (base + i)];
         }
-        const double d = dinv[i];
-        x[i] = i == j ? d : (i > j ? -((a0 + a1) + (a2 + a3)) * d : 0.0);
-    }
-    __syncthreads();   // everybody has finished reading M
+        __syncthreads();
+        if (tid < 64)
 #pragma unroll
-    for (int i = 0; i < 64; i++) T[i + 65 * j] = x[i];
+            for (int i = 0; i < 8; i++) T[base + i + 65 * (base + c)] = x[i];
+    }
     __syncthreads();
-    for (int e = threadIdx.x; e < 64 * 64; e += 64) {
-        int a = e & 63, b = e >> 6;
+    for (int h = 8; h < 64; h *= 2) {
+        const int nent = 32 * h;   // (32 / h) pairs of h x h entries
+        // W = B * A^-1,  B = M[R0.., C0..] (still original),  A^-1 = T[C0.., C0..] (lower triangular)
+        for (int e = tid; e < nent; e += INV_THREADS) {
+            const int r = e % h, c = (e / h) % h, q = e / (h * h);
+            const int C0 = 2 * q * h, R0 = C0 + h;
+            double a0 = 0.0, a1 = 0.0;
+            for (int p = c; p < h; p++) {
+                const double t = T[R0 + r + 65 * (C0 + p)] * T[C0 + p + 65 * (C0 + c)];
+                if (p & 1) a1 += t;
+                else a0 += t;
+            }
+            Wk[e] = a0 + a1;
+        }
+        __syncthreads();
+        // the B block receives -C^-1 * W,  C^-1 = T[R0.., R0..] (lower triangular)
+        for (int e = tid; e < nent; e += INV_THREADS) {
+            const int r = e % h, c = (e / h) % h, q = e / (h * h);
+            const int C0 = 2 * q * h, R0 = C0 + h;
+            const double* wq = Wk + q * h * h + h * c;
+            double a0 = 0.0, a1 = 0.0;
+            for (int p = 0; p <= r; p++) {
+                const double t = T[R0 + r + 65 * (R0 + p)] * wq[p];
+                if (p & 1) a1 += t;
+                else a0 += t;
+            }
+            T[R0 + r + 65 * (C0 + c)] = -(a0 + a1);
+        }
+        __syncthreads();
+    }
+    for (int e = tid; e < 64 * 64; e += INV_THREADS) {
+        const int a = e & 63, b = e >> 6;
         if (a < kb && b < kb && (lower ? a > b : a >= b)) G[a + (int64_t)b * ld] = T[a + 65 * b];
     }
 }

@@ -106,8 +106,6 @@ struct nkp_solver {
     int n = 0;
     int64_t nnz = 0;
     cudaStream_t stream = nullptr;
-    cudaStream_t side = nullptr;          // diagonal-block inversion of finished levels, concurrent with the levels above
-    cudaEvent_t ev_level = nullptr, ev_side = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     // device data
     double* heap = nullptr;
@@ -221,6 +219,7 @@ void nkp_default_options(nkp_options* o) {
     if ((e = getenv("NKP_LEAF"))) o->leaf = atoi(e);
     if ((e = getenv("NKP_VERBOSE"))) o->verbose = atoi(e);
     if ((e = getenv("NKP_EQUIL"))) o->equil = atoi(e);
+    if ((e = getenv("NKP_REFINE_RULE"))) o->refine_rule = atoi(e);
 }
 
 static int create_impl(nkp_solver** out, int n, const int* rowptr, const int* colind, const int* ci,
@@ -287,9 +286,6 @@ static int create_impl(nkp_solver** out, int n, const int* rowptr, const int* co
     } while (0)
     auto body = [&]() -> int {
         CK(cudaStreamCreate(&s->stream));
-        CK(cudaStreamCreateWithFlags(&s->side, cudaStreamNonBlocking));
-        CK(cudaEventCreateWithFlags(&s->ev_level, cudaEventDisableTiming));
-        CK(cudaEventCreateWithFlags(&s->ev_side, cudaEventDisableTiming));
         for (int i = 0; i < 4; i++) CK(cudaEventCreate(&s->ev[i]));
         if (nranks > 1) {
             if (!nccl_load()) {
@@ -483,19 +479,15 @@ static int do_factor(nkp_solver* s) {
                 prof_mark(s, KC_GEMM);
             }
         }
-        // the sweeps use inverted 64 x 64 diagonal blocks; nothing above this level reads them, so the
-        // inversion of a finished level runs on the side stream while the main stream factors on
+        // the sweeps use inverted 64 x 64 diagonal blocks; nothing above this level reads them.  (Running
+        // this on a second stream next to the upper levels was measured slower: its small CTAs displace
+        // Schur-update CTAs.)
         if (L.inv_end > L.inv_begin) {
-            CK(cudaEventRecord(s->ev_level, st));
-            CK(cudaStreamWaitEvent(s->side, s->ev_level, 0));
-            k_invert_diag<<<dim3((unsigned)(L.inv_end - L.inv_begin), 2), 64, 0, s->side>>>(s->d_inv + L.inv_begin,
-                                                                                                   s->heap);
+            k_invert_diag<<<dim3((unsigned)(L.inv_end - L.inv_begin), 2), INV_THREADS, 0, st>>>(s->d_inv + L.inv_begin, s->heap);
             s->launches++;
+            prof_mark(s, KC_DIAG);
         }
     }
-    // the sweeps' inverted diagonal blocks: the main stream joins the side stream (part of the factorisation time)
-    CK(cudaEventRecord(s->ev_side, s->side));
-    CK(cudaStreamWaitEvent(st, s->ev_side, 0));
     CK(cudaEventRecord(s->ev[2], st));
     CK(cudaGetLastError());
     int nrepl = 0;
@@ -727,6 +719,14 @@ static int solve_chunk(nkp_solver* s, double* dB, int ldb, int nr, double* berr_
     for (int c = 0; c < nr; c++) last[c] = 1e300;
     double berr[MAX_NR] = {0};
     bool done[MAX_NR] = {false};
+    const bool normwise = s->opt.refine_rule == 1;
+    double bnorm2[MAX_NR] = {0}, rnorm2[MAX_NR] = {0};
+    if (normwise) {
+        CK(cudaMemsetAsync(s->d_berr + MAX_NR, 0, sizeof(double) * MAX_NR, st));
+        k_sumsq<<<256, 256, 0, st>>>(n, nr, dB, ldb, s->d_berr + MAX_NR);
+        s->launches++;
+        CK(cudaMemcpyAsync(bnorm2, s->d_berr + MAX_NR, sizeof(double) * nr, cudaMemcpyDeviceToHost, st));
+    }
     int it = 0;
     for (;;) {
         // r = b - A x, berr
@@ -734,6 +734,12 @@ static int solve_chunk(nkp_solver* s, double* dB, int ldb, int nr, double* berr_
         k_residual<<<dim3(g, nr), 256, 0, st>>>(n, nr, s->d_rowptr, s->d_colind, s->d_val, s->d_x, n, dB, ldb, s->d_r, s->d_berr, safe);
         s->launches++;
         CK(cudaMemcpyAsync(berr, s->d_berr, sizeof(double) * nr, cudaMemcpyDeviceToHost, st));
+        if (normwise) {
+            CK(cudaMemsetAsync(s->d_berr + 2 * MAX_NR, 0, sizeof(double) * MAX_NR, st));
+            k_sumsq<<<256, 256, 0, st>>>(n, nr, s->d_r, n, s->d_berr + 2 * MAX_NR);
+            s->launches++;
+            CK(cudaMemcpyAsync(rnorm2, s->d_berr + 2 * MAX_NR, sizeof(double) * nr, cudaMemcpyDeviceToHost, st));
+        }
         CK(cudaStreamSynchronize(st));
         if (s->opt.verbose > 1) {
             fprintf(stderr, "[nkp] refine it %d berr:", it);
@@ -744,9 +750,12 @@ static int solve_chunk(nkp_solver* s, double* dB, int ldb, int nr, double* berr_
         for (int c = 0; c < nr; c++) {
             // SuperLU pdgsrfs, per right-hand side: continue while berr > eps and berr decreased by
             // at least a factor 2; a column that stops once stays stopped
-            if (!done[c] && berr[c] > eps && berr[c] * 2.0 <= last[c]) go = true;
+            // refine_rule 1 applies the same logic to the normwise relative residual with threshold 1e-14
+            const double crit = normwise ? (bnorm2[c] > 0 ? std::sqrt(rnorm2[c] / bnorm2[c]) : 0.0) : berr[c];
+            const double tol = normwise ? 1e-14 : eps;
+            if (!done[c] && crit > tol && crit * 2.0 <= last[c]) go = true;
             else done[c] = true;
-            last[c] = berr[c];
+            last[c] = crit;
         }
         if (!go || it >= s->opt.refine_max) break;
         it++;
@@ -986,6 +995,12 @@ int nkp_set_profile(nkp_solver* s, int on) {
     return NKP_OK;
 }
 
+int nkp_set_refine_rule(nkp_solver* s, int rule) {
+    if (!s || rule < 0 || rule > 1) return NKP_EINVAL;
+    s->opt.refine_rule = rule;
+    return NKP_OK;
+}
+
 int nkp_sync(nkp_solver* s) {
     if (!s) return NKP_EINVAL;
     CK(cudaStreamSynchronize(s->stream));
@@ -1011,9 +1026,6 @@ void nkp_destroy(nkp_solver* s) {
     for (int i = 0; i < 4; i++)
         if (s->ev[i]) cudaEventDestroy(s->ev[i]);
     for (cudaEvent_t e : s->prof_ev) cudaEventDestroy(e);
-    if (s->ev_level) cudaEventDestroy(s->ev_level);
-    if (s->ev_side) cudaEventDestroy(s->ev_side);
-    if (s->side) cudaStreamDestroy(s->side);
     if (s->stream) cudaStreamDestroy(s->stream);
     delete s;
 }

@@ -15,12 +15,12 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libnkprecond.so")
+LIB_PATH = os.environ.get("NKP_LIB", os.path.join(_HERE, "libnkprecond.so"))   # NKP_LIB: developer override
 
 
 class NkpOptions(C.Structure):
     _fields_ = [("nb", C.c_int), ("leaf", C.c_int), ("equil", C.c_int), ("refine_max", C.c_int),
-                ("device", C.c_int), ("verbose", C.c_int), ("reserved", C.c_int * 10)]
+                ("device", C.c_int), ("verbose", C.c_int), ("refine_rule", C.c_int), ("reserved", C.c_int * 9)]
 
 
 class NkpStats(C.Structure):
@@ -69,6 +69,7 @@ def load_library():
     lib.nkp_get_stats.argtypes = [vp, P(NkpStats)]
     lib.nkp_sync.argtypes = [vp]
     lib.nkp_set_profile.argtypes = [vp, C.c_int]
+    lib.nkp_set_refine_rule.argtypes = [vp, C.c_int]
     lib.nkp_destroy.argtypes = [vp]
     lib.nkp_destroy.restype = None
     lib.nkp_last_error.restype = C.c_char_p
@@ -195,6 +196,10 @@ class TracerJacobianSolver:
 
     def set_profile(self, on=True):
         _check(self._lib.nkp_set_profile(self._h, int(bool(on))), "nkp_set_profile")
+
+    def set_refine_rule(self, rule):
+        """0: SuperLU's componentwise berr rule (default); 1: normwise ||r|| <= 1e-14 ||b||."""
+        _check(self._lib.nkp_set_refine_rule(self._h, int(rule)), "nkp_set_refine_rule")
 
     def sync(self):
         _check(self._lib.nkp_sync(self._h), "nkp_sync")

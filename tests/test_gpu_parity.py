@@ -332,3 +332,23 @@ def test_native_batch_driver_cli(tmp_path, golden_matrix):
     assert bad.returncode != 0 and "usage" in bad.stderr
     missing = subprocess.run([prog, "-v", "NOPE", str(mat), str(tr)], capture_output=True, text=True)
     assert missing.returncode != 0
+
+
+def test_normwise_refinement_rule_meets_the_tolerances():
+    """nkp_options.refine_rule = 1 stops on ||b - A x|| <= 1e-14 ||b||: never more steps than SuperLU's
+    berr rule, and the BASELINE.json tolerances (residual 1e-10, solution 1e-8) still hold."""
+    from nk_ocn_tracer_jacobian_precond_b200 import solver
+    c = synth_case(40, 46, 24, seed=1)
+    A = sp.csr_matrix((c["nzval"], c["colind"], c["rowptr"]), shape=(c["n"], c["n"]))
+    s = solver.TracerJacobianSolver(c["n"], c["rowptr"], c["colind"], coords=(c["i"], c["j"], c["k"]))
+    s.factor(c["nzval"])
+    xs = np.random.default_rng(3).standard_normal((c["n"], 8))
+    B = np.asfortranarray(A @ xs)
+    X0 = B.copy(order="F"); s.solve(X0); steps0 = s.stats()["refine_steps"]
+    s.set_refine_rule(1)
+    X1 = B.copy(order="F"); s.solve(X1); steps1 = s.stats()["refine_steps"]
+    assert steps1 <= steps0
+    assert (np.linalg.norm(A @ X1 - B, axis=0) / np.linalg.norm(B, axis=0)).max() <= RES_TOL
+    assert (np.linalg.norm(X1 - xs, axis=0) / np.linalg.norm(xs, axis=0)).max() <= SOL_TOL
+    assert np.linalg.norm(X1 - X0) / np.linalg.norm(X0) <= 1e-9
+    s.close()
