@@ -833,7 +833,7 @@ int analyse(int n, const int* rowptr, const int* colind, const int* const coords
                 bf.m = st.m;
                 bf.npiv = (st.s + 63) / 64;
                 bf.nslab = bf.npiv + (st.r + 63) / 64;
-                bf.flag0 = plan.n_big_flags;
+                bf.pad0 = 0;
                 bf.nchild = st.nchild;
                 bf.child_list = st.child_list;
                 bf.nchunk = ((st.r + 63) / 64 + BWD_CHUNK - 1) / BWD_CHUNK;
@@ -849,7 +849,6 @@ int analyse(int n, const int* rowptr, const int* colind, const int* const coords
                     }
                 }
                 part_slots += (int64_t)bf.npiv * bf.nchunk;
-                plan.n_big_flags += bf.npiv;
                 plan.big_fronts.push_back(bf);
             } else {
                 plan.solve_small.push_back(st);

@@ -1144,10 +1144,13 @@ __global__ void __launch_bounds__(256, 2) k_sweep_big(const BigFront* __restrict
             if (2 * lc < nr) y[bf.first + r0 + p + (int64_t)(2 * lc) * n] = o0;
             if (2 * lc + 1 < nr) y[bf.first + r0 + p + (int64_t)(2 * lc + 1) * n] = o1;
         }
-        __threadfence();
+        // publish: the CTA barrier orders every thread's stores before thread 0's fence + release store
+        // (the grid-sync pattern), so the other 255 threads do not each pay a device-wide fence
         __syncthreads();
-        if (tid == 0)
+        if (tid == 0) {
+            __threadfence();
             st_release_u64(cnt + item.front, ((unsigned long long)epoch << 32) | (unsigned)(FWD ? i + 1 : bf.npiv - i));
+        }
     }
 }
 

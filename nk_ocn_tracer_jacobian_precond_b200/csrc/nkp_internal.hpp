@@ -115,7 +115,7 @@ struct BigFront {
     int first, s, r, m;
     int npiv;    // ceil(s / 64) pivot blocks
     int nslab;   // npiv + ceil(r / 64) row slabs
-    int flag0;   // first flag of this front (one per pivot block)
+    int pad0;
     int nchild;
     int64_t child_list;  // into Plan::solve_children
     int64_t part_off;    // backward sweep: first 64 x 8 partial-product slot of this front (level scratch)
@@ -203,7 +203,6 @@ struct Plan {
     int64_t bwd_part_slots = 0;           // 64 x 8 partial-product slots needed by the largest level
     std::vector<int> child_lo;            // see BigFront::clo_off
     std::vector<DiagTask> inv_tasks;      // diagonal blocks of the big fronts: inverted in place after the factorisation
-    int n_big_flags = 0;
     int64_t factor_len = 0;    // doubles in the factor arena  [0, factor_len)
     int64_t pool_len[2] = {0, 0};  // update-matrix pools follow the arena
     int64_t pool_off[2] = {0, 0};
