@@ -376,8 +376,10 @@ def run_own(args):
         solve_gbs = st["solve_bytes"] / sweep_s * 1e-9
         roofline_solve = {
             "kernel": "k_fwd/k_bwd sweep pair (nrhs=%d, no refinement)" % NRHS, "bound": "hbm",
-            "achieved": solve_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": solve_gbs / peaks["hbm_gbs"],
-            "peak_source": peaks["_hbm_src"], "traffic": None, "sweep_pair_ms": sweep_s * 1e3,
+            "achieved": solve_gbs, "peak": peaks["hbm_gbs"] * world, "unit": "GB/s",
+            "frac": solve_gbs / (peaks["hbm_gbs"] * world),
+            "peak_source": peaks["_hbm_src"] + (f" x {world} GPUs (whole-job bytes over the max-over-ranks time)" if world > 1 else ""),
+            "traffic": None, "sweep_pair_ms": sweep_s * 1e3,
             "alg_bytes_per_sweep_pair": st["solve_bytes"],
         }
         spmv_s = float(np.min(spmv_t))
