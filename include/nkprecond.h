@@ -82,10 +82,19 @@ typedef struct nkp_stats {
     double factor_flops_local; /* multi-GPU: flops of the fronts owned by this rank       */
     double nnz_lu_local;
     double n_xfers;          /* parent/child pairs whose data crosses GPUs               */
-    double reserved[5];
+    double order_cached;     /* 1: the ordering came from the on-disk analysis cache      */
+    double reserved[4];
 } nkp_stats;
 
 void nkp_default_options(nkp_options* opt);
+
+/* On-disk cache of the pattern-dependent ordering (the expensive part of the analysis), keyed by a hash
+ * of (rowptr, colind, coordinates, ordering options).  The reference repeats the whole analysis in every
+ * process (src/solve_ABglobal.c:350-353); with a cache directory set, nkp_create stores the nested-
+ * dissection tree there and later processes -- e.g. the next Newton iteration's solver run -- read it
+ * back.  Process-wide; dir = NULL or "" disables it.  Without this call the environment variable
+ * NKP_ANALYSIS_CACHE is consulted.  A missing, stale or damaged file only means "recompute". */
+int nkp_set_analysis_cache(const char* dir);
 
 /* Analysis (ordering, symbolic factorisation, memory plan, task lists) for the pattern
  * (n, rowptr, colind), 0-based CRS as in src/matrix.c:84-88.  coord_i/j/k are optional

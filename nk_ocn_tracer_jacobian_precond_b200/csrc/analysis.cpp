@@ -25,8 +25,12 @@
 #include <algorithm>
 #include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
+#include <string>
+
+#include <unistd.h>
 
 namespace nkp {
 
@@ -320,7 +324,134 @@ struct Dissector {
     }
 };
 
+// ---- on-disk cache of the ordering ------------------------------------
+// The nested dissection is the expensive, purely pattern-dependent part of the analysis (about two
+// thirds of it at gx1v6-shape).  The reference refactors from scratch on every process start
+// (src/solve_ABglobal.c:350-353); with a cache directory set (nkp_set_analysis_cache or the
+// NKP_ANALYSIS_CACHE environment variable) the dissection tree is stored under a key derived from
+// the pattern, the coordinates and the ordering options, and later processes read it back.
+// File: magic, key, n, nf, nroots, node sizes[nf], node parents[nf], roots[nroots], iperm[n]
+// (= the vertices of the nodes in node order).  Any mismatch or short read means "recompute".
+
+std::string g_cache_dir;
+bool g_cache_dir_set = false;
+
+uint64_t fnv1a(uint64_t h, const void* data, size_t bytes) {
+    const unsigned char* p = static_cast<const unsigned char*>(data);
+    for (size_t i = 0; i < bytes; i++) {
+        h ^= p[i];
+        h *= 1099511628211ull;
+    }
+    return h;
+}
+
+uint64_t ordering_key(int n, const int* rowptr, const int* colind, const int* const* coords, const Options& opt) {
+    uint64_t h = 1469598103934665603ull;
+    const int tag[4] = {0x4e4b5031 /* format 1 */, n, opt.leaf, opt.period_i};
+    h = fnv1a(h, tag, sizeof tag);
+    h = fnv1a(h, rowptr, sizeof(int) * ((size_t)n + 1));
+    h = fnv1a(h, colind, sizeof(int) * (size_t)rowptr[n]);
+    for (int d = 0; d < 3; d++) {
+        const int present = coords && coords[d] ? 1 : 0;
+        h = fnv1a(h, &present, sizeof present);
+        if (present) h = fnv1a(h, coords[d], sizeof(int) * (size_t)n);
+    }
+    return h;
+}
+
+std::string cache_dir() {
+    if (g_cache_dir_set) return g_cache_dir;
+    const char* e = getenv("NKP_ANALYSIS_CACHE");
+    return e ? std::string(e) : std::string();
+}
+
+std::string cache_path(const std::string& dir, uint64_t key) {
+    char name[64];
+    snprintf(name, sizeof name, "/nkp_order_%016llx.bin", (unsigned long long)key);
+    return dir + name;
+}
+
+const char CACHE_MAGIC[8] = {'N', 'K', 'P', 'O', 'R', 'D', '1', 0};
+
+bool load_ordering(const std::string& path, uint64_t key, int n, std::vector<TreeNode>& nodes, std::vector<int>& roots) {
+    FILE* f = fopen(path.c_str(), "rb");
+    if (!f) return false;
+    bool ok = false;
+    char magic[8];
+    uint64_t k = 0;
+    int hdr[3] = {0, 0, 0};
+    std::vector<int> sizes, parents, iperm;
+    do {
+        if (fread(magic, 1, 8, f) != 8 || memcmp(magic, CACHE_MAGIC, 8) != 0) break;
+        if (fread(&k, sizeof k, 1, f) != 1 || k != key) break;
+        if (fread(hdr, sizeof(int), 3, f) != 3 || hdr[0] != n || hdr[1] <= 0 || hdr[1] > n || hdr[2] <= 0 || hdr[2] > hdr[1]) break;
+        const int nf = hdr[1], nr = hdr[2];
+        sizes.resize(nf);
+        parents.resize(nf);
+        roots.resize(nr);
+        iperm.resize(n);
+        if (fread(sizes.data(), sizeof(int), nf, f) != (size_t)nf) break;
+        if (fread(parents.data(), sizeof(int), nf, f) != (size_t)nf) break;
+        if (fread(roots.data(), sizeof(int), nr, f) != (size_t)nr) break;
+        if (fread(iperm.data(), sizeof(int), n, f) != (size_t)n) break;
+        // consistency: sizes sum to n, parents come later (postorder), iperm is a permutation
+        int64_t tot = 0;
+        bool good = true;
+        for (int t = 0; t < nf && good; t++) {
+            good = sizes[t] > 0 && (parents[t] == -1 || (parents[t] > t && parents[t] < nf));
+            tot += sizes[t];
+        }
+        if (!good || tot != n) break;
+        std::vector<char> seen(n, 0);
+        for (int i = 0; i < n && good; i++) {
+            good = iperm[i] >= 0 && iperm[i] < n && !seen[iperm[i]];
+            if (good) seen[iperm[i]] = 1;
+        }
+        for (int r : roots) good = good && r >= 0 && r < nf && parents[r] == -1;
+        if (!good) break;
+        nodes.assign(nf, TreeNode());
+        int pos = 0;
+        for (int t = 0; t < nf; t++) {
+            nodes[t].verts.assign(iperm.begin() + pos, iperm.begin() + pos + sizes[t]);
+            pos += sizes[t];
+            nodes[t].parent = parents[t];
+            if (parents[t] >= 0) nodes[parents[t]].children.push_back(t);   // creation order == index order
+        }
+        ok = true;
+    } while (false);
+    fclose(f);
+    return ok;
+}
+
+void save_ordering(const std::string& path, uint64_t key, int n, const std::vector<TreeNode>& nodes, const std::vector<int>& roots) {
+    char tmp[32];
+    snprintf(tmp, sizeof tmp, ".tmp%ld", (long)getpid());
+    const std::string tpath = path + tmp;
+    FILE* f = fopen(tpath.c_str(), "wb");
+    if (!f) return;
+    const int nf = (int)nodes.size();
+    const int hdr[3] = {n, nf, (int)roots.size()};
+    std::vector<int> sizes(nf), parents(nf);
+    for (int t = 0; t < nf; t++) {
+        sizes[t] = (int)nodes[t].verts.size();
+        parents[t] = nodes[t].parent;
+    }
+    bool ok = fwrite(CACHE_MAGIC, 1, 8, f) == 8 && fwrite(&key, sizeof key, 1, f) == 1 && fwrite(hdr, sizeof(int), 3, f) == 3 &&
+              fwrite(sizes.data(), sizeof(int), nf, f) == (size_t)nf && fwrite(parents.data(), sizeof(int), nf, f) == (size_t)nf &&
+              fwrite(roots.data(), sizeof(int), roots.size(), f) == roots.size();
+    for (int t = 0; t < nf && ok; t++)
+        ok = fwrite(nodes[t].verts.data(), sizeof(int), nodes[t].verts.size(), f) == nodes[t].verts.size();
+    ok = (fclose(f) == 0) && ok;
+    if (ok) ok = rename(tpath.c_str(), path.c_str()) == 0;   // atomic: concurrent ranks write the same content
+    if (!ok) remove(tpath.c_str());
+}
+
 }  // namespace
+
+void set_analysis_cache_dir(const char* dir) {
+    g_cache_dir_set = true;
+    g_cache_dir = dir ? dir : "";
+}
 
 int analyse(int n, const int* rowptr, const int* colind, const int* const coords[3],
             const Options& opt, Plan& plan) {
@@ -338,7 +469,18 @@ int analyse(int n, const int* rowptr, const int* colind, const int* const coords
     bool have_coords = coords && (coords[0] || coords[1] || coords[2]);
     Dissector ds(g, have_coords ? coords : nullptr, opt);
     std::vector<int> roots;
-    ds.build(0, n, roots);
+    const std::string cdir = cache_dir();
+    uint64_t key = 0;
+    if (!cdir.empty()) {
+        key = ordering_key(n, rowptr, colind, have_coords ? coords : nullptr, opt);
+        plan.order_cached = load_ordering(cache_path(cdir, key), key, n, ds.nodes, roots);
+    }
+    if (!plan.order_cached) {
+        roots.clear();        // a rejected cache file may have left partial data behind
+        ds.nodes.clear();
+        ds.build(0, n, roots);
+        if (!cdir.empty()) save_ordering(cache_path(cdir, key), key, n, ds.nodes, roots);
+    }
     std::vector<TreeNode>& nodes = ds.nodes;
     int nf = (int)nodes.size();
 

@@ -213,6 +213,7 @@ struct Plan {
     int64_t nnz_lu = 0;        // stored factor entries incl. diagonal
     int max_front = 0;
     double t_order = 0, t_symbolic = 0, t_plan = 0;
+    bool order_cached = false;     // the dissection tree came from the on-disk cache
     // multi-GPU partition (identical on every rank)
     int rank = 0, nranks = 1;
     std::vector<int> owner;          // per front
@@ -225,6 +226,9 @@ struct Plan {
 };
 
 // analysis.cpp
+// directory of the on-disk ordering cache; nullptr or "" disables it.  Until this is called the
+// NKP_ANALYSIS_CACHE environment variable decides.
+void set_analysis_cache_dir(const char* dir);
 // coords may be null; otherwise coords[d] (d = 0,1,2) are per-unknown integer coordinates
 int analyse(int n, const int* rowptr, const int* colind, const int* const coords[3],
             const Options& opt, Plan& plan);

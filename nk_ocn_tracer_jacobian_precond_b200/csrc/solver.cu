@@ -207,6 +207,11 @@ static int upload(T** dptr, const std::vector<T>& v) {
 const char* nkp_last_error(void) { return g_err.c_str(); }
 const char* nkp_version(void) { return "nkprecond-b200 0.1 (sm_100a)"; }
 
+int nkp_set_analysis_cache(const char* dir) {
+    set_analysis_cache_dir(dir);
+    return NKP_OK;
+}
+
 void nkp_default_options(nkp_options* o) {
     memset(o, 0, sizeof(*o));
     o->nb = 64;
@@ -986,6 +991,7 @@ int nkp_get_stats(const nkp_solver* s, nkp_stats* st) {
     st->factor_flops_local = P.flops_local;
     st->nnz_lu_local = (double)P.nnz_lu_local;
     st->n_xfers = (double)P.xfers.size();
+    st->order_cached = P.order_cached ? 1.0 : 0.0;
     return NKP_OK;
 }
 

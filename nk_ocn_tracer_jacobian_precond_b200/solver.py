@@ -32,7 +32,7 @@ class NkpStats(C.Structure):
                 ("t_gemm", C.c_double), ("gemm_flops", C.c_double), ("n_gemm", C.c_int64),
                 ("t_trsm", C.c_double), ("t_diag", C.c_double), ("t_extend_add", C.c_double),
                 ("t_sweeps", C.c_double), ("factor_flops_local", C.c_double), ("nnz_lu_local", C.c_double),
-                ("n_xfers", C.c_double), ("reserved", C.c_double * 5)]
+                ("n_xfers", C.c_double), ("order_cached", C.c_double), ("reserved", C.c_double * 4)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
@@ -68,6 +68,7 @@ def load_library():
     lib.nkp_get_perm.argtypes = [vp, P(C.c_int)]
     lib.nkp_get_stats.argtypes = [vp, P(NkpStats)]
     lib.nkp_sync.argtypes = [vp]
+    lib.nkp_set_analysis_cache.argtypes = [C.c_char_p]
     lib.nkp_set_profile.argtypes = [vp, C.c_int]
     lib.nkp_set_refine_rule.argtypes = [vp, C.c_int]
     lib.nkp_destroy.argtypes = [vp]
@@ -90,6 +91,11 @@ def comm_unique_id() -> bytes:
     buf = C.create_string_buffer(UNIQUE_ID_BYTES)
     _check(load_library().nkp_comm_unique_id(buf), "nkp_comm_unique_id")
     return buf.raw
+
+
+def set_analysis_cache(path):
+    """Directory of the on-disk ordering cache (None disables); see nkp_set_analysis_cache."""
+    _check(load_library().nkp_set_analysis_cache(None if path is None else os.fsencode(path)), "nkp_set_analysis_cache")
 
 
 def _check(rc, what):

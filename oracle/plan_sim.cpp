@@ -137,7 +137,13 @@ void sim_invert_diag(double* H, const DiagTask& t) {
 
 }  // namespace
 
+static int g_last_order_cached = 0;
+
 extern "C" {
+
+// ordering cache of the analysis (csrc/analysis.cpp): directory, and whether the last analysis used it
+void nkp_sim_set_cache_dir(const char* dir) { set_analysis_cache_dir(dir); }
+int nkp_sim_last_order_cached(void) { return g_last_order_cached; }
 
 // Interprets the plans of `nranks` ranks in lockstep inside one process: every rank has its own
 // heap / work vectors; Plan::xfers and the top-front broadcasts are carried out as memcpys.
@@ -165,6 +171,7 @@ int nkp_sim_run_dist(int n, const int* rowptr, const int* colind, const double* 
         if (rc) return rc;
     }
     Plan& P0 = plans[0];
+    g_last_order_cached = P0.order_cached ? 1 : 0;
     if (stats_out) {
         stats_out[0] = (double)P0.fronts.size();
         stats_out[1] = P0.nlevels;

@@ -352,3 +352,23 @@ def test_normwise_refinement_rule_meets_the_tolerances():
     assert (np.linalg.norm(X1 - xs, axis=0) / np.linalg.norm(xs, axis=0)).max() <= SOL_TOL
     assert np.linalg.norm(X1 - X0) / np.linalg.norm(X0) <= 1e-9
     s.close()
+
+
+def test_analysis_cache_on_the_gpu_path(golden_matrix, tmp_path):
+    """nkp_set_analysis_cache: the second nkp_create of the same pattern reads the ordering back
+    (stats.order_cached) and factor + solve give bitwise the same answer."""
+    from nk_ocn_tracer_jacobian_precond_b200 import solver
+    c = _golden_case(golden_matrix)
+    b = np.random.default_rng(9).standard_normal(c["n"])
+    solver.set_analysis_cache(str(tmp_path))
+    try:
+        xs = []
+        for expect in (0.0, 1.0):
+            s = solver.TracerJacobianSolver(c["n"], c["rowptr"], c["colind"], coords=(c["i"], c["j"], c["k"]))
+            assert s.stats()["order_cached"] == expect
+            s.factor(c["nzval"])
+            x = b.copy(); s.solve(x); xs.append(x)
+            s.close()
+        assert np.array_equal(xs[0], xs[1])
+    finally:
+        solver.set_analysis_cache(None)

@@ -121,3 +121,41 @@ def test_plan_interpreter_on_reference_test_options(sim_lib, reftest_matrix, ref
     assert rel.max() <= 1e-8, rel
     Xo = oracle_solve.solve(m["n"], m["rowptr"], m["colind"], m["nzval_row_wise"], reftest_rhs["B"])
     assert np.allclose(Xo, reftest_rhs["X"], rtol=1e-11, atol=0)
+
+
+def test_ordering_cache_round_trip(sim_lib, golden_matrix, golden_rhs, tmp_path):
+    """the nested-dissection tree is stored on disk under a pattern hash and read
+    back by a later analysis; the cached plan is the same plan (identical permutation, statistics and
+    solution); a different pattern gets its own file; a damaged file only means 'recompute'."""
+    import ctypes
+    m = golden_matrix
+    coords = (m["tracer_state_ind_to_i"], m["tracer_state_ind_to_j"], m["tracer_state_ind_to_k"])
+    args = (m["n"], m["rowptr"], m["colind"], m["nzval_row_wise"], coords, golden_rhs["B"])
+    sim_lib.nkp_sim_set_cache_dir.argtypes = [ctypes.c_char_p]
+    sim_lib.nkp_sim_set_cache_dir(None)
+    X0, st0, p0 = run_sim(sim_lib, *args)
+    assert sim_lib.nkp_sim_last_order_cached() == 0
+    cache = tmp_path / "cache"
+    cache.mkdir()
+    sim_lib.nkp_sim_set_cache_dir(str(cache).encode())
+    try:
+        X1, st1, p1 = run_sim(sim_lib, *args)                 # miss: computes and stores
+        assert sim_lib.nkp_sim_last_order_cached() == 0
+        files = sorted(cache.iterdir())
+        assert len(files) == 1 and files[0].name.startswith("nkp_order_")
+        X2, st2, p2 = run_sim(sim_lib, *args)                 # hit
+        assert sim_lib.nkp_sim_last_order_cached() == 1
+        assert np.array_equal(p0, p1) and np.array_equal(p0, p2)
+        assert np.array_equal(st0[:6], st2[:6])
+        assert np.array_equal(X0, X2)                          # same plan, same arithmetic: bitwise
+        # without coordinates the ordering differs, and so does the key
+        run_sim(sim_lib, m["n"], m["rowptr"], m["colind"], m["nzval_row_wise"], None, golden_rhs["B"])
+        assert sim_lib.nkp_sim_last_order_cached() == 0 and len(list(cache.iterdir())) == 2
+        # a truncated file is ignored and rewritten
+        data = files[0].read_bytes()
+        files[0].write_bytes(data[: len(data) // 2])
+        X3, _, p3 = run_sim(sim_lib, *args)
+        assert sim_lib.nkp_sim_last_order_cached() == 0 and np.array_equal(p0, p3)
+        assert files[0].stat().st_size == len(data)
+    finally:
+        sim_lib.nkp_sim_set_cache_dir(None)
