@@ -122,6 +122,11 @@ int nkp_create_dist(nkp_solver** out, int n, const int* rowptr, const int* colin
 /* Numeric factorisation from HOST values (nzval_row_wise, src/matrix.c:84), includes the
  * host->device copy.  Replaces pdgssvx*(nrhs = 0). */
 int nkp_factor(nkp_solver* s, const double* nzval);
+/* Same from values in FILE byte order: nnz big-endian IEEE doubles exactly as they lie in the
+ * nzval_row_wise variable of the NetCDF-3 matrix file (src/matrix.c:3880; locate them with
+ * nkp_nc3_inq_var_extent, include/nkp_nc3.h).  The bytes travel to the device unchanged and are swapped
+ * there, replacing the host loop behind nc_get_var_double in get_sparse_matrix (src/matrix.c:3996). */
+int nkp_factor_be(nkp_solver* s, const void* nzval_be);
 /* Same with the values already resident in device memory. */
 int nkp_factor_device(nkp_solver* s, const double* d_nzval);
 

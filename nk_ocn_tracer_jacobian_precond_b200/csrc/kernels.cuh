@@ -111,6 +111,17 @@ __global__ void k_col_scale(int n, double* __restrict__ C) {
     C[i] = c;
 }
 
+// big-endian IEEE doubles (NetCDF-3 external representation, src/matrix.c:3880) -> host-order doubles;
+// src may alias dst (every thread converts its own element)
+__global__ void __launch_bounds__(256) k_bswap64(const unsigned long long* src, double* dst, int64_t n) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned long long v = src[i];
+    const unsigned lo = (unsigned)v, hi = (unsigned)(v >> 32);
+    const unsigned long long w = ((unsigned long long)__byte_perm(lo, 0, 0x0123) << 32) | __byte_perm(hi, 0, 0x0123);
+    dst[i] = __longlong_as_double((long long)w);
+}
+
 __global__ void k_fill(double* p, int64_t n, double v) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = v;

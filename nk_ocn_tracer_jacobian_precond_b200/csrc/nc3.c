@@ -1242,3 +1242,29 @@ nc_put_var_double (int ncid, int varid, const double *dp)
 {
    return put_var (ncid, varid, dp, 1);
 }
+
+/* Not part of the NetCDF API (declared in include/nkp_nc3.h): where the data of a fixed-size variable
+ * lies in the file and what it is, so that a caller can read the big-endian bytes itself and have
+ * them converted on the GPU (nkp_factor_be) instead of by the host loops above. */
+int
+nkp_nc3_inq_var_extent (int ncid, int varid, long long *offset, long long *nbytes, int *xtype)
+{
+   nc3_file *f = get_file (ncid);
+   const nc3_var *v;
+   if (f == NULL)
+      return NC_EBADID;
+   if (f->define_mode)
+      return NC_EINDEFINE;
+   if (varid < 0 || varid >= f->nvars)
+      return NC_ENOTVAR;
+   v = &f->vars[varid];
+   if (v->is_rec)
+      return NC_EINVAL;
+   if (offset)
+      *offset = (long long) v->begin;
+   if (nbytes)
+      *nbytes = (long long) (var_nelems (f, v) * type_size (v->type));
+   if (xtype)
+      *xtype = (int) v->type;
+   return NC_NOERR;
+}

@@ -20,6 +20,7 @@
  * Host code stays in C and reaches CUDA only through include/nkprecond.h; files are read
  * with the nc_* subset of include/compat/netcdf.h (libnkp_nc3.so, or a real libnetcdf).
  */
+#define _FILE_OFFSET_BITS 64
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -29,6 +30,9 @@
 
 #include "netcdf.h"
 #include "nkprecond.h"
+#ifndef NKP_NO_NC3_EXTENT
+#include "nkp_nc3.h"            /* raw variable extents: only libnkp_nc3.so has them */
+#endif
 
 static int iam = 0;
 static int dbg_lvl = 0;
@@ -144,7 +148,8 @@ typedef struct {
    int flat_len, nnz;
    int *ind_i, *ind_j, *ind_k;   /* tracer_state_ind_to_{i,j,k} */
    int *rowptr, *colind;
-   double *nzval;
+   double *nzval;               /* host byte order, or ... */
+   int nzval_is_file_order;     /* ... 1: the raw big-endian bytes of the file (swapped on the GPU) */
 } matrix_file_t;
 
 static int
@@ -197,7 +202,22 @@ read_matrix_file (const char *fname, matrix_file_t * mf)
       return 1;
    if ((status = nc_inq_varid (ncid, "nzval_row_wise", &varid)) != NC_NOERR)
       return nc_fail (status, "nc_inq_varid", "nzval_row_wise");
-   if ((status = nc_get_var_double (ncid, varid, mf->nzval)) != NC_NOERR)
+#ifndef NKP_NO_NC3_EXTENT
+   {
+      /* matrix-file ingest without the host byte-swap loop: read the variable's bytes as they are */
+      long long off = 0, nbytes = 0;
+      int xtype = 0;
+      FILE *fp;
+
+      if (nkp_nc3_inq_var_extent (ncid, varid, &off, &nbytes, &xtype) == NC_NOERR && xtype == NC_DOUBLE
+          && nbytes == (long long) sizeof (double) * mf->nnz && (fp = fopen (fname, "rb")) != NULL) {
+         if (fseeko (fp, (off_t) off, SEEK_SET) == 0 && fread (mf->nzval, 1, (size_t) nbytes, fp) == (size_t) nbytes)
+            mf->nzval_is_file_order = 1;
+         fclose (fp);
+      }
+   }
+#endif
+   if (!mf->nzval_is_file_order && (status = nc_get_var_double (ncid, varid, mf->nzval)) != NC_NOERR)
       return nc_fail (status, "nc_get_var_double", "nzval_row_wise");
    if ((status = nc_close (ncid)) != NC_NOERR)
       return nc_fail (status, "nc_close", fname);
@@ -259,8 +279,8 @@ main (int argc, char **argv)
    free (cj);
    free (ck);
    if (dbg_lvl)
-      printf ("(%d) calling nkp_factor\n", iam);
-   rc = nkp_factor (solver, mf.nzval);
+      printf ("(%d) calling %s\n", iam, mf.nzval_is_file_order ? "nkp_factor_be (values in file byte order)" : "nkp_factor");
+   rc = mf.nzval_is_file_order ? nkp_factor_be (solver, mf.nzval) : nkp_factor (solver, mf.nzval);
    if (dbg_lvl)
       printf ("(%d) factor info = %d\n", iam, rc);
    if (rc != NKP_OK) {

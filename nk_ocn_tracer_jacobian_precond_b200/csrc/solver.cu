@@ -539,6 +539,27 @@ int nkp_factor(nkp_solver* s, const double* nzval) {
     return do_factor(s);
 }
 
+int nkp_factor_be(nkp_solver* s, const void* nzval_be) {
+    if (!s || !nzval_be) {
+        g_err = "nkp_factor_be: invalid argument";
+        return NKP_EINVAL;
+    }
+    if (!s->opt.equil) {
+        g_err = "nkp_factor_be needs equilibration (the unscaled tiny-pivot threshold wants max|A| on the host)";
+        return NKP_EINVAL;
+    }
+    CK(cudaSetDevice(s->opt.device));
+    s->amax = 0;
+    // raw file bytes: pageable -> pinned staging -> device, then swapped in place
+    memcpy(s->h_pinned, nzval_be, sizeof(double) * (size_t)s->nnz);
+    CK(cudaMemcpyAsync(s->d_val, s->h_pinned, sizeof(double) * (size_t)s->nnz, cudaMemcpyHostToDevice, s->stream));
+    k_bswap64<<<(unsigned)((s->nnz + 255) / 256), 256, 0, s->stream>>>(reinterpret_cast<const unsigned long long*>(s->d_val),
+                                                                      s->d_val, s->nnz);
+    s->launches++;
+    CK(cudaGetLastError());
+    return do_factor(s);
+}
+
 // forward + backward sweeps on d_y (n x nr, permuted, scaled), in place
 template <int NR>
 static int sweeps(nkp_solver* s) {

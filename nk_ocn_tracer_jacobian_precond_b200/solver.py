@@ -58,6 +58,7 @@ def load_library():
                                     P(NkpOptions), C.c_int, C.c_int, C.c_char_p]
     lib.nkp_comm_unique_id.argtypes = [C.c_char_p]
     lib.nkp_factor.argtypes = [vp, P(C.c_double)]
+    lib.nkp_factor_be.argtypes = [vp, vp]
     lib.nkp_factor_device.argtypes = [vp, vp]
     lib.nkp_solve.argtypes = [vp, P(C.c_double), C.c_int, C.c_int, P(C.c_double)]
     lib.nkp_solve_device.argtypes = [vp, vp, C.c_int, C.c_int, P(C.c_double)]
@@ -146,6 +147,12 @@ class TracerJacobianSolver:
         nzval = np.ascontiguousarray(nzval, dtype=np.float64)
         assert nzval.size == self.nnz
         _check(self._lib.nkp_factor(self._h, nzval.ctypes.data_as(C.POINTER(C.c_double))), "nkp_factor")
+
+    def factor_be(self, raw):
+        """Numeric LU from nnz big-endian doubles (bytes / buffer as they lie in the matrix file)."""
+        buf = np.frombuffer(raw, dtype=np.uint8)
+        assert buf.size == 8 * self.nnz
+        _check(self._lib.nkp_factor_be(self._h, C.c_void_p(buf.ctypes.data)), "nkp_factor_be")
 
     def factor_device(self, d_ptr):
         """Numeric LU with values already on the device (d_ptr: int device address)."""

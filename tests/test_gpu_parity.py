@@ -372,3 +372,18 @@ def test_analysis_cache_on_the_gpu_path(golden_matrix, tmp_path):
         assert np.array_equal(xs[0], xs[1])
     finally:
         solver.set_analysis_cache(None)
+
+
+def test_factor_from_file_byte_order(golden_matrix):
+    """nkp_factor_be: big-endian values as they lie in the matrix file, swapped on the GPU (SURVEY.md
+    8(f) rank 2) -- bitwise the same factors as nkp_factor on host-order values."""
+    from nk_ocn_tracer_jacobian_precond_b200 import solver
+    c = _golden_case(golden_matrix)
+    b = np.random.default_rng(11).standard_normal(c["n"])
+    s = solver.TracerJacobianSolver(c["n"], c["rowptr"], c["colind"], coords=(c["i"], c["j"], c["k"]))
+    s.factor(c["nzval"])
+    x0 = b.copy(); s.solve(x0)
+    s.factor_be(np.ascontiguousarray(c["nzval"], dtype=np.float64).astype(">f8").tobytes())
+    x1 = b.copy(); s.solve(x1)
+    assert np.array_equal(x0, x1)
+    s.close()

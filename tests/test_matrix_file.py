@@ -193,3 +193,24 @@ def test_reference_gen_A_reproduces_reftest_golden(tmp_path, reftest_matrix):
     a = synth.read_matrix_file(str(tmp_path / "A.nc"))
     for k in ("nzval_row_wise", "colind", "rowptr"):
         assert np.array_equal(a[k], reftest_matrix[k]), k
+
+
+def test_raw_variable_extent_for_device_ingest(golden_matrix):
+    """nkp_nc3_inq_var_extent (include/nkp_nc3.h): the bytes at the reported extent are the big-endian
+    doubles nc_get_var_double would have swapped on the host (src/matrix.c:3996) -- the input of nkp_factor_be."""
+    import ctypes
+    lib = ctypes.CDLL(os.path.join(ROOT, "nk_ocn_tracer_jacobian_precond_b200", "libnkp_nc3.so"))
+    path = os.path.join(GOLDEN, "A_20x24x10.nc")
+    ncid, varid = ctypes.c_int(), ctypes.c_int()
+    assert lib.nc_open(path.encode(), 0, ctypes.byref(ncid)) == 0
+    assert lib.nc_inq_varid(ncid, b"nzval_row_wise", ctypes.byref(varid)) == 0
+    off, nbytes, xtype = ctypes.c_longlong(), ctypes.c_longlong(), ctypes.c_int()
+    assert lib.nkp_nc3_inq_var_extent(ncid, varid, ctypes.byref(off), ctypes.byref(nbytes), ctypes.byref(xtype)) == 0
+    nz = golden_matrix["nzval_row_wise"]
+    assert xtype.value == 6 and nbytes.value == 8 * nz.size          # NC_DOUBLE
+    with open(path, "rb") as f:
+        f.seek(off.value)
+        raw = f.read(nbytes.value)
+    assert np.array_equal(np.frombuffer(raw, dtype=">f8").astype(np.float64), nz)
+    assert lib.nkp_nc3_inq_var_extent(ncid, 9999, None, None, None) != 0
+    assert lib.nc_close(ncid) == 0
