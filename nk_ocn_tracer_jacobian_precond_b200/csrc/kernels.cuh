@@ -556,13 +556,17 @@ __global__ void k_permute_in(int n, int nrhs, const int* __restrict__ perm, cons
 }
 
 // x[i, c] (+)= C[i] * y[perm[i], c]
+// columns whose bit is clear in `mask` are left alone: a right-hand side that has met the refinement
+// stop rule is frozen, so a batched solve gives every column exactly what a single solve would
 __global__ void k_permute_out(int n, int nrhs, const int* __restrict__ perm, const double* __restrict__ Cs,
-                              const double* __restrict__ y, double* __restrict__ x, int ldx, int accumulate) {
+                              const double* __restrict__ y, double* __restrict__ x, int ldx, int accumulate,
+                              unsigned mask) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     int pi = perm[i];
     double cs = Cs[i];
     for (int c = 0; c < nrhs; c++) {
+        if (!((mask >> c) & 1u)) continue;
         double v = cs * y[pi + (int64_t)c * n];
         if (accumulate) x[i + (int64_t)c * ldx] += v;
         else x[i + (int64_t)c * ldx] = v;

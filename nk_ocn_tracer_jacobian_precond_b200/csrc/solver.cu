@@ -739,7 +739,7 @@ static int solve_chunk(nkp_solver* s, double* dB, int ldb, int nr, double* berr_
     if (nrp > nr) CK(cudaMemsetAsync(s->d_y, 0, sizeof(double) * (size_t)n * nrp, st));
     k_permute_in<<<g, 256, 0, st>>>(n, nr, s->d_perm, s->d_R, dB, ldb, s->d_y);
     if (sweeps_nr(s, nrp)) return NKP_ECUDA;
-    k_permute_out<<<g, 256, 0, st>>>(n, nr, s->d_perm, s->d_C, s->d_y, s->d_x, n, 0);
+    k_permute_out<<<g, 256, 0, st>>>(n, nr, s->d_perm, s->d_C, s->d_y, s->d_x, n, 0, 0xffu);
     s->launches += 2;
     double last[MAX_NR];
     for (int c = 0; c < nr; c++) last[c] = 1e300;
@@ -787,7 +787,10 @@ static int solve_chunk(nkp_solver* s, double* dB, int ldb, int nr, double* berr_
         it++;
         k_permute_in<<<g, 256, 0, st>>>(n, nr, s->d_perm, s->d_R, s->d_r, n, s->d_y);
         if (sweeps_nr(s, nrp)) return NKP_ECUDA;
-        k_permute_out<<<g, 256, 0, st>>>(n, nr, s->d_perm, s->d_C, s->d_y, s->d_x, n, 1);
+        unsigned active = 0;
+        for (int c = 0; c < nr; c++)
+            if (!done[c]) active |= 1u << c;
+        k_permute_out<<<g, 256, 0, st>>>(n, nr, s->d_perm, s->d_C, s->d_y, s->d_x, n, 1, active);
         s->launches += 2;
     }
     // write the solution over B
@@ -964,7 +967,7 @@ int nkp_sweeps_device(nkp_solver* s, double* dB, int ldb, int nrhs) {
     if (nrp > nrhs) CK(cudaMemsetAsync(s->d_y, 0, sizeof(double) * (size_t)n * nrp, s->stream));
     k_permute_in<<<g, 256, 0, s->stream>>>(n, nrhs, s->d_perm, s->d_R, dB, ldb, s->d_y);
     if (sweeps_nr(s, nrp)) return NKP_ECUDA;
-    k_permute_out<<<g, 256, 0, s->stream>>>(n, nrhs, s->d_perm, s->d_C, s->d_y, dB, ldb, 0);
+    k_permute_out<<<g, 256, 0, s->stream>>>(n, nrhs, s->d_perm, s->d_C, s->d_y, dB, ldb, 0, 0xffu);
     s->launches += 2;
     CK(cudaEventRecord(s->ev[3], s->stream));
     CK(cudaGetLastError());

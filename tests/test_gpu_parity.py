@@ -83,7 +83,9 @@ def test_batched_rhs_equals_single_rhs(golden_matrix):
     for col in range(8):
         x1 = B[:, col].copy()
         s.solve(x1)
-        assert np.linalg.norm(x1 - X8[:, col]) / np.linalg.norm(x1) <= 1e-12
+        # every column's arithmetic is independent of its neighbours (the right-hand sides are the N
+        # dimension of the DMMA products, converged columns are frozen during refinement): bitwise equal
+        assert np.array_equal(x1, X8[:, col])
     # more than 8 columns go through two chunks, ldb > n
     B11 = np.asfortranarray(rng.standard_normal((c["n"] + 5, 11)))
     X11 = B11.copy(order="F")
