@@ -436,6 +436,93 @@ int nkp_sim_partition(int n, const int* rowptr, const int* colind, const int* ci
     return nf;
 }
 
+// Structural invariants of the plan that the CUDA kernels rely on (checked on the CPU, no numerics):
+// returns 0 when all hold, otherwise a positive code naming the first violated invariant.
+int nkp_sim_check_plan(int n, const int* rowptr, const int* colind, const int* ci, const int* cj, const int* ck,
+                       int nb, int leaf, int nranks) {
+    Options opt;
+    opt.nb = nb;
+    opt.leaf = leaf;
+    if (opt.tn > nb) opt.tn = nb;
+    opt.nranks = nranks;
+    const int* coords[3] = {ci, cj, ck};
+    for (int rank = 0; rank < nranks; rank++) {
+        opt.rank = rank;
+        Plan P;
+        int rc = analyse(n, rowptr, colind, (ci || cj || ck) ? coords : nullptr, opt, P);
+        if (rc) return 1;
+        // 16-byte alignment of every panel column (cp.async 16 in the sweeps)
+        for (const Front& f : P.fronts) {
+            if (f.Loff < 0) continue;
+            if ((f.ld & 1) || f.ld < f.m || f.ld > f.m + 1 || (f.Loff & 1) || (f.UToff & 1)) return 2;
+        }
+        // every solve task is either small or big, never both; big fronts mirror their task
+        size_t nbig = 0, nsmall = 0;
+        for (const SolveTask& t : P.solve_tasks) (t.big ? nbig : nsmall)++;
+        if (nbig != P.big_fronts.size() || nsmall != P.solve_small.size()) return 3;
+        // the diagonal blocks of every front are inverted exactly once
+        size_t ninv = 0;
+        for (const SolveTask& t : P.solve_tasks) ninv += (size_t)(t.s + 63) / 64;
+        if (ninv != P.inv_tasks.size()) return 4;
+        for (const DiagTask& d : P.inv_tasks)
+            if (d.kb < 1 || d.kb > 64 || (d.ld & 1)) return 5;
+        for (const LevelPlan& L : P.levels) {
+            // forward items: every slab of every big front of the level exactly once, pivot slabs of a
+            // front in increasing order (a CTA only waits on items listed before its own)
+            std::vector<int> seen;
+            std::vector<int> last_piv(P.big_fronts.size(), -1);
+            int64_t nfwd = 0, nbwd = 0, nrect = 0, slots = 0;
+            for (int b = L.big_begin; b < L.big_end; b++) {
+                const BigFront& bf = P.big_fronts[b];
+                if (bf.npiv != (bf.s + 63) / 64 || bf.nslab != bf.npiv + (bf.r + 63) / 64) return 6;
+                if (bf.nchunk != ((bf.r + 63) / 64 + BWD_CHUNK - 1) / BWD_CHUNK) return 7;
+                if (bf.part_off != slots) return 8;
+                slots += (int64_t)bf.npiv * bf.nchunk;
+                nfwd += bf.nslab;
+                nbwd += bf.npiv;
+                nrect += (int64_t)bf.npiv * bf.nchunk;
+                // child_lo[child][slab] = first entry of the child's rel[] that maps to a row >= the slab's first row
+                for (int c = 0; c < bf.nchild; c++) {
+                    const SolveChild& sc = P.solve_children[bf.child_list + c];
+                    const int* rl = P.rel.data() + sc.rel_off;
+                    for (int j = 0; j < bf.nslab; j++) {
+                        int row0 = j < bf.npiv ? 64 * j : bf.s + 64 * (j - bf.npiv);
+                        int lo = P.child_lo[bf.clo_off + (int64_t)c * bf.nslab + j];
+                        if (lo < 0 || lo > sc.r) return 9;
+                        if (lo < sc.r && rl[lo] < row0) return 10;
+                        if (lo > 0 && rl[lo - 1] >= row0) return 11;
+                    }
+                }
+            }
+            if (slots > P.bwd_part_slots) return 12;
+            if (L.fwd_item_end - L.fwd_item_begin != nfwd || L.bwd_item_end - L.bwd_item_begin != nbwd ||
+                L.rect_item_end - L.rect_item_begin != nrect)
+                return 13;
+            for (int q = L.fwd_item_begin; q < L.fwd_item_end; q++) {
+                const BigItem& it = P.big_fwd_items[q];
+                if (it.front < L.big_begin || it.front >= L.big_end) return 14;
+                const BigFront& bf = P.big_fronts[it.front];
+                if (it.idx < 0 || it.idx >= bf.nslab) return 15;
+                if (it.idx < bf.npiv) {
+                    if (it.idx != last_piv[it.front] + 1) return 16;
+                    last_piv[it.front] = it.idx;
+                } else if (last_piv[it.front] != bf.npiv - 1) {
+                    return 17;   // a boundary slab listed before the last pivot slab of its front
+                }
+            }
+            std::vector<int> next_panel(P.big_fronts.size(), -2);
+            for (int q = L.bwd_item_begin; q < L.bwd_item_end; q++) {
+                const BigItem& it = P.big_bwd_items[q];
+                const BigFront& bf = P.big_fronts[it.front];
+                int expect = next_panel[it.front] == -2 ? bf.npiv - 1 : next_panel[it.front];
+                if (it.idx != expect) return 18;   // panels of a front from the last one down
+                next_panel[it.front] = it.idx - 1;
+            }
+        }
+    }
+    return 0;
+}
+
 int nkp_sim_run(int n, const int* rowptr, const int* colind, const double* val, const int* ci,
                 const int* cj, const int* ck, int nb, int leaf, const double* B, int nrhs,
                 double* X, double* stats_out, int* perm_out, int analysis_only) {

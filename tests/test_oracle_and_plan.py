@@ -159,3 +159,16 @@ def test_ordering_cache_round_trip(sim_lib, golden_matrix, golden_rhs, tmp_path)
         assert files[0].stat().st_size == len(data)
     finally:
         sim_lib.nkp_sim_set_cache_dir(None)
+
+
+@pytest.mark.parametrize("shape,nranks,leaf", [((20, 24, 10), 1, 96), ((40, 46, 24), 1, 96), ((40, 46, 24), 3, 96),
+                                               ((64, 74, 38), 2, 48)])
+def test_plan_invariants_the_kernels_rely_on(sim_lib, shape, nranks, leaf):
+    """Even leading dimensions and aligned panel offsets (16-byte cp.async), one inversion task per
+    diagonal block, complete and dependency-ordered item lists of the dataflow sweeps, the child run
+    starts of the forward slabs, the partial-product slots of the backward rectangles -- for one and for
+    several ranks (oracle/plan_sim.cpp::nkp_sim_check_plan)."""
+    c = synth_case(*shape, seed=2)
+    rc = sim_lib.nkp_sim_check_plan(c["n"], _ip(c["rowptr"]), _ip(c["colind"]), _ip(c["i"]), _ip(c["j"]), _ip(c["k"]),
+                                    64, leaf, nranks)
+    assert rc == 0, f"plan invariant {rc} violated"
