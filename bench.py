@@ -375,7 +375,7 @@ def run_own(args):
         }
         solve_gbs = st["solve_bytes"] / sweep_s * 1e-9
         roofline_solve = {
-            "kernel": "k_fwd/k_bwd sweep pair (nrhs=%d, no refinement)" % NRHS, "bound": "hbm",
+            "kernel": "k_sweep_big + k_fwd_small/k_bwd_small sweep pair (nrhs=%d, no refinement)" % NRHS, "bound": "hbm",
             "achieved": solve_gbs, "peak": peaks["hbm_gbs"] * world, "unit": "GB/s",
             "frac": solve_gbs / (peaks["hbm_gbs"] * world),
             "peak_source": peaks["_hbm_src"] + (f" x {world} GPUs (whole-job bytes over the max-over-ranks time)" if world > 1 else ""),

@@ -10,7 +10,13 @@
 //   k_diag           nb x nb diagonal-block LU, static pivoting          latency bound
 //   k_trsm           tall panel  X * T = B  (L panel and U^T panel)      FP64 FMA
 //   k_gemm           Schur update C -= A * B^T, FP64 tensor cores (DMMA) FP64 tensor
-//   k_fwd / k_bwd    level-scheduled triangular sweeps, multi-RHS        HBM bound
+//   k_invert_diag    64 x 64 diagonal blocks -> their inverses (for the sweeps) latency bound
+//   k_sweep_big      level-scheduled sweeps of the big fronts: many CTAs,  HBM bound
+//                    DMMA tile stream, counter-driven dataflow, multi-RHS
+//   k_fwd_small /    sweeps of the small fronts, one warp per front        HBM / latency
+//   k_bwd_small
+//   k_gather_fields / k_scatter_fields   tracer fields <-> right-hand sides HBM bound
+//   k_bswap64        matrix-file ingest (big-endian doubles)               HBM bound
 //   k_residual       r = b - A x and |A||x|+|b| (refinement, berr)       HBM bound
 #pragma once
 #include <cuda_runtime.h>

@@ -109,7 +109,7 @@ struct SolveChild {
     int s, r;
 };
 
-// big fronts are swept by many CTAs with a flag-driven dataflow (k_fwd_big / k_bwd_big)
+// big fronts are swept by many CTAs with a counter-driven dataflow (k_sweep_big)
 struct BigFront {
     int64_t Loff, UToff, bidx_off, woff;
     int first, s, r, m;

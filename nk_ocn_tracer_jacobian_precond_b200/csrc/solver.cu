@@ -107,6 +107,7 @@ struct nkp_solver {
     int64_t nnz = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_col[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // per-column D2H completion
     // device data
     double* heap = nullptr;
     int* d_rowptr = nullptr;
@@ -292,6 +293,7 @@ static int create_impl(nkp_solver** out, int n, const int* rowptr, const int* co
     auto body = [&]() -> int {
         CK(cudaStreamCreate(&s->stream));
         for (int i = 0; i < 4; i++) CK(cudaEventCreate(&s->ev[i]));
+        for (int i = 0; i < MAX_NR; i++) CK(cudaEventCreateWithFlags(&s->ev_col[i], cudaEventDisableTiming));
         if (nranks > 1) {
             if (!nccl_load()) {
                 g_err = "cannot load libnccl.so.2";
@@ -845,15 +847,25 @@ int nkp_solve(nkp_solver* s, double* B, int ldb, int nrhs, double* berr) {
     double tsum = 0;
     for (int c0 = 0; c0 < nrhs; c0 += MAX_NR) {
         int nr = std::min(MAX_NR, nrhs - c0);
-        for (int c = 0; c < nr; c++) memcpy(s->h_pinned + (size_t)c * n, B + (size_t)(c0 + c) * ldb, sizeof(double) * n);
-        CK(cudaMemcpyAsync(s->d_xb, s->h_pinned, sizeof(double) * (size_t)n * nr, cudaMemcpyHostToDevice, s->stream));
+        // column by column, so that the DMA of one column overlaps the host copy of the next
+        for (int c = 0; c < nr; c++) {
+            memcpy(s->h_pinned + (size_t)c * n, B + (size_t)(c0 + c) * ldb, sizeof(double) * n);
+            CK(cudaMemcpyAsync(s->d_xb + (size_t)c * n, s->h_pinned + (size_t)c * n, sizeof(double) * n,
+                               cudaMemcpyHostToDevice, s->stream));
+        }
         int rc = nkp_solve_device(s, s->d_xb, n, nr, berr ? berr + c0 : nullptr);
         if (rc) return rc;
         tsum += s->t_solve;
         maxsteps = std::max(maxsteps, s->refine_steps);
-        CK(cudaMemcpyAsync(s->h_pinned, s->d_xb, sizeof(double) * (size_t)n * nr, cudaMemcpyDeviceToHost, s->stream));
-        CK(cudaStreamSynchronize(s->stream));
-        for (int c = 0; c < nr; c++) memcpy(B + (size_t)(c0 + c) * ldb, s->h_pinned + (size_t)c * n, sizeof(double) * n);
+        for (int c = 0; c < nr; c++) {
+            CK(cudaMemcpyAsync(s->h_pinned + (size_t)c * n, s->d_xb + (size_t)c * n, sizeof(double) * n,
+                               cudaMemcpyDeviceToHost, s->stream));
+            CK(cudaEventRecord(s->ev_col[c], s->stream));
+        }
+        for (int c = 0; c < nr; c++) {
+            CK(cudaEventSynchronize(s->ev_col[c]));
+            memcpy(B + (size_t)(c0 + c) * ldb, s->h_pinned + (size_t)c * n, sizeof(double) * n);
+        }
     }
     s->t_solve = tsum;
     s->refine_steps = maxsteps;
@@ -1055,6 +1067,8 @@ void nkp_destroy(nkp_solver* s) {
     if (s->d_fields) cudaFree(s->d_fields);
     for (int i = 0; i < 4; i++)
         if (s->ev[i]) cudaEventDestroy(s->ev[i]);
+    for (int i = 0; i < MAX_NR; i++)
+        if (s->ev_col[i]) cudaEventDestroy(s->ev_col[i]);
     for (cudaEvent_t e : s->prof_ev) cudaEventDestroy(e);
     if (s->stream) cudaStreamDestroy(s->stream);
     delete s;

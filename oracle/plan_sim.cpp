@@ -313,7 +313,7 @@ int nkp_sim_run_dist(int n, const int* rowptr, const int* colind, const double* 
                     }
                     const double* Lr = H + t.Loff;
                     if (invdiag) {
-                        // block forward substitution with inverted 64 x 64 diagonal blocks (k_fwd_big)
+                        // block forward substitution with inverted 64 x 64 diagonal blocks (k_sweep_big<FWD>, k_fwd_small)
                         double tmp[64];
                         for (int k0 = 0; k0 < t.s; k0 += 64) {
                             int kb = std::min(64, t.s - k0);
@@ -353,7 +353,7 @@ int nkp_sim_run_dist(int n, const int* rowptr, const int* colind, const double* 
                     for (int a = 0; a < t.r; a++) w[t.s + a] = y[bi[a]];
                     const double* UT = H + t.UToff;
                     if (invdiag) {
-                        // block back substitution, diagonal blocks hold (U_kk^-1)^T (k_bwd_big)
+                        // block back substitution, diagonal blocks hold (U_kk^-1)^T (k_sweep_big<BWD_*>, k_bwd_small)
                         double z[64];
                         for (int k0 = (t.s - 1) / 64 * 64; k0 >= 0; k0 -= 64) {
                             int kb = std::min(64, t.s - k0);
