@@ -622,6 +622,9 @@ __global__ void __launch_bounds__(256) k_scatter_fields(int tsl, int ct, int nfi
 // warp shuffles.  With 8 fronts per CTA and no shared memory, thousands of fronts are in flight.
 // ------------------------------------------------------------------------------------------
 
+#ifndef NKP_SMALL_MINB
+#define NKP_SMALL_MINB 3
+#endif
 constexpr int SMALL_WARPS = 4;
 
 // accumulator layout (row 8g + lr, rhs 2 lc + {0,1}) -> B fragment of k-step ks: (k = 4 ks + lc, rhs = lr)
@@ -633,7 +636,7 @@ __device__ __forceinline__ double acc_to_bfrag(const double (&acc)[8][2], int ks
     return (lr & 1) ? v1 : v0;
 }
 
-__global__ void __launch_bounds__(32 * SMALL_WARPS, 3) k_fwd_small(const SolveTask* __restrict__ tasks, int ntasks,
+__global__ void __launch_bounds__(32 * SMALL_WARPS, NKP_SMALL_MINB) k_fwd_small(const SolveTask* __restrict__ tasks, int ntasks,
                                                                 const SolveChild* __restrict__ children,
                                                                 const int* __restrict__ rel,
                                                                 const double* __restrict__ heap, double* W, double* y,
@@ -734,7 +737,7 @@ __global__ void __launch_bounds__(32 * SMALL_WARPS, 3) k_fwd_small(const SolveTa
     }
 }
 
-__global__ void __launch_bounds__(32 * SMALL_WARPS, 3) k_bwd_small(const SolveTask* __restrict__ tasks, int ntasks,
+__global__ void __launch_bounds__(32 * SMALL_WARPS, NKP_SMALL_MINB) k_bwd_small(const SolveTask* __restrict__ tasks, int ntasks,
                                                                 const int* __restrict__ bidx,
                                                                 const double* __restrict__ heap, double* W, double* y,
                                                                 int n, int nr, int nrtot) {
@@ -842,7 +845,10 @@ __global__ void __launch_bounds__(32 * SMALL_WARPS, 3) k_bwd_small(const SolveTa
 
 constexpr int SW_LD = 68;                   // column stride of a staged tile: == 4 (mod 16) -> conflict-free fragment
                                             // loads in both directions, and room for 64 + 2 rows (alignment shift)
-constexpr int SW_ST = 3;                    // ring stages
+#ifndef NKP_SW_ST
+#define NKP_SW_ST 3
+#endif
+constexpr int SW_ST = NKP_SW_ST;            // ring stages
 constexpr int SW_TILE = 64 * SW_LD;         // doubles per stage: tile[col * SW_LD + (row - aligned first row)]
 constexpr int SW_SMEM = SW_ST * SW_TILE * 8;   // dynamic shared memory per CTA (bytes): 2 CTAs per SM
 static_assert(SW_ST * SW_TILE >= 8 * 64 * 8, "the ring doubles as the buffer of the eight 64 x 8 partial sums");
