@@ -391,3 +391,36 @@ def test_factor_from_file_byte_order(golden_matrix):
     x1 = b.copy(); s.solve(x1)
     assert np.array_equal(x0, x1)
     s.close()
+
+
+def test_solve_fields_with_two_coupled_tracers(golden_matrix):
+    """coupled_tracer_cnt = 2 (src/gen_A.c:221-234): the operand is two stacked copies of the grid graph
+    joined by a diagonal coupling (src/matrix.c:955-961), flat row = t * tracer_state_len + s
+    (src/matrix.c:778), and every pair of consecutive fields is ONE right-hand side
+    (src/solve_ABglobal.c:373-388)."""
+    from nk_ocn_tracer_jacobian_precond_b200 import solver
+    c = _golden_case(golden_matrix)
+    tsl = c["n"]
+    A = _A(c)
+    I = sp.identity(tsl, format="csr")
+    A2 = sp.bmat([[A, 0.3 * I], [-0.2 * I, 1.5 * A]], format="csr")
+    A2.sort_indices()
+    rp, ci, nz = A2.indptr.astype(np.int32), A2.indices.astype(np.int32), A2.data.astype(np.float64)
+    i2, j2, k2 = (np.concatenate([c[q], c[q]]) for q in ("i", "j", "k"))
+    s = solver.TracerJacobianSolver(2 * tsl, rp, ci, coords=(i2, j2, k2))
+    s.factor(nz)
+    s.set_tracer_maps(c["i"], c["j"], c["k"], (20, 24, 10), coupled_tracer_cnt=2)
+    rng = np.random.default_rng(17)
+    orig = [rng.standard_normal((10, 24, 20)) for _ in range(4)]      # two systems of two tracers
+    fields = [f.copy() for f in orig]
+    berr = s.solve_fields(fields)
+    assert berr.shape == (2,)
+    i, j, k = c["i"], c["j"], c["k"]
+    for g in range(2):
+        b = np.concatenate([orig[2 * g][k, j, i], orig[2 * g + 1][k, j, i]])
+        xo = oracle_solve.solve(2 * tsl, rp, ci, nz, b)
+        x = np.concatenate([fields[2 * g][k, j, i], fields[2 * g + 1][k, j, i]])
+        assert np.linalg.norm(x - xo) / np.linalg.norm(xo) <= SOL_TOL
+    with pytest.raises(solver.NkpError):
+        s.solve_fields(fields[:3])        # the list runs out inside a group (src/solve_ABglobal.c:376-379)
+    s.close()
