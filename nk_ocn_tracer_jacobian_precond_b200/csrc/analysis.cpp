@@ -23,6 +23,7 @@
 #include "nkp_internal.hpp"
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -68,23 +69,19 @@ void build_graph(int n, const int* rowptr, const int* colind, Graph& g) {
             tmp[pos[i]++] = j;
             tmp[pos[j]++] = i;
         }
-    // sort + unique each list
-    g.xadj.assign(n + 1, 0);
-    g.adj.resize(cnt[n]);
-    int64_t w = 0;
+    // sort + unique each list (rows are independent), then compact
+    std::vector<int64_t> ucnt(n + 1, 0);
+#pragma omp parallel for schedule(dynamic, 4096)
     for (int i = 0; i < n; i++) {
         int64_t b = cnt[i], e = cnt[i + 1];
         std::sort(tmp.begin() + b, tmp.begin() + e);
-        g.xadj[i] = w;
-        int last = -1;
-        for (int64_t p = b; p < e; p++)
-            if (tmp[p] != last) {
-                g.adj[w++] = tmp[p];
-                last = tmp[p];
-            }
+        ucnt[i + 1] = std::unique(tmp.begin() + b, tmp.begin() + e) - (tmp.begin() + b);
     }
-    g.xadj[n] = w;
-    g.adj.resize(w);
+    g.xadj.assign(n + 1, 0);
+    for (int i = 0; i < n; i++) g.xadj[i + 1] = g.xadj[i] + ucnt[i + 1];
+    g.adj.resize(g.xadj[n]);
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < n; i++) std::copy(tmp.begin() + cnt[i], tmp.begin() + cnt[i] + ucnt[i + 1], g.adj.begin() + g.xadj[i]);
 }
 
 struct TreeNode {
@@ -100,9 +97,19 @@ struct Dissector {
     std::vector<int> order;     // vertex list, partitioned in place
     std::vector<int> regid;     // region id per vertex
     std::vector<signed char> side;
-    std::vector<int> scratch;
-    std::vector<TreeNode> nodes;
-    int next_rid = 1;
+    std::vector<TreeNode> nodes;    // result: the dissection tree in postorder
+    std::atomic<int> next_rid{1};
+
+    // The two halves of a dissection are independent and are built by OpenMP tasks.  Every call
+    // returns its subtree with LOCAL node numbers (postorder) and the caller concatenates
+    // [first half | second half | separator], so the numbering does not depend on scheduling: all
+    // ranks of a multi-GPU run, and runs with any thread count, get the identical tree.  Tasks write
+    // regid / side / order only for vertices of their own region; a neighbour outside the region is
+    // only ever compared against this region's id, which nobody else writes.
+    struct Sub {
+        std::vector<TreeNode> nodes;
+        std::vector<int> roots;
+    };
 
     Dissector(const Graph& g_, const int* const* c, const Options& o) : g(g_), coords(c), opt(o) {
         order.resize(g.n);
@@ -111,15 +118,27 @@ struct Dissector {
         side.assign(g.n, 0);
     }
 
-    int make_node(int begin, int end, const std::vector<int>& children) {
+    int make_node(Sub& sub, int begin, int end, const std::vector<int>& children) {
         TreeNode nd;
         nd.verts.assign(order.begin() + begin, order.begin() + end);
         std::sort(nd.verts.begin(), nd.verts.end());
         nd.children = children;
-        int id = (int)nodes.size();
-        nodes.push_back(std::move(nd));
-        for (int c : children) nodes[c].parent = id;
+        int id = (int)sub.nodes.size();
+        sub.nodes.push_back(std::move(nd));
+        for (int c : children) sub.nodes[c].parent = id;
         return id;
+    }
+
+    // append `b` to `a`, shifting b's local node numbers
+    static void append(Sub& a, Sub&& b) {
+        const int off = (int)a.nodes.size();
+        a.nodes.reserve(a.nodes.size() + b.nodes.size());
+        for (TreeNode& nd : b.nodes) {
+            if (nd.parent >= 0) nd.parent += off;
+            for (int& c : nd.children) c += off;
+            a.nodes.push_back(std::move(nd));
+        }
+        for (int r : b.roots) a.roots.push_back(r + off);
     }
 
     // Evaluate the split "side[v] in {0,1}" of region rid: count the one-sided separators.
@@ -152,7 +171,7 @@ struct Dissector {
     void try_dim(int begin, int end, int rid, int d, Cand& best) {
         const int* x = coords[d];
         int nv = end - begin;
-        scratch.resize(nv);
+        std::vector<int> scratch(nv);
         for (int p = 0; p < nv; p++) scratch[p] = x[order[begin + p]];
         std::nth_element(scratch.begin(), scratch.begin() + nv / 2, scratch.end());
         int med = scratch[nv / 2];
@@ -190,10 +209,9 @@ struct Dissector {
     // BFS level-structure split when no coordinates are available
     bool bfs_split(int begin, int end, int rid) {
         int nv = end - begin;
-        std::vector<int>& lvl = scratch;
-        lvl.assign(nv, 0);
-        // local index map through side[] is not possible (n large) -> use a per-call map in regid-tagged array
-        // we reuse `dist` stored in a member vector sized n lazily
+        // distance labels: one n-sized array per thread, entries reset to -1 after use (no task
+        // scheduling point inside this function, so a thread runs one bfs_split at a time)
+        static thread_local std::vector<int> dist;
         if (dist.size() != (size_t)g.n) dist.assign(g.n, -1);
         auto bfs = [&](int src, std::vector<int>& out) {
             out.clear();
@@ -246,16 +264,16 @@ struct Dissector {
         }
         return true;
     }
-    std::vector<int> dist;
 
-    void build(int begin, int end, std::vector<int>& roots_out) {
+    Sub build(int begin, int end) {
+        Sub out;
         int nv = end - begin;
-        if (nv == 0) return;
+        if (nv == 0) return out;
         if (nv <= opt.leaf) {
-            roots_out.push_back(make_node(begin, end, {}));
-            return;
+            out.roots.push_back(make_node(out, begin, end, {}));
+            return out;
         }
-        int rid = next_rid++;
+        int rid = next_rid.fetch_add(1);
         for (int p = begin; p < end; p++) regid[order[p]] = rid;
 
         bool ok = false;
@@ -288,8 +306,8 @@ struct Dissector {
         }
         if (!ok) ok = bfs_split(begin, end, rid);
         if (!ok) {
-            roots_out.push_back(make_node(begin, end, {}));
-            return;
+            out.roots.push_back(make_node(out, begin, end, {}));
+            return out;
         }
         // partition order[begin:end) into [side0 | side1 | sep]
         int n0 = 0, n1 = 0, n2 = 0;
@@ -300,8 +318,8 @@ struct Dissector {
             n2 += sv == 2;
         }
         if ((n0 == 0 && n2 == 0) || (n1 == 0 && n2 == 0) || n2 == nv) {
-            roots_out.push_back(make_node(begin, end, {}));
-            return;
+            out.roots.push_back(make_node(out, begin, end, {}));
+            return out;
         }
         {
             std::vector<int> tmp(order.begin() + begin, order.begin() + end);
@@ -313,14 +331,27 @@ struct Dissector {
                 else order[p2++] = v;
             }
         }
-        std::vector<int> child_roots;
-        build(begin, begin + n0, child_roots);
-        build(begin + n0, begin + n0 + n1, child_roots);
-        if (n2 == 0) {
-            roots_out.insert(roots_out.end(), child_roots.begin(), child_roots.end());
-            return;
-        }
-        roots_out.push_back(make_node(begin + n0 + n1, end, child_roots));
+        Sub second;
+        const bool par = std::min(n0, n1) > 20000;   // small halves are not worth a task
+#pragma omp task shared(out) if (par)
+        out = build(begin, begin + n0);
+#pragma omp task shared(second) if (par)
+        second = build(begin + n0, begin + n0 + n1);
+#pragma omp taskwait
+        append(out, std::move(second));
+        if (n2 == 0) return out;
+        const std::vector<int> child_roots = out.roots;
+        out.roots.assign(1, make_node(out, begin + n0 + n1, end, child_roots));
+        return out;
+    }
+
+    void run(std::vector<int>& roots_out) {
+        Sub all;
+#pragma omp parallel
+#pragma omp single
+        all = build(0, g.n);
+        nodes = std::move(all.nodes);
+        roots_out = std::move(all.roots);
     }
 };
 
@@ -478,7 +509,7 @@ int analyse(int n, const int* rowptr, const int* colind, const int* const coords
     if (!plan.order_cached) {
         roots.clear();        // a rejected cache file may have left partial data behind
         ds.nodes.clear();
-        ds.build(0, n, roots);
+        ds.run(roots);
         if (!cdir.empty()) save_ordering(cache_path(cdir, key), key, n, ds.nodes, roots);
     }
     std::vector<TreeNode>& nodes = ds.nodes;
@@ -739,6 +770,8 @@ int analyse(int n, const int* rowptr, const int* colind, const int* const coords
         for (int t = 0; t < nf; t++)
             for (int a = 0; a < plan.fronts[t].s; a++) front_of[plan.fronts[t].first + a] = t;
         plan.scatter.resize(plan.nnz);
+        bool bad = false;
+#pragma omp parallel for schedule(dynamic, 8192) reduction(|| : bad)
         for (int i = 0; i < n; i++) {
             int pi = plan.perm[i];
             for (int p = rowptr[i]; p < rowptr[i + 1]; p++) {
@@ -758,10 +791,14 @@ int analyse(int n, const int* rowptr, const int* colind, const int* const coords
                     return f.s + (int)(it - b);
                 };
                 int a = local(pi), b = local(pj);
-                if (a < 0 || b < 0) return -7;
+                if (a < 0 || b < 0) {
+                    bad = true;
+                    continue;
+                }
                 plan.scatter[p] = front_entry(a, b, f.s, f.m, f.ld, nb, f.Loff, f.UToff, f.F22off);
             }
         }
+        if (bad) return -7;
     }
 
     // ---- task lists ------------------------------------------------------------------------------

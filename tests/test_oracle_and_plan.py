@@ -2,6 +2,7 @@
 symbolic structure, memory plan, task lists) validated by interpreting the plan on the
 CPU (oracle/plan_sim.cpp) and comparing with the oracle."""
 import ctypes
+import os
 
 import numpy as np
 import pytest
@@ -172,3 +173,28 @@ def test_plan_invariants_the_kernels_rely_on(sim_lib, shape, nranks, leaf):
     rc = sim_lib.nkp_sim_check_plan(c["n"], _ip(c["rowptr"]), _ip(c["colind"]), _ip(c["i"]), _ip(c["j"]), _ip(c["k"]),
                                     64, leaf, nranks)
     assert rc == 0, f"plan invariant {rc} violated"
+
+
+def test_analysis_is_independent_of_the_thread_count(tmp_path):
+    """The dissection halves are OpenMP tasks; the tree numbering must not depend on scheduling (every
+    rank of a multi-GPU run derives the same plan): same permutation with 1, 2 and 5 threads."""
+    import subprocess, sys
+    script = tmp_path / "perm.py"
+    script.write_text(
+        "import sys, ctypes, numpy as np\n"
+        f"sys.path.insert(0, {repr(os.path.dirname(os.path.abspath(__file__)))})\n"
+        f"sys.path.insert(0, {repr(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))})\n"
+        "from conftest import synth_case\n"
+        "from test_oracle_and_plan import run_sim\n"
+        "lib = ctypes.CDLL(sys.argv[1])\n"
+        "c = synth_case(64, 74, 38, seed=3)\n"
+        "X, st, perm = run_sim(lib, c['n'], c['rowptr'], c['colind'], c['nzval'], (c['i'], c['j'], c['k']),\n"
+        "                      np.zeros((c['n'], 1)), analysis_only=1)\n"
+        "np.save(sys.argv[2], perm)\n")
+    libpath = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "libnkp_sim.so")
+    perms = []
+    for nt in (1, 2, 5):
+        out = tmp_path / f"perm{nt}.npy"
+        subprocess.check_call([sys.executable, str(script), libpath, str(out)], env=dict(os.environ, OMP_NUM_THREADS=str(nt)))
+        perms.append(np.load(out))
+    assert np.array_equal(perms[0], perms[1]) and np.array_equal(perms[0], perms[2])
