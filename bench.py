@@ -138,16 +138,36 @@ def cpu_baseline(full_flops, nrhs=NRHS, shape=CPU_SAMPLE):
         rp = np.ascontiguousarray(c["rowptr"], dtype=np.int32)
         ci = np.ascontiguousarray(c["colind"], dtype=np.int32)
         os.environ.pop("NKP_SIM_REFINE", None)
+        perm = np.zeros(n, dtype=np.int32)
         rc = lib.nkp_sim_run(n, ip(rp), ip(ci), c["nzval"].ctypes.data_as(P(ctypes.c_double)), ip(ii), ip(jj), ip(kk),
-                             64, 96, None, 0, None, stats.ctypes.data_as(P(ctypes.c_double)), None, 1)
+                             64, 96, None, 0, None, stats.ctypes.data_as(P(ctypes.c_double)), ip(perm), 1)
         if rc == 0:
             sample_flops = float(stats[5])
+    # like-for-like variant: the GPU path's nested-dissection ordering applied first,
+    # then SuperLU with NATURAL column order and no pivoting (diag_pivot_thresh = 0) -- same fill, same
+    # flops as the GPU factorisation, on one host core
+    nd = {}
+    if sample_flops:
+        import scipy.sparse as sp
+        import scipy.sparse.linalg as spla
+        A = sp.csr_matrix((c["nzval"], c["colind"], c["rowptr"]), shape=(n, n))
+        iperm = np.empty(n, dtype=np.int64)
+        iperm[perm] = np.arange(n)
+        Ap = A[iperm][:, iperm].tocsc()
+        t0 = time.perf_counter()
+        lu2 = spla.splu(Ap, permc_spec="NATURAL", diag_pivot_thresh=0.0, options=dict(SymmetricMode=False))
+        t_nd = time.perf_counter() - t0
+        nd = {"sample_factor_s_nd_order_no_pivoting": t_nd, "sample_nnz_lu_nd": int(lu2.L.nnz + lu2.U.nnz),
+              "sample_gflops_nd": sample_flops / t_nd * 1e-9}
     scale = (full_flops / sample_flops) if (sample_flops and full_flops) else None
     return {
+        **nd,
         "value": t_factor * scale if scale else None, "unit": "s", "cores": 1, "kind": "port",
         "sample": f"scipy.sparse.linalg.splu (serial SuperLU, COLAMD, partial pivoting) on a {shape[0]}x{shape[1]}x{shape[2]} "
                   f"grid of the same generator: n={n}, factor {t_factor:.2f} s, {t_solve * 1e3:.1f} ms/solve; "
-                  f"scaled by the factor-flop ratio {scale:.1f}x to the workload" if scale else "flop model unavailable",
+                  f"scaled by the factor-flop ratio {scale:.1f}x to the workload"
+                  + (f"; like-for-like (the GPU path's nested-dissection order, no pivoting): factor {nd['sample_factor_s_nd_order_no_pivoting']:.2f} s"
+                     if nd else "") if scale else "flop model unavailable",
         "sample_factor_s": t_factor, "sample_solve_s": t_solve, "sample_n": n, "host_cores": os.cpu_count(),
         "solves_per_sec_sample": 1.0 / t_solve,
     }
