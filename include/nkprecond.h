@@ -50,7 +50,13 @@ typedef struct nkp_options {
                          /*    halving (default, what the reference gets);                    */
                          /* 1: normwise -- stop once ||b - A x||_2 <= 1e-14 ||b||_2 for every */
                          /*    right-hand side (or no halving); typically 2-3 steps fewer     */
-    int reserved[9];
+    int residual_extra;  /* 1 (default): the refinement residual b - A x is accumulated in twice the      */
+                         /*    working precision (LAPACK xGERFSX-style extra-precise refinement): the     */
+                         /*    iteration converges to the solution of the double-precision system instead */
+                         /*    of wandering at cond(A) * eps, and SuperLU's berr rule is met 2-3 steps    */
+                         /*    earlier (gx1v6-shape: 3 steps instead of 4-7, profiles/r02_refine_probe_   */
+                         /*    gx1v6.log);  0: working precision, exactly what pdgsrfs does               */
+    int reserved[8];
 } nkp_options;
 
 /* Statistics in the spirit of PStatPrint (src/solve_ABglobal.c:351-360). */
@@ -169,6 +175,8 @@ int nkp_get_stats(const nkp_solver* s, nkp_stats* st);
 int nkp_set_profile(nkp_solver* s, int on);
 /* Change the refinement stopping rule of an existing handle (see nkp_options.refine_rule). */
 int nkp_set_refine_rule(nkp_solver* s, int rule);
+/* Switch the extra-precise residual of an existing handle on or off (see nkp_options.residual_extra). */
+int nkp_set_residual_extra(nkp_solver* s, int on);
 /* Block until all device work of this handle has finished. */
 int nkp_sync(nkp_solver* s);
 void nkp_destroy(nkp_solver* s);

@@ -1264,42 +1264,86 @@ __global__ void __launch_bounds__(INV_THREADS) k_invert_diag(const DiagTask* __r
 //   r = b - A x ;  berr_c = max_i |r_i| / (|A||x| + |b|)_i
 // ------------------------------------------------------------------------------------------
 
-// grid: (ceil(n/256), nrhs); one thread per (row, rhs); the matrix is re-read per rhs from L2
+// One thread per row, ALL right-hand sides in one pass over A (12 nnz + 4 (n+1) + 24 n nrhs bytes,
+// BASELINE.md section 4): a and its column index are loaded once per nonzero and used for NR columns.
+// x is column-major; consecutive rows are consecutive cells of a water column (src/matrix.c:239-251), so
+// the gathers x[col + c ldx] of a warp are contiguous runs per neighbour direction and per column.
+// berr follows pdgsrfs: rows with (|A||x| + |b|)_i > safe2 contribute |r_i| / den_i, rows with a non-zero
+// smaller denominator (|r_i| + safe1) / (den_i + safe1), rows with a zero denominator nothing.
+// EXTRA: the residual is accumulated in twice the working precision (error-free products by FMA, error-free
+// sums, Ogita-Rump-Oishi Dot2) and rounded once -- LAPACK's "extra-precise iterative refinement" (xGERFSX);
+// the refined solution then no longer carries cond(A) times the rounding errors of a working-precision residual.
+template <int NR, bool EXTRA>
 __global__ void __launch_bounds__(256) k_residual(int n, int nrhs, const int* __restrict__ rowptr,
                                                   const int* __restrict__ colind, const double* __restrict__ val,
                                                   const double* __restrict__ x, int ldx, const double* __restrict__ b,
                                                   int ldb, double* __restrict__ r, double* __restrict__ berr,
-                                                  double safe) {
-    __shared__ double wmax[8];
+                                                  double safe1, double safe2) {
+    __shared__ double wmax[8][NR];
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const int c = blockIdx.y;
-    double e = 0.0;
+    double e[NR];
+#pragma unroll
+    for (int c = 0; c < NR; c++) e[c] = 0.0;
     if (i < n) {
-        const double* xc = x + (int64_t)c * ldx;
-        const double bi = b[i + (int64_t)c * ldb];
-        double acc = bi, aabs = fabs(bi);
+        double acc[NR], aabs[NR], lo[NR];
+#pragma unroll
+        for (int c = 0; c < NR; c++) {
+            const double bi = c < nrhs ? b[i + (int64_t)c * ldb] : 0.0;
+            acc[c] = bi;
+            lo[c] = 0.0;
+            aabs[c] = fabs(bi);
+        }
         const int p1 = rowptr[i + 1];
         for (int p = rowptr[i]; p < p1; p++) {
-            double a = val[p], xv = xc[colind[p]];
-            acc = fma(-a, xv, acc);
-            aabs = fma(fabs(a), fabs(xv), aabs);
+            const double a = val[p], aa = fabs(a);
+            const double* xp = x + colind[p];
+#pragma unroll
+            for (int c = 0; c < NR; c++) {
+                const double xv = c < nrhs ? xp[(int64_t)c * ldx] : 0.0;
+                if (EXTRA) {
+                    const double pr = a * xv, pe = fma(a, xv, -pr);        // a * xv == pr + pe exactly
+                    const double sm = acc[c] - pr, bb = sm - acc[c];
+                    const double se = (acc[c] - (sm - bb)) + (-pr - bb);   // acc - pr == sm + se exactly
+                    acc[c] = sm;
+                    lo[c] += se - pe;
+                } else {
+                    acc[c] = fma(-a, xv, acc[c]);
+                }
+                aabs[c] = fma(aa, fabs(xv), aabs[c]);
+            }
         }
-        r[i + (int64_t)c * n] = acc;
-        e = aabs > safe ? fabs(acc) / aabs : (fabs(acc) + safe) / (aabs + safe);
+        if (EXTRA)
+#pragma unroll
+            for (int c = 0; c < NR; c++) acc[c] += lo[c];
+#pragma unroll
+        for (int c = 0; c < NR; c++) {
+            if (c < nrhs) {
+                r[i + (int64_t)c * n] = acc[c];
+                if (aabs[c] > safe2) e[c] = fabs(acc[c]) / aabs[c];
+                else if (aabs[c] != 0.0) e[c] = (fabs(acc[c]) + safe1) / (aabs[c] + safe1);
+                if (e[c] != e[c]) e[c] = 1e300;   // a NaN residual must not pass for "converged" (fmax drops NaNs)
+            }
+        }
     }
     if (berr == nullptr) return;
-    for (int o = 16; o > 0; o >>= 1) e = fmax(e, __shfl_xor_sync(0xffffffffu, e, o));
-    if ((threadIdx.x & 31) == 0) wmax[threadIdx.x >> 5] = e;
+#pragma unroll
+    for (int c = 0; c < NR; c++) {
+        double m = e[c];
+        for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if ((threadIdx.x & 31) == 0) wmax[threadIdx.x >> 5][c] = m;
+    }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        double m = wmax[0];
-        for (int w = 1; w < 8; w++) m = fmax(m, wmax[w]);
-        atomic_max_pos_double(&berr[c], m);
+    if (threadIdx.x < NR && threadIdx.x < nrhs) {
+        double m = wmax[0][threadIdx.x];
+        for (int w = 1; w < 8; w++) m = fmax(m, wmax[w][threadIdx.x]);
+        atomic_max_pos_double(&berr[threadIdx.x], m);   // max is order-independent: deterministic
     }
 }
 
-// sum of squares per column (for the relative residual reported in the stats)
-__global__ void k_sumsq(int n, int nrhs, const double* __restrict__ v, int ld, double* __restrict__ out) {
+// sum of squares per column (normwise stopping rule), deterministic: every block writes its partial
+// sum to part[block * nrhs + c]; k_sumsq_final adds the partials in block order.
+constexpr int SUMSQ_BLOCKS = 256;
+__global__ void __launch_bounds__(256) k_sumsq(int n, int nrhs, const double* __restrict__ v, int ld, double* __restrict__ part) {
     __shared__ double red[256];
     for (int c = 0; c < nrhs; c++) {
         double acc = 0;
@@ -1313,9 +1357,25 @@ __global__ void k_sumsq(int n, int nrhs, const double* __restrict__ v, int ld, d
             if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
             __syncthreads();
         }
-        if (threadIdx.x == 0) atomicAdd(&out[c], red[0]);
+        if (threadIdx.x == 0) part[blockIdx.x * nrhs + c] = red[0];
         __syncthreads();
     }
+}
+__global__ void k_sumsq_final(int nblocks, int nrhs, const double* __restrict__ part, double* __restrict__ out) {
+    const int c = threadIdx.x;
+    if (c >= nrhs) return;
+    double acc = 0;
+    for (int b = 0; b < nblocks; b++) acc += part[b * nrhs + c];
+    out[c] = acc;
+}
+
+// max |a| over the stored values (tiny-pivot threshold of an unequilibrated factorisation)
+__global__ void __launch_bounds__(256) k_absmax(int64_t nnz, const double* __restrict__ val, double* __restrict__ out) {
+    double m = 0.0;
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < nnz; p += (int64_t)gridDim.x * blockDim.x)
+        m = fmax(m, fabs(val[p]));
+    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) atomic_max_pos_double(out, m);
 }
 
 }  // namespace nkp

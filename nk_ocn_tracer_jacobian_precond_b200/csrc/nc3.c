@@ -18,7 +18,8 @@
  * (src/matrix.c:288, :3865) grows the header and relocates the data section.
  *
  * Limits (sufficient for the reference's use): whole-variable get/put only;
- * record variables are readable when numrecs <= 1; no CDF-5.
+ * record variables are readable and writable when numrecs <= 1 (one contiguous slab each);
+ * files with interleaved records are refused by get/put and by nc_redef's relocation; no CDF-5.
  */
 #define _FILE_OFFSET_BITS 64
 #include <stdio.h>
@@ -498,7 +499,16 @@ do_enddef (nc3_file * f)
 {
    bbuf b = { NULL, 0, 0 };
    uint64_t off, end;
-   int i;
+   int i, k, nmove = 0;
+   int *order;
+
+   /* The layout below places ONE record slab per record variable, which is the whole record section
+    * only while numrecs <= 1.  A file with interleaved records is refused before anything is touched
+    * (the reference never redefines such a file: src/matrix.c:288, :3865 act on its own matrix file). */
+   if (f->numrecs > 1)
+      for (i = 0; i < f->nvars; i++)
+         if (f->vars[i].is_rec)
+            return NC_EINVAL;
 
    /* header length does not depend on the begin values, only on the version */
    if (build_header (f, &b)) {
@@ -526,27 +536,39 @@ do_enddef (nc3_file * f)
       return NC_EINVAL;
    }
 
-   /* grow the file first, then relocate existing variables last-to-first */
+   /* grow the file first (never shrink it), then relocate the existing variables in DESCENDING order
+    * of their old position: data only ever moves towards the end of the file, so a variable moved
+    * later (lower old offset) cannot be overwritten by one moved earlier */
    fflush (f->fp);
-   if (ftruncate (fileno (f->fp), (off_t) end)) {
-      /* only fail if the file would end up too short */
+   {
       off_t cur;
       fseeko (f->fp, 0, SEEK_END);
       cur = ftello (f->fp);
-      if ((uint64_t) cur < end) {
+      if (cur < 0 || ((uint64_t) cur < end && ftruncate (fileno (f->fp), (off_t) end))) {
          free (b.p);
          return NC_EIO;
       }
    }
-   for (i = f->nvars - 1; i >= 0; i--) {
-      nc3_var *v = &f->vars[i];
-      if (v->old_begin != (uint64_t) - 1 && v->old_begin != v->begin) {
-         if (move_bytes (f->fp, v->old_begin, v->begin, v->vsize)) {
-            free (b.p);
-            return NC_EIO;
-         }
+   if ((order = malloc (sizeof (int) * (size_t) (f->nvars ? f->nvars : 1))) == NULL) {
+      free (b.p);
+      return NC_ENOMEM;
+   }
+   for (i = 0; i < f->nvars; i++)
+      if (f->vars[i].old_begin != (uint64_t) - 1 && f->vars[i].old_begin != f->vars[i].begin) {
+         int v = i;
+         for (k = nmove++; k > 0 && f->vars[order[k - 1]].old_begin < f->vars[v].old_begin; k--)
+            order[k] = order[k - 1];
+         order[k] = v;
+      }
+   for (k = 0; k < nmove; k++) {
+      nc3_var *v = &f->vars[order[k]];
+      if (move_bytes (f->fp, v->old_begin, v->begin, v->vsize)) {
+         free (order);
+         free (b.p);
+         return NC_EIO;
       }
    }
+   free (order);
    for (i = 0; i < f->nvars; i++)
       f->vars[i].old_begin = f->vars[i].begin;
 
@@ -1152,8 +1174,8 @@ put_var (int ncid, int varid, const void *in, int kind)
    v = &f->vars[varid];
    if (v->type == NC_CHAR)
       return NC_ECHAR;
-   if (v->is_rec)
-      return NC_EINVAL;
+   if (v->is_rec && f->numrecs > 1)
+      return NC_EINVAL;         /* interleaved records; one record is one contiguous slab, like get_var */
    n = var_nelems (f, v);
    ts = type_size (v->type);
    if ((buf = malloc ((size_t) IO_CHUNK_ELEMS * ts)) == NULL)

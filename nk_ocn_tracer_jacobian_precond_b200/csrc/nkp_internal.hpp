@@ -132,21 +132,68 @@ struct BigItem {
     int idx;     // row slab (forward) or pivot panel (backward)
 };
 
-// multi-GPU: the update matrix (factorisation) / update vector (forward sweep) of `front`
-// travels from the owner of the front to the owner of its parent
+// multi-GPU, forward sweep: the update vector of `front` (a child of a top front) travels from a rank
+// that has swept it to a member of the parent's group that has not
 struct Xfer {
     int front;
     int src, dst;
     int level;   // level of `front` (the child)
 };
 
+// ---- multi-GPU: distributed factorisation of the top separator fronts --------------------------------
+// A top front (an ancestor of the rank-private subtrees) is factored by its GROUP: the ranks that own
+// something below it.  Every member keeps a full copy of the front's arrays; the pivot columns are cut
+// into outer blocks of W = outer * nb columns, block K (its Larr and UTarr column blocks) belongs to member
+// K mod g, the column blocks of the update matrix continue the same cycle.  Per block: the owner factors
+// the panel, both column blocks are broadcast over the group's communicator, every member applies the
+// wide Schur update to the blocks it owns -- the block that is factored next first (look-ahead), so that
+// its broadcast overlaps everybody's remaining update.  After the last block every member holds the
+// complete factors of the front, and the sweeps of the top fronts need no communication at all.
+struct TopBcast {       // one ncclBroadcast over the group of the receiving front
+    int root;           // world rank that holds the data
+    int pad;
+    int64_t off;        // heap offset on THIS rank (send buffer on the root, receive buffer elsewhere)
+    int64_t count;      // doubles
+};
+
+struct TopStep {        // one inner panel (nb columns) of the panel factorisation, owner only
+    int diag_begin = 0, diag_end = 0;
+    int trsm_begin = 0, trsm_end = 0, trsm_ctas = 0;
+    int gemm_begin = 0, gemm_end = 0, gemm_tiles = 0;   // narrow update of the rest of the outer block
+};
+
+struct TopBlock {       // one outer block of a top front
+    int owner = 0;      // world rank
+    int step_begin = 0, step_end = 0;                       // Plan::top_steps (empty unless this rank is the owner)
+    int next_begin = 0, next_end = 0, next_tiles = 0;       // GemmTasks: wide update of block K + 1 (its owner only)
+    int rest_begin = 0, rest_end = 0, rest_tiles = 0;       // GemmTasks: wide update of the other blocks this rank owns
+    TopBcast bl, bu;                                        // the factored Larr / UTarr column blocks
+};
+
+struct TopFront {
+    int front = 0;
+    int group = 0;              // index into Plan::groups
+    int member = 0;             // this rank belongs to the group (and stores the front)
+    int block_begin = 0, block_end = 0;   // Plan::top_blocks
+    int cb_begin = 0, cb_end = 0;         // Plan::top_child_bcasts: update matrices of the children
+    std::vector<int> add_begin, add_tiles;   // extend-add passes (one per child), ranges into Plan::add_tasks
+    int inv_begin = 0, inv_end = 0;       // Plan::inv_tasks: diagonal blocks inverted after the factorisation
+    int64_t f22_off = 0, f22_len = 0;     // this front's own update matrix (cleared before the extend-add)
+};
+
+// solution ranges published after the backward sweep: [lo, hi) of the permuted numbering, held by `root`
+struct PubRange {
+    int lo, hi, root;
+};
+
 struct LevelPlan {
     int level = 0;
     std::vector<int> fronts;             // fronts on this level (all ranks)
-    std::vector<int> mine;               // ... owned by this rank
-    std::vector<int> ghosts;             // ... not owned, but children of fronts owned by this rank
+    std::vector<int> mine;               // ... rank-private (non-top) fronts owned by this rank: batched factor launches
+    std::vector<int> stored;             // ... every front this rank keeps factors of (mine + its top fronts): sweeps
+    std::vector<int> ghosts;             // ... not stored, but children of fronts stored by this rank
     std::vector<int> xfers;              // indices into Plan::xfers whose child lives on this level
-    std::vector<int> tops;               // top fronts (shared part of the tree) on this level
+    std::vector<int> tops;               // indices into Plan::top_fronts of the top fronts on this level (all ranks)
     int nsteps = 0;                      // ceil(max s / nb)
     // per step task ranges into the flat arrays below
     std::vector<int> diag_begin, trsm_begin, gemm_begin;  // size nsteps+1
@@ -220,9 +267,16 @@ struct Plan {
     std::vector<char> is_top;        // per front: part of the shared top of the tree
     std::vector<int> subtree_roots;  // roots of the rank-private subtrees
     std::vector<int> subtree_lo;     // per subtree root: first permuted index of the subtree
-    std::vector<Xfer> xfers;         // every parent/child pair with different owners
-    double flops_local = 0;          // factor flops of the fronts owned by this rank
-    int64_t nnz_lu_local = 0;
+    std::vector<Xfer> xfers;         // forward sweep: update vectors that a member of a top front's group lacks
+    std::vector<std::vector<int>> groups;   // distinct rank sets of the top fronts (sorted world ranks)
+    std::vector<int> group_of;              // per front: index into groups (-1 for rank-private fronts)
+    std::vector<TopFront> top_fronts;       // in postorder (children before parents), all ranks
+    std::vector<TopBlock> top_blocks;
+    std::vector<TopStep> top_steps;
+    std::vector<TopBcast> top_child_bcasts;
+    std::vector<PubRange> pub;              // who publishes which part of the solution
+    double flops_local = 0;          // factor flops of the fronts owned by this rank (top fronts: 1 / group size)
+    int64_t nnz_lu_local = 0;        // factor entries stored by this rank (top fronts: full copy on every member)
 };
 
 // analysis.cpp

@@ -100,6 +100,35 @@ bool nccl_load() {
 
 static const int MAX_NR = 8;
 
+// ---- host staging ---------------------------------------------------------------------------------
+// Caller buffers are plain C arrays (src/matrix.c:84, src/solve_ABglobal.c:344).  Page-locked ones
+// (cudaMallocHost / cudaHostRegister by the caller) are handed to the copy engine directly; pageable
+// ones go through the solver's pinned staging area with a multi-threaded copy -- one core moves about
+// 10 GB/s, a PCIe 5 x16 link 50+.
+#include <omp.h>
+static bool host_is_pinned(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost;
+}
+static void par_memcpy(void* dst, const void* src, size_t bytes) {
+    const size_t chunk = (size_t)1 << 21;
+    const long nchunks = (long)((bytes + chunk - 1) / chunk);
+    const int nt = std::max(1, std::min(16, omp_get_max_threads()));
+    if (nchunks <= 1 || nt == 1) {
+        memcpy(dst, src, bytes);
+        return;
+    }
+#pragma omp parallel for schedule(static) num_threads(nt)
+    for (long c = 0; c < nchunks; c++) {
+        const size_t o = (size_t)c * chunk;
+        memcpy((char*)dst + o, (const char*)src + o, std::min(chunk, bytes - o));
+    }
+}
+
 struct nkp_solver {
     Plan plan;
     nkp_options opt;
@@ -145,13 +174,15 @@ struct nkp_solver {
     double* d_xb = nullptr;     // n x MAX_NR staging for host-pointer solves (B)
     double* d_x = nullptr;      // n x MAX_NR solution accumulator
     double* d_berr = nullptr;   // MAX_NR (+ MAX_NR sums)
+    double* d_sumsq = nullptr;  // per-block partial sums of k_sumsq (fixed-order final reduction)
     int* d_nrepl = nullptr;
     // tracer fields (nkp_set_tracer_maps / nkp_solve_fields)
     int tsl = 0, ct = 0;        // tracer_state_len, coupled_tracer_cnt
     int64_t ncell = 0;          // imt * jmt * km
     int* d_cell = nullptr;      // flat (k, j, i) cell index of every tracer-state entry
     double* d_fields = nullptr; // MAX_NR * ct device copies of the 3-D fields
-    double* h_field = nullptr;  // pinned staging, one field
+    double* h_field = nullptr;  // pinned staging, one slot per field of a batch
+    std::vector<cudaEvent_t> ev_field;   // per-field D2H completion
     double* h_pinned = nullptr; // pinned staging for values / rhs
     size_t pinned_bytes = 0;
     bool factored = false;
@@ -218,14 +249,16 @@ void nkp_default_options(nkp_options* o) {
     o->nb = 64;
     o->leaf = 96;
     o->equil = 1;
-    o->refine_max = 10;
+    o->refine_max = 20;   // ITMAX of pdgsrfs
     o->device = 0;
     o->verbose = 0;
+    o->residual_extra = 1;   // see include/nkprecond.h: costs nothing (the SpMV is HBM bound), converges in fewer steps
     const char* e;
     if ((e = getenv("NKP_LEAF"))) o->leaf = atoi(e);
     if ((e = getenv("NKP_VERBOSE"))) o->verbose = atoi(e);
     if ((e = getenv("NKP_EQUIL"))) o->equil = atoi(e);
     if ((e = getenv("NKP_REFINE_RULE"))) o->refine_rule = atoi(e);
+    if ((e = getenv("NKP_RESIDUAL_EXTRA"))) o->residual_extra = atoi(e);
 }
 
 static int create_impl(nkp_solver** out, int n, const int* rowptr, const int* colind, const int* ci,
@@ -357,6 +390,7 @@ static int create_impl(nkp_solver** out, int n, const int* rowptr, const int* co
         CK(cudaMalloc((void**)&s->d_x, sizeof(double) * (size_t)n * MAX_NR));
         CK(cudaMalloc((void**)&s->d_xb, sizeof(double) * (size_t)n * MAX_NR));
         CK(cudaMalloc((void**)&s->d_berr, sizeof(double) * 4 * MAX_NR));
+        CK(cudaMalloc((void**)&s->d_sumsq, sizeof(double) * SUMSQ_BLOCKS * MAX_NR));
         CK(cudaMalloc((void**)&s->d_nrepl, sizeof(int)));
         s->pinned_bytes = sizeof(double) * std::max<size_t>((size_t)s->nnz, (size_t)n * MAX_NR);
         CK(cudaMallocHost((void**)&s->h_pinned, s->pinned_bytes));
@@ -514,6 +548,16 @@ static int do_factor(nkp_solver* s) {
     return NKP_OK;
 }
 
+// max |A| of the values in d_val (tiny-pivot threshold without equilibration)
+static int device_amax(nkp_solver* s) {
+    CK(cudaMemsetAsync(s->d_berr + 3 * MAX_NR, 0, sizeof(double), s->stream));
+    k_absmax<<<1024, 256, 0, s->stream>>>(s->nnz, s->d_val, s->d_berr + 3 * MAX_NR);
+    s->launches++;
+    CK(cudaMemcpyAsync(&s->amax, s->d_berr + 3 * MAX_NR, sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
 int nkp_factor_device(nkp_solver* s, const double* d_nzval) {
     if (!s || !d_nzval) {
         g_err = "nkp_factor_device: invalid argument";
@@ -522,6 +566,7 @@ int nkp_factor_device(nkp_solver* s, const double* d_nzval) {
     CK(cudaSetDevice(s->opt.device));
     if (d_nzval != s->d_val)
         CK(cudaMemcpyAsync(s->d_val, d_nzval, sizeof(double) * (size_t)s->nnz, cudaMemcpyDeviceToDevice, s->stream));
+    if (!s->opt.equil && device_amax(s)) return NKP_ECUDA;
     return do_factor(s);
 }
 
@@ -535,9 +580,17 @@ int nkp_factor(nkp_solver* s, const double* nzval) {
     if (!s->opt.equil)
         for (int64_t p = 0; p < s->nnz; p++) amax = std::max(amax, std::fabs(nzval[p]));
     s->amax = amax;
-    // pageable -> pinned staging -> device (one async copy)
-    memcpy(s->h_pinned, nzval, sizeof(double) * (size_t)s->nnz);
-    CK(cudaMemcpyAsync(s->d_val, s->h_pinned, sizeof(double) * (size_t)s->nnz, cudaMemcpyHostToDevice, s->stream));
+    if (host_is_pinned(nzval)) {
+        CK(cudaMemcpyAsync(s->d_val, nzval, sizeof(double) * (size_t)s->nnz, cudaMemcpyHostToDevice, s->stream));
+    } else {
+        // pageable -> pinned staging (all cores) -> device, in four pieces so that DMA overlaps the host copies
+        const size_t nnz = (size_t)s->nnz, piece = (nnz + 3) / 4;
+        for (size_t o = 0; o < nnz; o += piece) {
+            const size_t len = std::min(piece, nnz - o);
+            par_memcpy(s->h_pinned + o, nzval + o, sizeof(double) * len);
+            CK(cudaMemcpyAsync(s->d_val + o, s->h_pinned + o, sizeof(double) * len, cudaMemcpyHostToDevice, s->stream));
+        }
+    }
     return do_factor(s);
 }
 
@@ -546,19 +599,20 @@ int nkp_factor_be(nkp_solver* s, const void* nzval_be) {
         g_err = "nkp_factor_be: invalid argument";
         return NKP_EINVAL;
     }
-    if (!s->opt.equil) {
-        g_err = "nkp_factor_be needs equilibration (the unscaled tiny-pivot threshold wants max|A| on the host)";
-        return NKP_EINVAL;
-    }
     CK(cudaSetDevice(s->opt.device));
     s->amax = 0;
-    // raw file bytes: pageable -> pinned staging -> device, then swapped in place
-    memcpy(s->h_pinned, nzval_be, sizeof(double) * (size_t)s->nnz);
-    CK(cudaMemcpyAsync(s->d_val, s->h_pinned, sizeof(double) * (size_t)s->nnz, cudaMemcpyHostToDevice, s->stream));
+    // raw file bytes: (pageable -> pinned staging ->) device, then swapped in place
+    if (host_is_pinned(nzval_be)) {
+        CK(cudaMemcpyAsync(s->d_val, nzval_be, sizeof(double) * (size_t)s->nnz, cudaMemcpyHostToDevice, s->stream));
+    } else {
+        par_memcpy(s->h_pinned, nzval_be, sizeof(double) * (size_t)s->nnz);
+        CK(cudaMemcpyAsync(s->d_val, s->h_pinned, sizeof(double) * (size_t)s->nnz, cudaMemcpyHostToDevice, s->stream));
+    }
     k_bswap64<<<(unsigned)((s->nnz + 255) / 256), 256, 0, s->stream>>>(reinterpret_cast<const unsigned long long*>(s->d_val),
                                                                       s->d_val, s->nnz);
     s->launches++;
     CK(cudaGetLastError());
+    if (!s->opt.equil && device_amax(s)) return NKP_ECUDA;
     return do_factor(s);
 }
 
@@ -718,6 +772,21 @@ static int sweeps(nkp_solver* s) {
     return 0;
 }
 
+// r = b - A x for nr right-hand sides in ONE pass over A
+static void launch_residual(nkp_solver* s, int nr, const double* x, int ldx, const double* b, int ldb, double* r, double* berr,
+                            double safe1, double safe2) {
+    const int g = (s->n + 255) / 256;
+    cudaStream_t st = s->stream;
+#define NKP_RES(NRT, EX) k_residual<NRT, EX><<<g, 256, 0, st>>>(s->n, nr, s->d_rowptr, s->d_colind, s->d_val, x, ldx, b, ldb, r, berr, safe1, safe2)
+    const bool ex = s->opt.residual_extra != 0;
+    if (nr <= 1) { if (ex) NKP_RES(1, true); else NKP_RES(1, false); }
+    else if (nr == 2) { if (ex) NKP_RES(2, true); else NKP_RES(2, false); }
+    else if (nr <= 4) { if (ex) NKP_RES(4, true); else NKP_RES(4, false); }
+    else { if (ex) NKP_RES(8, true); else NKP_RES(8, false); }
+#undef NKP_RES
+    s->launches++;
+}
+
 static int sweeps_nr(nkp_solver* s, int nr) {
     switch (nr) {
         case 1: return sweeps<1>(s);
@@ -736,7 +805,9 @@ static int solve_chunk(nkp_solver* s, double* dB, int ldb, int nr, double* berr_
     const int nrp = padded_nr(nr);
     const int g = (n + 255) / 256;
     const double eps = 2.220446049250313e-16;
-    const double safe = 2.2250738585072014e-308 * (double)(s->nnz / n + 2) / eps;
+    // pdgsrfs: safe1 = nz * safmin (nz = A->ncol + 1 in the library; any small multiple of safmin serves), safe2 = safe1 / eps
+    const double safe1 = 2.2250738585072014e-308 * (double)(s->nnz / n + 2);
+    const double safe2 = safe1 / eps;
     // x = 0-th solve
     if (nrp > nr) CK(cudaMemsetAsync(s->d_y, 0, sizeof(double) * (size_t)n * nrp, st));
     k_permute_in<<<g, 256, 0, st>>>(n, nr, s->d_perm, s->d_R, dB, ldb, s->d_y);
@@ -744,28 +815,27 @@ static int solve_chunk(nkp_solver* s, double* dB, int ldb, int nr, double* berr_
     k_permute_out<<<g, 256, 0, st>>>(n, nr, s->d_perm, s->d_C, s->d_y, s->d_x, n, 0, 0xffu);
     s->launches += 2;
     double last[MAX_NR];
-    for (int c = 0; c < nr; c++) last[c] = 1e300;
+    for (int c = 0; c < nr; c++) last[c] = 3.0;   // lstres of pdgsrfs
     double berr[MAX_NR] = {0};
     bool done[MAX_NR] = {false};
     const bool normwise = s->opt.refine_rule == 1;
     double bnorm2[MAX_NR] = {0}, rnorm2[MAX_NR] = {0};
     if (normwise) {
-        CK(cudaMemsetAsync(s->d_berr + MAX_NR, 0, sizeof(double) * MAX_NR, st));
-        k_sumsq<<<256, 256, 0, st>>>(n, nr, dB, ldb, s->d_berr + MAX_NR);
-        s->launches++;
+        k_sumsq<<<SUMSQ_BLOCKS, 256, 0, st>>>(n, nr, dB, ldb, s->d_sumsq);
+        k_sumsq_final<<<1, 32, 0, st>>>(SUMSQ_BLOCKS, nr, s->d_sumsq, s->d_berr + MAX_NR);
+        s->launches += 2;
         CK(cudaMemcpyAsync(bnorm2, s->d_berr + MAX_NR, sizeof(double) * nr, cudaMemcpyDeviceToHost, st));
     }
     int it = 0;
     for (;;) {
         // r = b - A x, berr
         CK(cudaMemsetAsync(s->d_berr, 0, sizeof(double) * MAX_NR, st));
-        k_residual<<<dim3(g, nr), 256, 0, st>>>(n, nr, s->d_rowptr, s->d_colind, s->d_val, s->d_x, n, dB, ldb, s->d_r, s->d_berr, safe);
-        s->launches++;
+        launch_residual(s, nr, s->d_x, n, dB, ldb, s->d_r, s->d_berr, safe1, safe2);
         CK(cudaMemcpyAsync(berr, s->d_berr, sizeof(double) * nr, cudaMemcpyDeviceToHost, st));
         if (normwise) {
-            CK(cudaMemsetAsync(s->d_berr + 2 * MAX_NR, 0, sizeof(double) * MAX_NR, st));
-            k_sumsq<<<256, 256, 0, st>>>(n, nr, s->d_r, n, s->d_berr + 2 * MAX_NR);
-            s->launches++;
+            k_sumsq<<<SUMSQ_BLOCKS, 256, 0, st>>>(n, nr, s->d_r, n, s->d_sumsq);
+            k_sumsq_final<<<1, 32, 0, st>>>(SUMSQ_BLOCKS, nr, s->d_sumsq, s->d_berr + 2 * MAX_NR);
+            s->launches += 2;
             CK(cudaMemcpyAsync(rnorm2, s->d_berr + 2 * MAX_NR, sizeof(double) * nr, cudaMemcpyDeviceToHost, st));
         }
         CK(cudaStreamSynchronize(st));
@@ -848,23 +918,27 @@ int nkp_solve(nkp_solver* s, double* B, int ldb, int nrhs, double* berr) {
     for (int c0 = 0; c0 < nrhs; c0 += MAX_NR) {
         int nr = std::min(MAX_NR, nrhs - c0);
         // column by column, so that the DMA of one column overlaps the host copy of the next
+        const bool pinned = host_is_pinned(B + (size_t)c0 * ldb);
         for (int c = 0; c < nr; c++) {
-            memcpy(s->h_pinned + (size_t)c * n, B + (size_t)(c0 + c) * ldb, sizeof(double) * n);
-            CK(cudaMemcpyAsync(s->d_xb + (size_t)c * n, s->h_pinned + (size_t)c * n, sizeof(double) * n,
-                               cudaMemcpyHostToDevice, s->stream));
+            const double* src = B + (size_t)(c0 + c) * ldb;
+            if (!pinned) {
+                par_memcpy(s->h_pinned + (size_t)c * n, src, sizeof(double) * n);
+                src = s->h_pinned + (size_t)c * n;
+            }
+            CK(cudaMemcpyAsync(s->d_xb + (size_t)c * n, src, sizeof(double) * n, cudaMemcpyHostToDevice, s->stream));
         }
         int rc = nkp_solve_device(s, s->d_xb, n, nr, berr ? berr + c0 : nullptr);
         if (rc) return rc;
         tsum += s->t_solve;
         maxsteps = std::max(maxsteps, s->refine_steps);
         for (int c = 0; c < nr; c++) {
-            CK(cudaMemcpyAsync(s->h_pinned + (size_t)c * n, s->d_xb + (size_t)c * n, sizeof(double) * n,
-                               cudaMemcpyDeviceToHost, s->stream));
+            double* dst = pinned ? B + (size_t)(c0 + c) * ldb : s->h_pinned + (size_t)c * n;
+            CK(cudaMemcpyAsync(dst, s->d_xb + (size_t)c * n, sizeof(double) * n, cudaMemcpyDeviceToHost, s->stream));
             CK(cudaEventRecord(s->ev_col[c], s->stream));
         }
         for (int c = 0; c < nr; c++) {
             CK(cudaEventSynchronize(s->ev_col[c]));
-            memcpy(B + (size_t)(c0 + c) * ldb, s->h_pinned + (size_t)c * n, sizeof(double) * n);
+            if (!pinned) par_memcpy(B + (size_t)(c0 + c) * ldb, s->h_pinned + (size_t)c * n, sizeof(double) * n);
         }
     }
     s->t_solve = tsum;
@@ -899,7 +973,7 @@ int nkp_set_tracer_maps(nkp_solver* s, int tracer_state_len, int coupled_tracer_
     s->ncell = (int64_t)imt * jmt * km;
     if (upload(&s->d_cell, cell)) return NKP_ECUDA;
     CK(cudaMalloc((void**)&s->d_fields, sizeof(double) * (size_t)s->ncell * MAX_NR * s->ct));
-    CK(cudaMallocHost((void**)&s->h_field, sizeof(double) * (size_t)s->ncell));
+    CK(cudaMallocHost((void**)&s->h_field, sizeof(double) * (size_t)s->ncell * MAX_NR * s->ct));
     return NKP_OK;
 }
 
@@ -931,10 +1005,14 @@ int nkp_solve_fields(nkp_solver* s, double* const* fields, int nfields, double* 
     for (int g0 = 0; g0 < ngroups; g0 += MAX_NR) {
         const int ng = std::min(MAX_NR, ngroups - g0);
         const int nf = ng * ct;
+        // one pinned staging slot per field: no synchronisation between the copies
         for (int f = 0; f < nf; f++) {
-            memcpy(s->h_field, fields[g0 * ct + f], fbytes);
-            CK(cudaMemcpyAsync(s->d_fields + (size_t)f * s->ncell, s->h_field, fbytes, cudaMemcpyHostToDevice, st));
-            CK(cudaStreamSynchronize(st));   // the staging buffer is reused
+            const double* src = fields[g0 * ct + f];
+            if (!host_is_pinned(src)) {
+                par_memcpy(s->h_field + (size_t)f * s->ncell, src, fbytes);
+                src = s->h_field + (size_t)f * s->ncell;
+            }
+            CK(cudaMemcpyAsync(s->d_fields + (size_t)f * s->ncell, src, fbytes, cudaMemcpyHostToDevice, st));
         }
         k_gather_fields<<<(tsl + 255) / 256, 256, 0, st>>>(tsl, ct, nf, s->d_cell, s->d_fields, s->ncell, s->d_xb, n);
         s->launches++;
@@ -945,10 +1023,21 @@ int nkp_solve_fields(nkp_solver* s, double* const* fields, int nfields, double* 
         k_scatter_fields<<<(tsl + 255) / 256, 256, 0, st>>>(tsl, ct, nf, s->d_cell, s->d_fields, s->ncell, s->d_xb, n);
         s->launches++;
         CK(cudaGetLastError());
+        if ((int)s->ev_field.size() < nf) {
+            const size_t old = s->ev_field.size();
+            s->ev_field.resize(nf, nullptr);
+            for (size_t q = old; q < s->ev_field.size(); q++) CK(cudaEventCreateWithFlags(&s->ev_field[q], cudaEventDisableTiming));
+        }
         for (int f = 0; f < nf; f++) {
-            CK(cudaMemcpyAsync(s->h_field, s->d_fields + (size_t)f * s->ncell, fbytes, cudaMemcpyDeviceToHost, st));
-            CK(cudaStreamSynchronize(st));
-            memcpy(fields[g0 * ct + f], s->h_field, fbytes);
+            double* dst = fields[g0 * ct + f];
+            if (!host_is_pinned(dst)) dst = s->h_field + (size_t)f * s->ncell;
+            CK(cudaMemcpyAsync(dst, s->d_fields + (size_t)f * s->ncell, fbytes, cudaMemcpyDeviceToHost, st));
+            CK(cudaEventRecord(s->ev_field[f], st));
+        }
+        for (int f = 0; f < nf; f++) {
+            CK(cudaEventSynchronize(s->ev_field[f]));
+            double* dst = fields[g0 * ct + f];
+            if (!host_is_pinned(dst)) par_memcpy(dst, s->h_field + (size_t)f * s->ncell, fbytes);
         }
     }
     s->t_solve = tsum;
@@ -961,9 +1050,8 @@ int nkp_residual_device(nkp_solver* s, const double* dx, const double* db, doubl
     if (nrhs == 0) return NKP_OK;
     CK(cudaSetDevice(s->opt.device));
     const int n = s->n;
-    k_residual<<<dim3((n + 255) / 256, nrhs), 256, 0, s->stream>>>(n, nrhs, s->d_rowptr, s->d_colind, s->d_val, dx, n, db, n, dr,
-                                                      nullptr, 0.0);
-    s->launches++;
+    for (int c0 = 0; c0 < nrhs; c0 += MAX_NR)
+        launch_residual(s, std::min(MAX_NR, nrhs - c0), dx + (size_t)c0 * n, n, db + (size_t)c0 * n, n, dr + (size_t)c0 * n, nullptr, 0.0, 0.0);
     CK(cudaGetLastError());
     return NKP_OK;
 }
@@ -1043,6 +1131,12 @@ int nkp_set_refine_rule(nkp_solver* s, int rule) {
     return NKP_OK;
 }
 
+int nkp_set_residual_extra(nkp_solver* s, int on) {
+    if (!s) return NKP_EINVAL;
+    s->opt.residual_extra = on != 0;
+    return NKP_OK;
+}
+
 int nkp_sync(nkp_solver* s) {
     if (!s) return NKP_EINVAL;
     CK(cudaStreamSynchronize(s->stream));
@@ -1058,7 +1152,7 @@ void nkp_destroy(nkp_solver* s) {
                     s->d_bidx, s->d_rel,    s->d_R,      s->d_C,      s->d_diag, s->d_trsm,    s->d_gemm,
                     s->d_add,  s->d_solve,  s->d_children, s->d_W,    s->d_y,    s->d_r,       s->d_x,
                     s->d_xb,   s->d_berr,   s->d_nrepl,  s->d_small,  s->d_big,  s->d_fwd_items, s->d_bwd_items,
-                    s->d_cnt,  s->d_inv,    s->d_rect_items, s->d_part, s->d_clo};
+                    s->d_cnt,  s->d_inv,    s->d_rect_items, s->d_part, s->d_clo, s->d_sumsq};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (s->h_pinned) cudaFreeHost(s->h_pinned);
@@ -1070,6 +1164,8 @@ void nkp_destroy(nkp_solver* s) {
     for (int i = 0; i < MAX_NR; i++)
         if (s->ev_col[i]) cudaEventDestroy(s->ev_col[i]);
     for (cudaEvent_t e : s->prof_ev) cudaEventDestroy(e);
+    for (cudaEvent_t e : s->ev_field)
+        if (e) cudaEventDestroy(e);
     if (s->stream) cudaStreamDestroy(s->stream);
     delete s;
 }

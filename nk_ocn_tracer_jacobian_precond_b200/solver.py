@@ -20,7 +20,8 @@ LIB_PATH = os.environ.get("NKP_LIB", os.path.join(_HERE, "libnkprecond.so"))   #
 
 class NkpOptions(C.Structure):
     _fields_ = [("nb", C.c_int), ("leaf", C.c_int), ("equil", C.c_int), ("refine_max", C.c_int),
-                ("device", C.c_int), ("verbose", C.c_int), ("refine_rule", C.c_int), ("reserved", C.c_int * 9)]
+                ("device", C.c_int), ("verbose", C.c_int), ("refine_rule", C.c_int), ("residual_extra", C.c_int),
+                ("reserved", C.c_int * 8)]
 
 
 class NkpStats(C.Structure):
@@ -72,6 +73,7 @@ def load_library():
     lib.nkp_set_analysis_cache.argtypes = [C.c_char_p]
     lib.nkp_set_profile.argtypes = [vp, C.c_int]
     lib.nkp_set_refine_rule.argtypes = [vp, C.c_int]
+    lib.nkp_set_residual_extra.argtypes = [vp, C.c_int]
     lib.nkp_destroy.argtypes = [vp]
     lib.nkp_destroy.restype = None
     lib.nkp_last_error.restype = C.c_char_p
@@ -213,6 +215,10 @@ class TracerJacobianSolver:
     def set_refine_rule(self, rule):
         """0: SuperLU's componentwise berr rule (default); 1: normwise ||r|| <= 1e-14 ||b||."""
         _check(self._lib.nkp_set_refine_rule(self._h, int(rule)), "nkp_set_refine_rule")
+
+    def set_residual_extra(self, on=True):
+        """Refinement residual accumulated in twice the working precision (nkp_options.residual_extra)."""
+        _check(self._lib.nkp_set_residual_extra(self._h, int(bool(on))), "nkp_set_residual_extra")
 
     def sync(self):
         _check(self._lib.nkp_sync(self._h), "nkp_sync")

@@ -242,15 +242,17 @@ def make_full_fields(grid: dict, circ: dict, seed: int = 0) -> dict:
         coef[off] = c
         self_c -= c
     coef[(0, 0, 0)] = np.where(ocean, self_c, 0.0)
-    kidx, jidx, iidx = np.meshgrid(np.arange(km), np.arange(jmt), np.arange(imt), indexing="ij")
+    # every (cell, offset) pair belongs to exactly one residue class, and the 15 offsets of one cell fall
+    # into 15 different classes: one scatter per offset fills all 36 fields
+    ka, ja, ia = np.arange(km)[:, None, None], np.arange(jmt)[None, :, None], np.arange(imt)[None, None, :]
+    irf = np.zeros((36, km, jmt, imt))
+    for (dk, dj, di), c in coef.items():
+        cls = ((((ia + di) % imt) % 4) * 3 + (ja + dj) % 3) * 3 + (ka + dk) % 3
+        np.put_along_axis(irf, np.broadcast_to(cls, (km, jmt, imt))[None], (c + 0.0)[None], axis=0)   # + 0.0: no negative zeros
     for ip in range(4):
         for jp in range(3):
             for kp in range(3):
-                irf = np.zeros((km, jmt, imt))
-                for (dk, dj, di), c in coef.items():
-                    match = (((iidx + di) % imt) % 4 == ip) & ((jidx + dj) % 3 == jp) & ((kidx + dk) % 3 == kp)
-                    irf += np.where(match, c, 0.0)
-                out[f"HDIF_EXPLICIT_3D_IRF_{ip + 1}_{jp + 1}_{kp + 1}"] = irf
+                out[f"HDIF_EXPLICIT_3D_IRF_{ip + 1}_{jp + 1}_{kp + 1}"] = irf[(ip * 3 + jp) * 3 + kp]
     return out
 
 

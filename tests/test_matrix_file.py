@@ -169,6 +169,73 @@ def test_nc3_reads_scipy_written_file(tmp_path):
     assert lib.nc_open(str(tmp_path / "missing.nc").encode(), 0, ctypes.byref(ncid)) != 0
 
 
+def _scipy_record_file(fn, nrec):
+    from scipy.io import netcdf_file
+    f = netcdf_file(fn, "w", version=2)
+    f.createDimension("time", None)
+    f.createDimension("z", 3)
+    fx = f.createVariable("fixed", "d", ("z",))
+    fx[:] = [7.0, 8.0, 9.0]
+    v = f.createVariable("T", "d", ("time", "z"))
+    w = f.createVariable("S", "d", ("time", "z"))
+    for r in range(nrec):
+        v[r] = [1.0 + 10 * r, 2.0 + 10 * r, 3.0 + 10 * r]
+        w[r] = [-1.0 - 10 * r, -2.0 - 10 * r, -3.0 - 10 * r]
+    f.close()
+
+
+def test_nc3_record_variable_one_record_read_write_redef(tmp_path):
+    """A POP tracer file whose fields carry an unlimited time dimension of length 1 works with the
+    reference on real libnetcdf (get_var_3d_double / put_var_3d_double, src/file_io.c:273-334): the
+    provider reads AND writes such a variable, and nc_redef + nc_enddef relocates it intact."""
+    from scipy.io import netcdf_file
+    lib = _nc3()
+    fn = str(tmp_path / "rec1.nc")
+    _scipy_record_file(fn, 1)
+    dp = lambda a: a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+    ncid, vid, sid = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    assert lib.nc_open(fn.encode(), 1, ctypes.byref(ncid)) == 0      # NC_WRITE
+    assert lib.nc_inq_varid(ncid, b"T", ctypes.byref(vid)) == 0
+    out = np.zeros(3)
+    assert lib.nc_get_var_double(ncid, vid, dp(out)) == 0 and np.array_equal(out, [1.0, 2.0, 3.0])
+    new = np.array([0.5, 0.25, 0.125])
+    assert lib.nc_put_var_double(ncid, vid, dp(new)) == 0
+    # grow the header: fixed and record data both move, nothing may be lost or overwritten
+    assert lib.nc_redef(ncid) == 0
+    d2, v2 = ctypes.c_int(), ctypes.c_int()
+    assert lib.nc_def_dim(ncid, b"a_long_dimension_name_that_grows_the_header_by_a_lot", ctypes.c_size_t(4), ctypes.byref(d2)) == 0
+    dims = (ctypes.c_int * 1)(d2.value)
+    assert lib.nc_def_var(ncid, b"extra_fixed_variable_with_a_long_name", 6, 1, dims, ctypes.byref(v2)) == 0
+    assert lib.nc_enddef(ncid) == 0
+    assert lib.nc_close(ncid) == 0
+    f = netcdf_file(fn, "r", mmap=False)
+    assert np.array_equal(f.variables["fixed"].data, [7.0, 8.0, 9.0])
+    assert np.array_equal(f.variables["T"].data, [[0.5, 0.25, 0.125]])
+    assert np.array_equal(f.variables["S"].data, [[-1.0, -2.0, -3.0]])
+    f.close()
+
+
+def test_nc3_refuses_interleaved_records_without_damage(tmp_path):
+    """numrecs > 1: whole-variable get/put and the relocation of nc_redef are refused, and the file is
+    left byte for byte as it was (no truncation, no partial move)."""
+    lib = _nc3()
+    fn = str(tmp_path / "rec2.nc")
+    _scipy_record_file(fn, 2)
+    before = open(fn, "rb").read()
+    ncid, vid = ctypes.c_int(), ctypes.c_int()
+    assert lib.nc_open(fn.encode(), 1, ctypes.byref(ncid)) == 0
+    assert lib.nc_inq_varid(ncid, b"T", ctypes.byref(vid)) == 0
+    buf = np.zeros(6)
+    assert lib.nc_get_var_double(ncid, vid, buf.ctypes.data_as(ctypes.POINTER(ctypes.c_double))) != 0
+    assert lib.nc_put_var_double(ncid, vid, buf.ctypes.data_as(ctypes.POINTER(ctypes.c_double))) != 0
+    assert lib.nc_redef(ncid) == 0
+    d2 = ctypes.c_int()
+    assert lib.nc_def_dim(ncid, b"another_long_dimension_name_to_grow_the_header", ctypes.c_size_t(4), ctypes.byref(d2)) == 0
+    assert lib.nc_enddef(ncid) != 0
+    lib.nc_abort(ncid) if hasattr(lib, "nc_abort") else lib.nc_close(ncid)
+    assert open(fn, "rb").read() == before
+
+
 def test_reftest_golden_known_answers(reftest_matrix):
     """The reference's own test options (test/test_gen_A.csh:22-23): upwind3 + isop_file rows have
     up to 21 entries (src/matrix.c:621-650), sorted, diagonal present, zeros stripped."""
