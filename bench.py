@@ -610,8 +610,9 @@ def run_own(args):
                 "levels": st["n_levels"], "max_front": st["max_front"], "analysis_s": m["analysis_s"],
                 "l2": "operand and factors exceed L2 (%.1f GB heap); no flush needed" % (st["heap_bytes"] * 1e-9),
                 "parallelism": "1 GPU" if world == 1 else
-                f"{world} GPUs: nested-dissection subtrees sharded over the GPUs, top separator fronts on their heaviest "
-                f"child's GPU, NCCL send/recv of update matrices and broadcast of separator solutions ({int(st['n_xfers'])} transfers)",
+                f"{world} GPUs: nested-dissection subtrees sharded over the GPUs; the top separator fronts are factored by the "
+                f"group of GPUs below them (block-cyclic column blocks, panel broadcasts over NCCL with look-ahead) and swept "
+                f"by every member, so a sweep pair needs {int(st['n_xfers'])} update-vector transfers and one solution exchange",
                 "generate_s": t_gen,
             },
             "tiny_pivots_replaced": m["tiny_pivots_replaced"],

@@ -656,18 +656,11 @@ int analyse(int n, const int* rowptr, const int* colind, const int* const coords
         }
         plan.subtree_roots = cand;
         std::sort(plan.subtree_roots.begin(), plan.subtree_roots.end());
-        // owners: subtree members inherit top-down, top fronts take the owner of their heaviest child
+        // owners: subtree members inherit top-down
         for (int t = nf - 1; t >= 0; t--) {
             if (plan.is_top[t]) continue;
             if (cand_owner[t] >= 0) plan.owner[t] = cand_owner[t];
             else plan.owner[t] = plan.owner[plan.fronts[t].parent];
-        }
-        for (int t = 0; t < nf; t++) {
-            if (!plan.is_top[t]) continue;
-            int best = -1;
-            for (int c : nodes[t].children)
-                if (best < 0 || flsub[c] > flsub[best]) best = c;
-            plan.owner[t] = plan.owner[best];
         }
         // first permuted index of every subtree (postorder => contiguous ranges)
         std::vector<int> lo(nf);
@@ -678,9 +671,40 @@ int analyse(int n, const int* rowptr, const int* colind, const int* const coords
         plan.subtree_lo.clear();
         for (int t : plan.subtree_roots) plan.subtree_lo.push_back(lo[t]);
     }
-    auto mine = [&](int t) { return plan.owner[t] == plan.rank; };
+    // groups of the top fronts: the ranks that own something below them (children come first in postorder)
+    plan.group_of.assign(nf, -1);
+    {
+        std::vector<std::vector<int>> grp(nf);
+        for (int t = 0; t < nf; t++) {
+            if (!plan.is_top[t]) continue;
+            std::vector<int>& g = grp[t];
+            for (int c : nodes[t].children) {
+                if (plan.is_top[c]) g.insert(g.end(), grp[c].begin(), grp[c].end());
+                else g.push_back(plan.owner[c]);
+            }
+            std::sort(g.begin(), g.end());
+            g.erase(std::unique(g.begin(), g.end()), g.end());
+            int gi = -1;
+            for (size_t q = 0; q < plan.groups.size(); q++)
+                if (plan.groups[q] == g) gi = (int)q;
+            if (gi < 0) {
+                gi = (int)plan.groups.size();
+                plan.groups.push_back(g);
+            }
+            plan.group_of[t] = gi;
+            plan.owner[t] = g[0];   // the member that publishes the front's part of the solution
+        }
+    }
+    auto in_group = [&](int t, int r) {
+        const std::vector<int>& g = plan.groups[plan.group_of[t]];
+        return std::binary_search(g.begin(), g.end(), r);
+    };
+    // stores(t): this rank keeps the factors of front t (its own subtrees; every top front whose group it is in)
+    auto stores_r = [&](int t, int r) { return plan.is_top[t] ? in_group(t, r) : plan.owner[t] == r; };
+    auto stores = [&](int t) { return stores_r(t, plan.rank); };
+    auto mine = [&](int t) { return !plan.is_top[t] && plan.owner[t] == plan.rank; };
     auto ghost = [&](int t) {
-        return !mine(t) && plan.fronts[t].parent >= 0 && mine(plan.fronts[t].parent);
+        return !stores(t) && plan.fronts[t].parent >= 0 && stores(plan.fronts[t].parent);
     };
 
     // ---- memory plan (this rank's fronts only) ---------------------------------------------------
@@ -692,11 +716,11 @@ int analyse(int n, const int* rowptr, const int* colind, const int* const coords
         Front& f = plan.fronts[t];
         flops += fl[t];
         nnz_lu += (int64_t)f.s * f.s + 2 * (int64_t)f.s * f.r;
-        if (!mine(t)) {
+        if (!stores(t)) {
             f.Loff = f.UToff = -1;
             continue;
         }
-        plan.flops_local += fl[t];
+        plan.flops_local += plan.is_top[t] ? fl[t] / (double)plan.groups[plan.group_of[t]].size() : fl[t];
         plan.nnz_lu_local += (int64_t)f.s * f.s + 2 * (int64_t)f.s * f.r;
         f.Loff = off;
         off = align_up(off + (int64_t)f.ld * f.s, AL);
@@ -713,14 +737,30 @@ int analyse(int n, const int* rowptr, const int* colind, const int* const coords
         LevelPlan& L = plan.levels[plan.fronts[t].level];
         L.fronts.push_back(t);
         if (mine(t)) L.mine.push_back(t);
+        if (stores(t)) L.stored.push_back(t);
         else if (ghost(t)) L.ghosts.push_back(t);
-        if (plan.is_top[t]) L.tops.push_back(t);
+        // forward sweep: members of the parent's group that do not sweep this child receive its update vector
         int pa = plan.fronts[t].parent;
-        if (pa >= 0 && plan.owner[pa] != plan.owner[t]) {
-            L.xfers.push_back((int)plan.xfers.size());
-            plan.xfers.push_back(Xfer{t, plan.owner[t], plan.owner[pa], plan.fronts[t].level});
+        if (pa >= 0 && plan.is_top[pa]) {
+            std::vector<int> have;
+            if (plan.is_top[t]) have = plan.groups[plan.group_of[t]];
+            else have.push_back(plan.owner[t]);
+            int k = 0;
+            for (int p : plan.groups[plan.group_of[pa]]) {
+                if (std::binary_search(have.begin(), have.end(), p)) continue;
+                L.xfers.push_back((int)plan.xfers.size());
+                plan.xfers.push_back(Xfer{t, have[k % have.size()], p, plan.fronts[t].level});
+                k++;
+            }
         }
     }
+    // who publishes which part of the solution after the backward sweep
+    for (size_t q = 0; q < plan.subtree_roots.size(); q++) {
+        int t = plan.subtree_roots[q];
+        plan.pub.push_back(PubRange{plan.subtree_lo[q], plan.fronts[t].first + plan.fronts[t].s, plan.owner[t]});
+    }
+    for (int t = 0; t < nf; t++)
+        if (plan.is_top[t]) plan.pub.push_back(PubRange{plan.fronts[t].first, plan.fronts[t].first + plan.fronts[t].s, plan.owner[t]});
     // update-matrix pools: level l uses pool l & 1 (own fronts and ghost children)
     {
         int64_t len[2] = {0, 0};
@@ -728,7 +768,7 @@ int analyse(int n, const int* rowptr, const int* colind, const int* const coords
             int64_t o = 0;
             for (int t : plan.levels[l].fronts) {
                 Front& f = plan.fronts[t];
-                if (!mine(t) && !ghost(t)) {
+                if (!stores(t) && !ghost(t)) {
                     f.F22off = -1;
                     continue;
                 }
@@ -753,7 +793,7 @@ int analyse(int n, const int* rowptr, const int* colind, const int* const coords
     {
         int64_t o = 0;
         for (int t = 0; t < nf; t++) {
-            if (!mine(t) && !ghost(t)) {
+            if (!stores(t) && !ghost(t)) {
                 plan.fronts[t].woff = -1;
                 continue;
             }
@@ -778,7 +818,7 @@ int analyse(int n, const int* rowptr, const int* colind, const int* const coords
                 int pj = plan.perm[colind[p]];
                 int t = front_of[std::min(pi, pj)];
                 const Front& f = plan.fronts[t];
-                if (!mine(t)) {
+                if (!stores(t)) {
                     plan.scatter[p] = -1;
                     continue;
                 }
@@ -802,6 +842,93 @@ int analyse(int n, const int* rowptr, const int* colind, const int* const coords
     }
 
     // ---- task lists ------------------------------------------------------------------------------
+    // one Schur-update task: C[M x N] -= A[M x K] B[N x K]^T; tile0 counts the tiles of the launch it belongs to
+    auto push_gemm = [&](int& tile0, int64_t A, int64_t B, int64_t C, int M, int N, int K, int lda, int ldb, int ldc, int skip) {
+        if (M <= 0 || N <= 0) return;
+        GemmTask gt;
+        gt.Aoff = A;
+        gt.Boff = B;
+        gt.Coff = C;
+        gt.M = M;
+        gt.N = N;
+        gt.K = K;
+        gt.lda = lda;
+        gt.ldb = ldb;
+        gt.ldc = ldc;
+        gt.skip = skip;
+        gt.tile0 = tile0;
+        gt.tiles_m = (M + opt.tm - 1) / opt.tm;
+        gt.pad = 0;
+        tile0 += gt.tiles_m * ((N + opt.tn - 1) / opt.tn);
+        plan.gemm_tasks.push_back(gt);
+        // useful (algorithmic) entries of this update
+        double area = 0;
+        if (skip == 0) area = (double)M * N;
+        else
+            for (int c0 = 0; c0 < N; c0 += nb) {
+                int w = std::min(nb, N - c0);
+                int first_row = skip == 1 ? c0 : std::min(c0 + nb, N);
+                area += (double)(M - first_row) * w;
+            }
+        plan.gemm_flops += 2.0 * K * area;
+    };
+    // inner panel [k0, k0 + kb) of front f: diagonal block, both panel solves, and -- while the outer block
+    // [ko0, ke) is not finished -- the narrow update of the rest of the outer block (K = kb).
+    // Two-level blocking: G inner panels (nb columns each) form an outer block.  After every inner panel only
+    // the rest of the outer block is updated; after the last one everything beyond the outer block receives ONE
+    // wide update with K = width of the outer block, so the big trailing matrices are read and written once per
+    // G panels.
+    auto push_panel = [&](const Front& f, int k0, int ke, int& cta0, int& tile0) {
+        const int kb = std::min(nb, f.s - k0), k1 = k0 + kb;
+        const int64_t ld = f.ld;
+        int64_t Dblk = f.Loff + k0 + (int64_t)k0 * ld;
+        DiagTask d;
+        d.Doff = Dblk;
+        d.UTDoff = f.UToff + k0 + (int64_t)k0 * ld;
+        d.ld = f.ld;
+        d.kb = kb;
+        plan.diag_tasks.push_back(d);
+        const int below = f.m - k1;
+        if (below <= 0) return;
+        for (int which = 0; which < 2; which++) {
+            TrsmTask tt;
+            tt.Xoff = (which == 0 ? f.Loff : f.UToff) + k1 + (int64_t)k0 * ld;
+            tt.Toff = Dblk;
+            tt.ld = f.ld;
+            tt.nrows = below;
+            tt.kb = kb;
+            tt.unit = which;
+            tt.cta0 = cta0;
+            tt.pad = 0;
+            cta0 += (below + opt.trsm_rows - 1) / opt.trsm_rows;
+            plan.trsm_tasks.push_back(tt);
+        }
+        if (k1 < ke) {
+            // narrow: block columns / rows [k1, ke) of the outer block, all rows below
+            int64_t Lpan = f.Loff + k1 + (int64_t)k0 * ld;    // L[k1.., k0:k1]
+            int64_t UTpan = f.UToff + k1 + (int64_t)k0 * ld;  // U^T[k1.., k0:k1]
+            push_gemm(tile0, Lpan, UTpan, f.Loff + k1 + (int64_t)k1 * ld, below, ke - k1, kb, f.ld, f.ld, f.ld, 1);
+            push_gemm(tile0, UTpan, Lpan, f.UToff + k1 + (int64_t)k1 * ld, below, ke - k1, kb, f.ld, f.ld, f.ld, 2);
+        }
+    };
+    auto push_add = [&](const Front& fc, const Front& fp, int& tile0) {
+        AddTask a;
+        a.Coff = fc.F22off;
+        a.rel_off = fc.rel_off;
+        a.Loff = fp.Loff;
+        a.UToff = fp.UToff;
+        a.F22off = fp.F22off;
+        a.rc = fc.r;
+        a.sp = fp.s;
+        a.mp = fp.m;
+        a.tile0 = tile0;
+        a.tiles_m = (fc.r + opt.add_tile - 1) / opt.add_tile;
+        a.ldp = fp.ld;
+        tile0 += a.tiles_m * a.tiles_m;
+        plan.add_tasks.push_back(a);
+    };
+    const int G = std::max(1, opt.outer);
+    const int W = G * nb;   // outer block width = distribution block of the top fronts
     for (int l = plan.nlevels - 1; l >= 0; l--) {
         LevelPlan& L = plan.levels[l];
         int maxs = 0;
@@ -820,21 +947,7 @@ int analyse(int n, const int* rowptr, const int* colind, const int* const coords
                 for (int c : plan.levels[l + 1].fronts) {
                     const Front& fc = plan.fronts[c];
                     if (fc.child_rank != pass || fc.r == 0 || !mine(fc.parent)) continue;
-                    const Front& fp = plan.fronts[fc.parent];
-                    AddTask a;
-                    a.Coff = fc.F22off;
-                    a.rel_off = fc.rel_off;
-                    a.Loff = fp.Loff;
-                    a.UToff = fp.UToff;
-                    a.F22off = fp.F22off;
-                    a.rc = fc.r;
-                    a.sp = fp.s;
-                    a.mp = fp.m;
-                    a.tile0 = tile0;
-                    a.tiles_m = (fc.r + opt.add_tile - 1) / opt.add_tile;
-                    a.ldp = fp.ld;
-                    tile0 += a.tiles_m * a.tiles_m;
-                    plan.add_tasks.push_back(a);
+                    push_add(fc, plan.fronts[fc.parent], tile0);
                 }
                 L.add_tiles[pass] = tile0;
             }
@@ -855,91 +968,26 @@ int analyse(int n, const int* rowptr, const int* colind, const int* const coords
             for (int t : L.mine) {
                 const Front& f = plan.fronts[t];
                 if (k0 >= f.s) continue;
-                int kb = std::min(nb, f.s - k0);
-                int k1 = k0 + kb;
-                int64_t Dblk = f.Loff + k0 + (int64_t)k0 * f.ld;
-                DiagTask d;
-                d.Doff = Dblk;
-                d.UTDoff = f.UToff + k0 + (int64_t)k0 * f.ld;
-                d.ld = f.ld;
-                d.kb = kb;
-                plan.diag_tasks.push_back(d);
-                int below = f.m - k1;
-                if (below > 0) {
-                    for (int which = 0; which < 2; which++) {
-                        TrsmTask tt;
-                        tt.Xoff = (which == 0 ? f.Loff : f.UToff) + k1 + (int64_t)k0 * f.ld;
-                        tt.Toff = Dblk;
-                        tt.ld = f.ld;
-                        tt.nrows = below;
-                        tt.kb = kb;
-                        tt.unit = which;
-                        tt.cta0 = cta0;
-                        tt.pad = 0;
-                        cta0 += (below + opt.trsm_rows - 1) / opt.trsm_rows;
-                        plan.trsm_tasks.push_back(tt);
-                    }
-                    // Two-level blocking: G inner panels (nb columns each) form an outer block.
-                    // After every inner panel only the rest of the outer block is updated
-                    // ("narrow", K = kb); after the last inner panel of the outer block everything
-                    // beyond it receives ONE update with K = width of the outer block ("wide").
-                    // The big trailing matrices are therefore read and written once per G panels.
-                    const int G = std::max(1, opt.outer);
-                    const int ko0 = (step / G) * G * nb;                 // first column of the outer block
-                    const int ke = std::min(f.s, ko0 + G * nb);          // one past its last column
-                    auto push_gemm = [&](int64_t A, int64_t B, int64_t C, int M, int N, int K, int lda, int ldb, int ldc,
-                                         int skip) {
-                        if (M <= 0 || N <= 0) return;
-                        GemmTask gt;
-                        gt.Aoff = A;
-                        gt.Boff = B;
-                        gt.Coff = C;
-                        gt.M = M;
-                        gt.N = N;
-                        gt.K = K;
-                        gt.lda = lda;
-                        gt.ldb = ldb;
-                        gt.ldc = ldc;
-                        gt.skip = skip;
-                        gt.tile0 = tile0;
-                        gt.tiles_m = (M + opt.tm - 1) / opt.tm;
-                        gt.pad = 0;
-                        tile0 += gt.tiles_m * ((N + opt.tn - 1) / opt.tn);
-                        plan.gemm_tasks.push_back(gt);
-                        // useful (algorithmic) entries of this update
-                        double area = 0;
-                        if (skip == 0) area = (double)M * N;
-                        else
-                            for (int c0 = 0; c0 < N; c0 += nb) {
-                                int w = std::min(nb, N - c0);
-                                int first_row = skip == 1 ? c0 : std::min(c0 + nb, N);
-                                area += (double)(M - first_row) * w;
-                            }
-                        plan.gemm_flops += 2.0 * K * area;
-                    };
+                const int k1 = k0 + std::min(nb, f.s - k0);
+                const int ko0 = (step / G) * W;                     // first column of the outer block
+                const int ke = std::min(f.s, ko0 + W);              // one past its last column
+                push_panel(f, k0, ke, cta0, tile0);
+                if (k1 == ke && f.m > k1) {
+                    // wide: the outer block [ko0, ke) is completely factored
                     const int64_t ld = f.ld;
-                    if (k1 < ke) {
-                        // narrow: block columns / rows [k1, ke) of the outer block, all rows below
-                        int64_t Lpan = f.Loff + k1 + (int64_t)k0 * ld;    // L[k1.., k0:k1]
-                        int64_t UTpan = f.UToff + k1 + (int64_t)k0 * ld;  // U^T[k1.., k0:k1]
-                        push_gemm(Lpan, UTpan, f.Loff + k1 + (int64_t)k1 * ld, below, ke - k1, kb, f.ld, f.ld, f.ld, 1);
-                        push_gemm(UTpan, Lpan, f.UToff + k1 + (int64_t)k1 * ld, below, ke - k1, kb, f.ld, f.ld, f.ld, 2);
-                    } else {
-                        // wide: k1 == ke, the outer block [ko0, ke) is completely factored
-                        const int K = ke - ko0;
-                        const int rest = f.m - ke;
-                        const int trail_s = f.s - ke;
-                        int64_t Lpan = f.Loff + ke + (int64_t)ko0 * ld;    // L[ke.., ko0:ke]
-                        int64_t UTpan = f.UToff + ke + (int64_t)ko0 * ld;  // U^T[ke.., ko0:ke]
-                        if (trail_s > 0) {
-                            push_gemm(Lpan, UTpan, f.Loff + ke + (int64_t)ke * ld, rest, trail_s, K, f.ld, f.ld, f.ld, 1);
-                            push_gemm(UTpan, Lpan, f.UToff + ke + (int64_t)ke * ld, rest, trail_s, K, f.ld, f.ld, f.ld, 2);
-                        }
-                        if (f.r > 0) {
-                            int64_t Lb = f.Loff + f.s + (int64_t)ko0 * ld;
-                            int64_t UTb = f.UToff + f.s + (int64_t)ko0 * ld;
-                            push_gemm(Lb, UTb, f.F22off, f.r, f.r, K, f.ld, f.ld, f.r, 0);
-                        }
+                    const int K = ke - ko0;
+                    const int rest = f.m - ke;
+                    const int trail_s = f.s - ke;
+                    int64_t Lpan = f.Loff + ke + (int64_t)ko0 * ld;    // L[ke.., ko0:ke]
+                    int64_t UTpan = f.UToff + ke + (int64_t)ko0 * ld;  // U^T[ke.., ko0:ke]
+                    if (trail_s > 0) {
+                        push_gemm(tile0, Lpan, UTpan, f.Loff + ke + (int64_t)ke * ld, rest, trail_s, K, f.ld, f.ld, f.ld, 1);
+                        push_gemm(tile0, UTpan, Lpan, f.UToff + ke + (int64_t)ke * ld, rest, trail_s, K, f.ld, f.ld, f.ld, 2);
+                    }
+                    if (f.r > 0) {
+                        int64_t Lb = f.Loff + f.s + (int64_t)ko0 * ld;
+                        int64_t UTb = f.UToff + f.s + (int64_t)ko0 * ld;
+                        push_gemm(tile0, Lb, UTb, f.F22off, f.r, f.r, K, f.ld, f.ld, f.r, 0);
                     }
                 }
             }
@@ -949,13 +997,121 @@ int analyse(int n, const int* rowptr, const int* colind, const int* const coords
         L.diag_begin[L.nsteps] = (int)plan.diag_tasks.size();
         L.trsm_begin[L.nsteps] = (int)plan.trsm_tasks.size();
         L.gemm_begin[L.nsteps] = (int)plan.gemm_tasks.size();
+
+        // ---- the top fronts of this level (identical list on every rank; tasks only where this rank takes part)
+        for (int t : L.fronts) {
+            if (!plan.is_top[t]) continue;
+            const Front& f = plan.fronts[t];
+            const std::vector<int>& grp = plan.groups[plan.group_of[t]];
+            const int g = (int)grp.size();
+            TopFront tf;
+            tf.front = t;
+            tf.group = plan.group_of[t];
+            tf.member = stores(t) ? 1 : 0;
+            const int nK = (f.s + W - 1) / W;
+            auto f22_owner = [&](const Front& ff, const std::vector<int>& gg, int jc) {
+                return gg[(((ff.s + W - 1) / W) + jc) % (int)gg.size()];
+            };
+            // update matrices of the children -> every member (complete copies; the extend-add is done by all)
+            tf.cb_begin = (int)plan.top_child_bcasts.size();
+            for (int c : nodes[t].children) {
+                const Front& fc = plan.fronts[c];
+                if (fc.r == 0) continue;
+                if (!plan.is_top[c]) {
+                    plan.top_child_bcasts.push_back(TopBcast{plan.owner[c], 0, tf.member ? fc.F22off : -1, (int64_t)fc.r * fc.r});
+                } else {
+                    const std::vector<int>& gc = plan.groups[plan.group_of[c]];
+                    for (int jc = 0; jc * W < fc.r; jc++) {
+                        const int w = std::min(W, fc.r - jc * W);
+                        plan.top_child_bcasts.push_back(TopBcast{f22_owner(fc, gc, jc), 0,
+                                                                 tf.member ? fc.F22off + (int64_t)jc * W * fc.r : -1,
+                                                                 (int64_t)w * fc.r});
+                    }
+                }
+            }
+            tf.cb_end = (int)plan.top_child_bcasts.size();
+            tf.block_begin = (int)plan.top_blocks.size();
+            if (tf.member) {
+                tf.f22_off = f.F22off;
+                tf.f22_len = (int64_t)f.r * f.r;
+                for (int c : nodes[t].children) {   // one pass per child: no two tasks of a launch touch the same entries
+                    const Front& fc = plan.fronts[c];
+                    tf.add_begin.push_back((int)plan.add_tasks.size());
+                    int tile0 = 0;
+                    if (fc.r > 0) push_add(fc, f, tile0);
+                    tf.add_tiles.push_back(tile0);
+                }
+                tf.add_begin.push_back((int)plan.add_tasks.size());
+            }
+            for (int K = 0; K < nK; K++) {
+                TopBlock tb;
+                const int K0 = K * W, ke = std::min(f.s, K0 + W);
+                tb.owner = grp[K % g];
+                tb.step_begin = tb.step_end = (int)plan.top_steps.size();
+                tb.next_begin = tb.next_end = tb.rest_begin = tb.rest_end = (int)plan.gemm_tasks.size();
+                if (tf.member) {
+                    const int64_t ld = f.ld;
+                    // the factored column blocks, as flat ranges from (K0, K0) to (m - 1, ke - 1)
+                    const int64_t cnt = (int64_t)(ke - 1 - K0) * ld + (f.m - K0);
+                    tb.bl = TopBcast{tb.owner, 0, f.Loff + K0 + (int64_t)K0 * ld, cnt};
+                    tb.bu = TopBcast{tb.owner, 0, f.UToff + K0 + (int64_t)K0 * ld, cnt};
+                    if (tb.owner == plan.rank) {
+                        for (int k0 = K0; k0 < ke; k0 += nb) {
+                            TopStep ts;
+                            ts.diag_begin = (int)plan.diag_tasks.size();
+                            ts.trsm_begin = (int)plan.trsm_tasks.size();
+                            ts.gemm_begin = (int)plan.gemm_tasks.size();
+                            int cta0 = 0, tile0 = 0;
+                            push_panel(f, k0, ke, cta0, tile0);
+                            ts.diag_end = (int)plan.diag_tasks.size();
+                            ts.trsm_end = (int)plan.trsm_tasks.size();
+                            ts.gemm_end = (int)plan.gemm_tasks.size();
+                            ts.trsm_ctas = cta0;
+                            ts.gemm_tiles = tile0;
+                            plan.top_steps.push_back(ts);
+                        }
+                        tb.step_end = (int)plan.top_steps.size();
+                    }
+                    // wide update from block K: first the block that is factored next, then the rest of what this rank owns
+                    const int Kw = ke - K0;
+                    auto wide_pivot_block = [&](int J, int& tile0) {
+                        const int J0 = J * W, wJ = std::min(f.s, J0 + W) - J0;
+                        int64_t Lrow = f.Loff + J0 + (int64_t)K0 * ld;     // L[J0.., K0:ke]
+                        int64_t UTrow = f.UToff + J0 + (int64_t)K0 * ld;   // U^T[J0.., K0:ke]
+                        push_gemm(tile0, Lrow, UTrow, f.Loff + J0 + (int64_t)J0 * ld, f.m - J0, wJ, Kw, f.ld, f.ld, f.ld, 1);
+                        push_gemm(tile0, UTrow, Lrow, f.UToff + J0 + (int64_t)J0 * ld, f.m - J0, wJ, Kw, f.ld, f.ld, f.ld, 2);
+                    };
+                    tb.next_begin = (int)plan.gemm_tasks.size();
+                    int tile0 = 0;
+                    if (K + 1 < nK && grp[(K + 1) % g] == plan.rank) wide_pivot_block(K + 1, tile0);
+                    tb.next_end = (int)plan.gemm_tasks.size();
+                    tb.next_tiles = tile0;
+                    tb.rest_begin = (int)plan.gemm_tasks.size();
+                    tile0 = 0;
+                    for (int J = K + 2; J < nK; J++)
+                        if (grp[J % g] == plan.rank) wide_pivot_block(J, tile0);
+                    for (int jc = 0; jc * W < f.r; jc++) {
+                        if (f22_owner(f, grp, jc) != plan.rank) continue;
+                        const int jc0 = jc * W, wj = std::min(W, f.r - jc0);
+                        push_gemm(tile0, f.Loff + f.s + (int64_t)K0 * ld, f.UToff + f.s + jc0 + (int64_t)K0 * ld,
+                                  f.F22off + (int64_t)jc0 * f.r, f.r, wj, Kw, f.ld, f.ld, f.r, 0);
+                    }
+                    tb.rest_end = (int)plan.gemm_tasks.size();
+                    tb.rest_tiles = tile0;
+                }
+                plan.top_blocks.push_back(tb);
+            }
+            tf.block_end = (int)plan.top_blocks.size();
+            L.tops.push_back((int)plan.top_fronts.size());
+            plan.top_fronts.push_back(tf);
+        }
     }
 
     // solve tasks grouped by level, deepest first
     for (int l = plan.nlevels - 1; l >= 0; l--) {
         LevelPlan& L = plan.levels[l];
         L.solve_begin = (int)plan.solve_tasks.size();
-        for (int t : L.mine) {
+        for (int t : L.stored) {
             const Front& f = plan.fronts[t];
             SolveTask st;
             st.Loff = f.Loff;

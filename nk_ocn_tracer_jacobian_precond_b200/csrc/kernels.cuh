@@ -1369,6 +1369,22 @@ __global__ void k_sumsq_final(int nblocks, int nrhs, const double* __restrict__ 
     out[c] = acc;
 }
 
+// multi-GPU: parts of the solution y (n x nr, column-major) <-> contiguous per-range blocks of `pack`
+// (range [lo, hi) occupies pack[lo * nr, hi * nr), column c at offset c * (hi - lo)), so that every range
+// travels as ONE broadcast.  dir 0 packs the ranges this rank publishes, dir 1 unpacks the others.
+__global__ void __launch_bounds__(256) k_pub_pack(const PubRange* __restrict__ ranges, int me, int dir, double* __restrict__ y,
+                                                  int n, int nr, double* __restrict__ pack) {
+    const PubRange pr = ranges[blockIdx.y];
+    if ((dir == 0) != (pr.root == me)) return;
+    const int len = pr.hi - pr.lo;
+    double* pk = pack + (int64_t)pr.lo * nr;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < len; i += gridDim.x * blockDim.x)
+        for (int c = 0; c < nr; c++) {
+            if (dir == 0) pk[(int64_t)c * len + i] = y[pr.lo + i + (int64_t)c * n];
+            else y[pr.lo + i + (int64_t)c * n] = pk[(int64_t)c * len + i];
+        }
+}
+
 // max |a| over the stored values (tiny-pivot threshold of an unequilibrated factorisation)
 __global__ void __launch_bounds__(256) k_absmax(int64_t nnz, const double* __restrict__ val, double* __restrict__ out) {
     double m = 0.0;

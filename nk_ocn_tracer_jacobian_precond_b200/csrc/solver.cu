@@ -10,6 +10,7 @@
 #include <cuda_runtime.h>
 #include <nccl.h>
 
+#include <algorithm>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -47,6 +48,8 @@ struct NcclApi {
     ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
     ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*CommSplit)(ncclComm_t, int, int, ncclComm_t*, ncclConfig_t*) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*GroupStart)() = nullptr;
     ncclResult_t (*GroupEnd)() = nullptr;
     ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
@@ -66,6 +69,8 @@ bool nccl_load() {
     NKP_SYM(GetUniqueId, "ncclGetUniqueId")
     NKP_SYM(CommInitRank, "ncclCommInitRank")
     NKP_SYM(CommDestroy, "ncclCommDestroy")
+    NKP_SYM(CommSplit, "ncclCommSplit")
+    NKP_SYM(AllGather, "ncclAllGather")
     NKP_SYM(GroupStart, "ncclGroupStart")
     NKP_SYM(GroupEnd, "ncclGroupEnd")
     NKP_SYM(Send, "ncclSend")
@@ -80,6 +85,8 @@ bool nccl_load() {
 #define ncclGetUniqueId g_nccl.GetUniqueId
 #define ncclCommInitRank g_nccl.CommInitRank
 #define ncclCommDestroy g_nccl.CommDestroy
+#define ncclCommSplit g_nccl.CommSplit
+#define ncclAllGather g_nccl.AllGather
 #define ncclGroupStart g_nccl.GroupStart
 #define ncclGroupEnd g_nccl.GroupEnd
 #define ncclSend g_nccl.Send
@@ -168,6 +175,11 @@ struct nkp_solver {
     int coop_ctas = 0;          // co-resident CTAs for the dataflow sweeps
     ncclComm_t comm = nullptr;  // multi-GPU only
     int rank = 0, nranks = 1;
+    std::vector<ncclComm_t> gcomm;   // per Plan::groups entry: communicator of the group (null: this rank is not in it, or size 1)
+    cudaStream_t cstream = nullptr;  // high-priority stream of the panel / update-matrix broadcasts (top fronts)
+    cudaEvent_t ev_p = nullptr, ev_b = nullptr;   // main -> comm ("data ready"), comm -> main ("broadcast done")
+    PubRange* d_pub = nullptr;       // Plan::pub
+    double* d_pack = nullptr;        // n x MAX_NR staging of the published solution ranges
     double* d_W = nullptr;      // solve work vectors, MAX_NR columns
     double* d_y = nullptr;      // n x MAX_NR permuted rhs / solution
     double* d_r = nullptr;      // n x MAX_NR residual
@@ -336,6 +348,27 @@ static int create_impl(nkp_solver** out, int n, const int* rowptr, const int* co
             static_assert(sizeof(ncclUniqueId) <= NKP_UNIQUE_ID_BYTES, "unique id size");
             memcpy(&id, unique_id, sizeof(id));
             CKN(ncclCommInitRank(&s->comm, nranks, id, rank));
+            // one communicator per group of a top front (every rank takes part in every split)
+            s->gcomm.assign(P.groups.size(), nullptr);
+            for (size_t q = 0; q < P.groups.size(); q++) {
+                const std::vector<int>& grp = P.groups[q];
+                const bool member = std::binary_search(grp.begin(), grp.end(), rank);
+                if ((int)grp.size() == nranks) {
+                    s->gcomm[q] = s->comm;
+                    continue;
+                }
+                if (grp.size() < 2) continue;
+                ncclComm_t sub = nullptr;
+                CKN(ncclCommSplit(s->comm, member ? 0 : NCCL_SPLIT_NOCOLOR, rank, &sub, nullptr));
+                s->gcomm[q] = member ? sub : nullptr;
+            }
+            int least = 0, greatest = 0;
+            CK(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+            CK(cudaStreamCreateWithPriority(&s->cstream, cudaStreamNonBlocking, greatest));
+            CK(cudaEventCreateWithFlags(&s->ev_p, cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&s->ev_b, cudaEventDisableTiming));
+            if (upload(&s->d_pub, P.pub)) return NKP_ECUDA;
+            CK(cudaMalloc((void**)&s->d_pack, sizeof(double) * (size_t)n * MAX_NR));
         }
         CK(cudaMalloc((void**)&s->heap, sizeof(double) * (size_t)std::max<int64_t>(P.heap_len, 1)));
         std::vector<int> rp(rowptr, rowptr + n + 1), cidx(colind, colind + s->nnz), ridx((size_t)s->nnz);
@@ -434,24 +467,98 @@ int nkp_comm_unique_id(void* unique_id) {
     return NKP_OK;
 }
 
-// update matrices of the children on level `child_level` that live on another GPU than their parent
-static int exchange_updates(nkp_solver* s, int child_level) {
+
+// One top front of the shared part of the tree, factored by its group (nkp_internal.hpp, TopFront): update
+// matrices of the children to every member, extend-add by every member into its own full copy, then per outer
+// block: panel factorisation by the owner, broadcast of the two factored column blocks, wide Schur update of the
+// blocks each member owns -- the block that is factored next first, so that its panel and its broadcast overlap
+// everybody's remaining update.  All NCCL calls go to the high-priority communication stream; events carry the
+// dependencies between it and the compute stream.
+static int factor_top_front(nkp_solver* s, const TopFront& tf, double tiny) {
+    if (!tf.member) return 0;
     Plan& P = s->plan;
-    if (s->nranks == 1 || child_level >= P.nlevels) return 0;
-    const LevelPlan& L = P.levels[child_level];
-    bool any = false;
-    for (int q : L.xfers) any = any || P.xfers[q].src == s->rank || P.xfers[q].dst == s->rank;
-    if (!any) return 0;
-    CKN(ncclGroupStart());
-    for (int q : L.xfers) {
-        const Xfer& x = P.xfers[q];
-        const Front& f = P.fronts[x.front];
-        size_t cnt = (size_t)f.r * f.r;
-        if (cnt == 0) continue;
-        if (x.src == s->rank) CKN(ncclSend(s->heap + f.F22off, cnt, ncclDouble, x.dst, s->comm, s->stream));
-        if (x.dst == s->rank) CKN(ncclRecv(s->heap + f.F22off, cnt, ncclDouble, x.src, s->comm, s->stream));
+    cudaStream_t st = s->stream, cs = s->cstream;
+    const int nb = P.opt.nb;
+    const std::vector<int>& grp = P.groups[tf.group];
+    const int g = (int)grp.size();
+    ncclComm_t gc = s->gcomm[tf.group];
+    auto bcast = [&](const TopBcast& b) -> int {
+        const int root = (int)(std::lower_bound(grp.begin(), grp.end(), b.root) - grp.begin());
+        CKN(ncclBroadcast(s->heap + b.off, s->heap + b.off, (size_t)b.count, ncclDouble, root, gc, cs));
+        return 0;
+    };
+    if (g > 1 && tf.cb_end > tf.cb_begin) {
+        CK(cudaEventRecord(s->ev_p, st));
+        CK(cudaStreamWaitEvent(cs, s->ev_p, 0));
+        CKN(ncclGroupStart());
+        for (int q = tf.cb_begin; q < tf.cb_end; q++)
+            if (bcast(P.top_child_bcasts[q])) return NKP_ECUDA;
+        CKN(ncclGroupEnd());
+        CK(cudaEventRecord(s->ev_b, cs));
+        CK(cudaStreamWaitEvent(st, s->ev_b, 0));
+        prof_mark(s, KC_OTHER);
     }
-    CKN(ncclGroupEnd());
+    for (size_t pass = 0; pass + 1 < tf.add_begin.size(); pass++) {
+        const int nt = tf.add_begin[pass + 1] - tf.add_begin[pass];
+        if (nt == 0 || tf.add_tiles[pass] == 0) continue;
+        k_extend_add<<<tf.add_tiles[pass], 256, 0, st>>>(s->d_add + tf.add_begin[pass], nt, s->d_rel, s->heap, nb);
+        s->launches++;
+        prof_mark(s, KC_ADD);
+    }
+    auto panel = [&](const TopBlock& tb) {
+        for (int q = tb.step_begin; q < tb.step_end; q++) {
+            const TopStep& ts = P.top_steps[q];
+            if (ts.diag_end > ts.diag_begin) {
+                k_diag<<<ts.diag_end - ts.diag_begin, 256, 0, st>>>(s->d_diag + ts.diag_begin, s->heap, tiny, s->d_nrepl);
+                s->launches++;
+                prof_mark(s, KC_DIAG);
+            }
+            if (ts.trsm_ctas > 0) {
+                k_trsm<<<ts.trsm_ctas, TRSM_THREADS, TRSM_SMEM, st>>>(s->d_trsm + ts.trsm_begin, ts.trsm_end - ts.trsm_begin, s->heap);
+                s->launches++;
+                prof_mark(s, KC_TRSM);
+            }
+            if (ts.gemm_tiles > 0) {
+                k_gemm<<<ts.gemm_tiles, 256, G_SMEM, st>>>(s->d_gemm + ts.gemm_begin, ts.gemm_end - ts.gemm_begin, s->heap, nb);
+                s->launches++;
+                prof_mark(s, KC_GEMM);
+            }
+        }
+    };
+    const int nK = tf.block_end - tf.block_begin;
+    for (int K = 0; K < nK; K++) {
+        const TopBlock& tb = P.top_blocks[tf.block_begin + K];
+        const bool own = tb.owner == s->rank;
+        if (K == 0 && own) {
+            panel(tb);
+            if (g > 1) CK(cudaEventRecord(s->ev_p, st));
+        }
+        if (g > 1) {
+            if (own) CK(cudaStreamWaitEvent(cs, s->ev_p, 0));
+            CKN(ncclGroupStart());
+            if (bcast(tb.bl) || bcast(tb.bu)) return NKP_ECUDA;
+            CKN(ncclGroupEnd());
+            CK(cudaEventRecord(s->ev_b, cs));
+            if (!own) CK(cudaStreamWaitEvent(st, s->ev_b, 0));   // the owner already has what it sends
+        }
+        if (tb.next_tiles > 0) {
+            k_gemm<<<tb.next_tiles, 256, G_SMEM, st>>>(s->d_gemm + tb.next_begin, tb.next_end - tb.next_begin, s->heap, nb);
+            s->launches++;
+            prof_mark(s, KC_GEMM);
+        }
+        if (K + 1 < nK && P.top_blocks[tf.block_begin + K + 1].owner == s->rank) {
+            panel(P.top_blocks[tf.block_begin + K + 1]);
+            if (g > 1) CK(cudaEventRecord(s->ev_p, st));
+        }
+        if (tb.rest_tiles > 0) {
+            k_gemm<<<tb.rest_tiles, 256, G_SMEM, st>>>(s->d_gemm + tb.rest_begin, tb.rest_end - tb.rest_begin, s->heap, nb);
+            s->launches++;
+            prof_mark(s, KC_GEMM);
+        }
+    }
+    // every broadcast of this front (our own sends included) is complete before anything changes the panels again
+    // (k_invert_diag) or reuses the children's update matrices
+    if (g > 1) CK(cudaStreamWaitEvent(st, s->ev_b, 0));
     return 0;
 }
 
@@ -491,7 +598,6 @@ static int do_factor(nkp_solver* s) {
             CK(cudaMemsetAsync(s->heap + L.f22_zero_off, 0, sizeof(double) * (size_t)L.f22_zero_len, st));
             prof_mark(s, KC_OTHER);
         }
-        if (exchange_updates(s, l + 1)) return NKP_ECUDA;
         int npass = (int)L.add_tiles.size();
         for (int pass = 0; pass < npass; pass++) {
             int nt = L.add_begin[pass + 1] - L.add_begin[pass];
@@ -520,6 +626,9 @@ static int do_factor(nkp_solver* s) {
                 prof_mark(s, KC_GEMM);
             }
         }
+        // the top fronts of this level: factored together with the other members of their groups
+        for (int ti : L.tops)
+            if (int rc = factor_top_front(s, P.top_fronts[ti], tiny)) return rc;
         // the sweeps use inverted 64 x 64 diagonal blocks; nothing above this level reads them.  (Running
         // this on a second stream next to the upper levels was measured slower: its small CTAs displace
         // Schur-update CTAs.)
@@ -731,33 +840,23 @@ static int sweeps(nkp_solver* s) {
             s->launches++;
             mark("bwd big", l, nitems);
         }
-        if (s->nranks > 1 && !L.tops.empty()) {
-            // separator solutions of the shared top of the tree go to every GPU
-            CKN(ncclGroupStart());
-            for (int t : L.tops) {
-                const Front& f = P.fronts[t];
-                for (int c = 0; c < NR; c++) {
-                    double* p = s->d_y + f.first + (size_t)c * n;
-                    CKN(ncclBroadcast(p, p, (size_t)f.s, ncclDouble, P.owner[t], s->comm, st));
-                }
-            }
-            CKN(ncclGroupEnd());
-            mark("bwd bcast", l, (int)L.tops.size());
-        }
     }
-    if (s->nranks > 1) {
-        // every rank-private subtree range is published by its owner: all ranks hold the full solution
+    if (s->nranks > 1 && !P.pub.empty()) {
+        // The top fronts were swept by every member of their groups: no communication so far.  Now every part of
+        // the solution is published by one rank that holds it (rank-private subtree ranges by their owner, top
+        // fronts by the first member of their group): packed per range, ONE broadcast per range, one group call.
+        const int nrg = (int)P.pub.size();
+        k_pub_pack<<<dim3(64, nrg), 256, 0, st>>>(s->d_pub, s->rank, 0, s->d_y, n, NR, s->d_pack);
         CKN(ncclGroupStart());
-        for (size_t q = 0; q < P.subtree_roots.size(); q++) {
-            int t = P.subtree_roots[q];
-            int lo = P.subtree_lo[q], hi = P.fronts[t].first + P.fronts[t].s;
-            for (int c = 0; c < NR; c++) {
-                double* p = s->d_y + lo + (size_t)c * n;
-                CKN(ncclBroadcast(p, p, (size_t)(hi - lo), ncclDouble, P.owner[t], s->comm, st));
-            }
+        for (const PubRange& pr : P.pub) {
+            if (pr.hi <= pr.lo) continue;
+            double* p = s->d_pack + (size_t)pr.lo * NR;
+            CKN(ncclBroadcast(p, p, (size_t)(pr.hi - pr.lo) * NR, ncclDouble, pr.root, s->comm, st));
         }
         CKN(ncclGroupEnd());
-        mark("subtree bcast", -1, (int)P.subtree_roots.size());
+        k_pub_pack<<<dim3(64, nrg), 256, 0, st>>>(s->d_pub, s->rank, 1, s->d_y, n, NR, s->d_pack);
+        s->launches += 2;
+        mark("publish", -1, nrg);
     }
     CK(cudaGetLastError());
     if (trace) {
@@ -1147,7 +1246,15 @@ void nkp_destroy(nkp_solver* s) {
     if (!s) return;
     cudaSetDevice(s->opt.device);
     if (s->stream) cudaStreamSynchronize(s->stream);
+    if (s->cstream) cudaStreamSynchronize(s->cstream);
+    for (ncclComm_t c : s->gcomm)
+        if (c && c != s->comm) ncclCommDestroy(c);
     if (s->comm) ncclCommDestroy(s->comm);
+    if (s->cstream) cudaStreamDestroy(s->cstream);
+    if (s->ev_p) cudaEventDestroy(s->ev_p);
+    if (s->ev_b) cudaEventDestroy(s->ev_b);
+    if (s->d_pub) cudaFree(s->d_pub);
+    if (s->d_pack) cudaFree(s->d_pack);
     void* ptrs[] = {s->heap,   s->d_rowptr, s->d_colind, s->d_rowidx, s->d_val,  s->d_scatter, s->d_perm,
                     s->d_bidx, s->d_rel,    s->d_R,      s->d_C,      s->d_diag, s->d_trsm,    s->d_gemm,
                     s->d_add,  s->d_solve,  s->d_children, s->d_W,    s->d_y,    s->d_r,       s->d_x,

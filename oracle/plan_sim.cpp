@@ -10,6 +10,7 @@
 // SuperLU_DIST's pdgstrf for the reference (src/SuperLU_brief_tree.txt:11-15), followed
 // by the forward/backward sweeps of pdgstrs (src/SuperLU_brief_tree.txt:17-18).
 // Parity of this interpreter is pinned against scipy's SuperLU in tests/.
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -218,15 +219,6 @@ int nkp_sim_run_dist(int n, const int* rowptr, const int* colind, const double* 
             const LevelPlan& L = plans[r].levels[l];
             memset(heaps[r].data() + L.f22_zero_off, 0, sizeof(double) * (size_t)L.f22_zero_len);
         }
-        // update matrices of children (level l+1) owned elsewhere: src -> dst
-        if (l + 1 < P0.nlevels)
-            for (int q : P0.levels[l + 1].xfers) {
-                const Xfer& x = P0.xfers[q];
-                const Front& fs = plans[x.src].fronts[x.front];
-                const Front& fd = plans[x.dst].fronts[x.front];
-                if (fs.F22off < 0 || fd.F22off < 0) return -22;
-                memcpy(heaps[x.dst].data() + fd.F22off, heaps[x.src].data() + fs.F22off, sizeof(double) * (size_t)fs.r * fs.r);
-            }
         for (int r = 0; r < nranks; r++) {
             Plan& P = plans[r];
             double* H = heaps[r].data();
@@ -241,6 +233,60 @@ int nkp_sim_run_dist(int n, const int* rowptr, const int* colind, const double* 
                 for (int q = L.diag_begin[step]; q < L.diag_begin[step + 1]; q++) sim_diag(H, P.diag_tasks[q], tiny, &nrepl);
                 for (int q = L.trsm_begin[step]; q < L.trsm_begin[step + 1]; q++) sim_trsm(H, P.trsm_tasks[q]);
                 for (int q = L.gemm_begin[step]; q < L.gemm_begin[step + 1]; q++) sim_gemm(H, P.gemm_tasks[q], P.opt);
+            }
+        }
+        // the top fronts of this level, in postorder: factored by their groups (nkp_internal.hpp, TopFront).
+        // A broadcast is a memcpy from the root's heap into every other member's heap.
+        for (int ti : P0.levels[l].tops) {
+            const std::vector<int>& grp = P0.groups[P0.top_fronts[ti].group];
+            auto bcast = [&](int which /* 0 child, 1 bl, 2 bu */, int idx) -> int {
+                auto get = [&](int r) -> const TopBcast& {
+                    return which == 0 ? plans[r].top_child_bcasts[idx] : (which == 1 ? plans[r].top_blocks[idx].bl : plans[r].top_blocks[idx].bu);
+                };
+                const int root = get(grp[0]).root;
+                if (!std::binary_search(grp.begin(), grp.end(), root)) return -24;
+                for (int r : grp) {
+                    if (r == root) continue;
+                    if (get(r).root != root || get(r).count != get(root).count || get(r).off < 0 || get(root).off < 0) return -25;
+                    memcpy(heaps[r].data() + get(r).off, heaps[root].data() + get(root).off, sizeof(double) * (size_t)get(root).count);
+                }
+                return 0;
+            };
+            const TopFront& tf0 = plans[grp[0]].top_fronts[ti];
+            for (int q = tf0.cb_begin; q < tf0.cb_end; q++)
+                if (int rc = bcast(0, q)) return rc;
+            for (int r : grp) {
+                Plan& P = plans[r];
+                const TopFront& tf = P.top_fronts[ti];
+                if (!tf.member) return -26;
+                for (size_t pass = 0; pass + 1 < tf.add_begin.size(); pass++)
+                    for (int q = tf.add_begin[pass]; q < tf.add_begin[pass + 1]; q++) sim_add(heaps[r].data(), P.add_tasks[q], P.rel.data(), nb);
+            }
+            auto panel = [&](int r, const TopBlock& tb) {
+                Plan& P = plans[r];
+                double* H = heaps[r].data();
+                for (int st = tb.step_begin; st < tb.step_end; st++) {
+                    const TopStep& ts = P.top_steps[st];
+                    for (int q = ts.diag_begin; q < ts.diag_end; q++) sim_diag(H, P.diag_tasks[q], tiny, &nrepl);
+                    for (int q = ts.trsm_begin; q < ts.trsm_end; q++) sim_trsm(H, P.trsm_tasks[q]);
+                    for (int q = ts.gemm_begin; q < ts.gemm_end; q++) sim_gemm(H, P.gemm_tasks[q], P.opt);
+                }
+            };
+            const int nK = tf0.block_end - tf0.block_begin;
+            for (int K = 0; K < nK; K++) {
+                const int bi = tf0.block_begin + K;
+                const int owner = plans[grp[0]].top_blocks[bi].owner;
+                if (K == 0) panel(owner, plans[owner].top_blocks[bi]);
+                if (int rc = bcast(1, bi)) return rc;
+                if (int rc = bcast(2, bi)) return rc;
+                for (int r : grp) {
+                    Plan& P = plans[r];
+                    const TopBlock& tb = P.top_blocks[bi];
+                    if (tb.owner != owner) return -27;
+                    for (int q = tb.next_begin; q < tb.next_end; q++) sim_gemm(heaps[r].data(), P.gemm_tasks[q], P.opt);
+                    if (K + 1 < nK && P.top_blocks[bi + 1].owner == r) panel(r, P.top_blocks[bi + 1]);
+                    for (int q = tb.rest_begin; q < tb.rest_end; q++) sim_gemm(heaps[r].data(), P.gemm_tasks[q], P.opt);
+                }
             }
         }
     }
@@ -379,22 +425,11 @@ int nkp_sim_run_dist(int n, const int* rowptr, const int* colind, const double* 
                     }
                 }
             }
-            // the owner of every top front of this level broadcasts its solution
-            for (int t : P0.levels[l].tops) {
-                int o = P0.owner[t];
-                const Front& f = P0.fronts[t];
-                for (int r = 0; r < nranks; r++)
-                    if (r != o) memcpy(ys[r].data() + f.first, ys[o].data() + f.first, sizeof(double) * (size_t)f.s);
-            }
         }
-        // finally every rank-private subtree range is broadcast by its owner
-        for (size_t q = 0; q < P0.subtree_roots.size(); q++) {
-            int t = P0.subtree_roots[q];
-            int o = P0.owner[t];
-            int lo = P0.subtree_lo[q], hi = P0.fronts[t].first + P0.fronts[t].s;
+        // every part of the solution is published by one rank that holds it (Plan::pub)
+        for (const PubRange& pr : P0.pub)
             for (int r = 0; r < nranks; r++)
-                if (r != o) memcpy(ys[r].data() + lo, ys[o].data() + lo, sizeof(double) * (size_t)(hi - lo));
-        }
+                if (r != pr.root) memcpy(ys[r].data() + pr.lo, ys[pr.root].data() + pr.lo, sizeof(double) * (size_t)(pr.hi - pr.lo));
         for (int i = 0; i < n; i++) {
             xacc[i] += ys[0][P0.perm[i]];
             X[i + (int64_t)c * n] = xacc[i];
@@ -414,6 +449,7 @@ int nkp_sim_partition(int n, const int* rowptr, const int* colind, const int* ci
     if (opt.tn > nb) opt.tn = nb;
     opt.rank = rank;
     opt.nranks = nranks;
+    if (getenv("NKP_OUTER")) opt.outer = atoi(getenv("NKP_OUTER"));
     const int* coords[3] = {ci, cj, ck};
     Plan P;
     int rc = analyse(n, rowptr, colind, (ci || cj || ck) ? coords : nullptr, opt, P);
@@ -432,6 +468,15 @@ int nkp_sim_partition(int n, const int* rowptr, const int* colind, const int* ci
         local_out[1] = P.flops;
         local_out[2] = (double)P.heap_len;
         local_out[3] = (double)P.nnz_lu_local;
+        // distributed top of the tree: number of top fronts, largest number of outer blocks of one of them,
+        // number of distinct groups, largest group
+        int maxblk = 0, maxgrp = 0;
+        for (const TopFront& tf : P.top_fronts) maxblk = std::max(maxblk, tf.block_end - tf.block_begin);
+        for (const std::vector<int>& g : P.groups) maxgrp = std::max(maxgrp, (int)g.size());
+        local_out[4] = (double)P.top_fronts.size();
+        local_out[5] = maxblk;
+        local_out[6] = (double)P.groups.size();
+        local_out[7] = maxgrp;
     }
     return nf;
 }

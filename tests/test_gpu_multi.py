@@ -47,16 +47,20 @@ sys.exit(0 if ok else 1)
 '''
 
 
-@pytest.mark.parametrize("world", [2, 4])
-def test_multi_gpu_matches_single_gpu(tmp_path, world):
+@pytest.mark.parametrize("world,outer", [(2, 8), (2, 1), (4, 8), (4, 1), (8, 2)])
+def test_multi_gpu_matches_single_gpu(tmp_path, world, outer):
+    """outer (NKP_OUTER) sets the width of the distribution blocks of the top fronts (outer * 64 columns): with 1 or 2
+    the 40x46x24 grid gives every top front many blocks, so owner rotation, look-ahead panels, panel broadcasts and
+    the column-block broadcasts of distributed update matrices are all exercised."""
     import torch
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
     script = tmp_path / "worker.py"
     script.write_text(WORKER)
-    env = dict(os.environ, NKP_ROOT=ROOT)
+    env = dict(os.environ, NKP_ROOT=ROOT, NKP_OUTER=str(outer))
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
-                          "--master-addr", "127.0.0.1", "--master-port", str(29600 + world), str(script)],
+                          "--master-addr", "127.0.0.1", "--master-port", str(29600 + 10 * world + outer), str(script)],
                          capture_output=True, text=True, timeout=600, env=env)
+    print(out.stdout[-400:])
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert "MULTI" in out.stdout

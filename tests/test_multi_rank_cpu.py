@@ -21,8 +21,11 @@ def _dp(a):
     return a.ctypes.data_as(P(ctypes.c_double)) if a is not None else None
 
 
-@pytest.mark.parametrize("nranks", [2, 3, 4, 8])
-def test_lockstep_ranks_match_single_rank(sim_lib, nranks):
+@pytest.mark.parametrize("nranks,outer", [(2, 8), (3, 8), (4, 8), (8, 8), (2, 1), (4, 1), (8, 1), (8, 2)])
+def test_lockstep_ranks_match_single_rank(sim_lib, nranks, outer, monkeypatch):
+    """outer = 1 / 2 makes the distribution blocks of the top fronts 64 / 128 columns wide, so that the small test
+    grid exercises several owner rotations, look-ahead panels and update-matrix column blocks per top front."""
+    monkeypatch.setenv("NKP_OUTER", str(outer))
     c = synth_case(24, 28, 16, seed=2)
     n = c["n"]
     A = sp.csr_matrix((c["nzval"], c["colind"], c["rowptr"]), shape=(n, n))
@@ -48,6 +51,17 @@ def test_lockstep_ranks_match_single_rank(sim_lib, nranks):
     assert part[:, 1].sum() == part[:, 2].sum() > 0    # sends match receives
     assert abs(part[:, 3].sum() - st1[5]) <= 1e-6 * st1[5]   # flops partition the total
     assert part[:, 3].max() <= 0.85 * st1[5]           # and no rank does (nearly) everything
+    # shape of the distributed top of the tree, as rank 0 plans it
+    local = np.zeros(8)
+    owner = np.zeros(8192, dtype=np.int32)
+    xfer = np.zeros(3 * 8192, dtype=np.int32)
+    nx = ctypes.c_int()
+    nf = sim_lib.nkp_sim_partition(n, _ip(rp), _ip(ci), _ip(c["i"]), _ip(c["j"]), _ip(c["k"]), 64, 48, 0, nranks,
+                                   _ip(owner), 8192, _ip(xfer), 8192, ctypes.byref(nx), _dp(local))
+    assert nf > 0
+    assert local[4] >= 1 and local[7] == nranks                    # the root is a top front and its group is everyone
+    if outer == 1:
+        assert local[5] >= 3                                        # several distribution blocks per top front
 
 
 def _worker(rank, world, port, q):
@@ -60,7 +74,7 @@ def _worker(rank, world, port, q):
     owner = np.zeros(4096, dtype=np.int32)
     xfer = np.zeros(3 * 4096, dtype=np.int32)
     nx = ctypes.c_int()
-    local = np.zeros(4)
+    local = np.zeros(8)
     nf = lib.nkp_sim_partition(c["n"], _ip(c["rowptr"]), _ip(c["colind"]), _ip(c["i"]), _ip(c["j"]), _ip(c["k"]), 64, 48,
                                rank, world, _ip(owner), 4096, _ip(xfer), 4096, ctypes.byref(nx), _dp(local))
     mine = dict(nf=nf, owner=owner[:nf].tolist(), xfers=xfer[:3 * nx.value].reshape(-1, 3).tolist(),
