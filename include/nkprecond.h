@@ -143,6 +143,14 @@ int nkp_solve(nkp_solver* s, double* B, int ldb, int nrhs, double* berr);
 /* Same with B in device memory (berr stays a host pointer). */
 int nkp_solve_device(nkp_solver* s, double* d_B, int ldb, int nrhs, double* berr);
 
+/* Multi-GPU with a DISTRIBUTED right-hand side -- what pdgssvx does for solve_ABdist (src/solve_ABdist.c:141-144,
+ * :571): rank r passes rows [fst_row, fst_row + m_loc) of B (HOST memory, column-major m_loc x nrhs, leading
+ * dimension ldb >= m_loc) and receives the same rows of X in place; the slabs of all ranks must tile [0, n) (any
+ * sizes; the reference uses n / P with the remainder on the last rank).  Every rank moves only its slab across
+ * PCIe; the slabs are exchanged between the GPUs over NVLink (NCCL).  berr[nrhs] is the same on every rank.
+ * With one rank this is nkp_solve (fst_row = 0, m_loc = n). */
+int nkp_solve_dist(nkp_solver* s, double* B_loc, int ldb, int nrhs, int fst_row, int m_loc, double* berr);
+
 /* Tracer fields in, tracer fields out -- get_B_global + pdgssvx*(FACTORED) + put_B_global of the
  * reference in one call (src/solve_ABglobal.c:154-208, :395, :213-267).
  * nkp_set_tracer_maps registers the index maps of the matrix file (tracer_state_ind_to_{i,j,k},
@@ -177,6 +185,8 @@ int nkp_set_profile(nkp_solver* s, int on);
 int nkp_set_refine_rule(nkp_solver* s, int rule);
 /* Switch the extra-precise residual of an existing handle on or off (see nkp_options.residual_extra). */
 int nkp_set_residual_extra(nkp_solver* s, int on);
+/* Diagnostics on stderr: 0 silent, 1 phase summary, 2 timeline of the factorisation, 3 + per-launch sweep trace. */
+int nkp_set_verbose(nkp_solver* s, int level);
 /* Block until all device work of this handle has finished. */
 int nkp_sync(nkp_solver* s);
 void nkp_destroy(nkp_solver* s);

@@ -633,35 +633,70 @@ int analyse(int n, const int* rowptr, const int* colind, const int* const coords
         flsub[t] += fl[t];
         if (plan.fronts[t].parent >= 0) flsub[plan.fronts[t].parent] += flsub[t];
     }
+    // Proportional mapping onto a binary hierarchy of rank ranges ([0,P) -> halves -> ... -> single ranks).
+    // mapping(cands, [lo,hi)): the candidate subtrees handed to the range [lo,hi) are distributed over its two halves
+    // by longest-processing-time (a half of k ranks works k times as fast); while the halves are unbalanced beyond
+    // `split_tol`, the heaviest candidate is split: the split front becomes a TOP front factored jointly by all ranks
+    // of [lo,hi), its children are new candidates.  Then each half maps its candidates the same way; a range of one
+    // rank owns its candidates' whole subtrees.  Every group is a node of the hierarchy: at most P - 1 communicators,
+    // nested, and the imbalance is bounded at every level instead of compounding.
+    std::vector<int> top_lo(nf, 0), top_hi(nf, 0);
     {
-        std::vector<int> cand(roots.begin(), roots.end());
-        while ((int)cand.size() < P) {
-            int best = -1;
-            for (size_t q = 0; q < cand.size(); q++)
-                if (!nodes[cand[q]].children.empty() && (best < 0 || flsub[cand[q]] > flsub[cand[best]])) best = (int)q;
-            if (best < 0) break;
-            int t = cand[best];
-            plan.is_top[t] = 1;
-            cand.erase(cand.begin() + best);
-            for (int c : nodes[t].children) cand.push_back(c);
-        }
-        // longest-processing-time assignment of the subtrees to ranks
-        std::sort(cand.begin(), cand.end(), [&](int x, int y) { return flsub[x] > flsub[y] || (flsub[x] == flsub[y] && x < y); });
-        std::vector<double> load(P, 0.0);
         std::vector<int> cand_owner(nf, -1);
-        for (int t : cand) {
-            int r = (int)(std::min_element(load.begin(), load.end()) - load.begin());
-            cand_owner[t] = r;
-            load[r] += flsub[t];
+        struct Job {
+            std::vector<int> cands;
+            int lo, hi;
+        };
+        std::vector<Job> jobs;
+        jobs.push_back(Job{std::vector<int>(roots.begin(), roots.end()), 0, P});
+        while (!jobs.empty()) {
+            Job job = std::move(jobs.back());
+            jobs.pop_back();
+            std::vector<int>& cand = job.cands;
+            if (job.hi - job.lo == 1) {
+                for (int t : cand) cand_owner[t] = job.lo;
+                continue;
+            }
+            const int mid = job.lo + (job.hi - job.lo + 1) / 2;
+            const double sp[2] = {(double)(mid - job.lo), (double)(job.hi - mid)};
+            std::vector<int> bin[2];
+            for (;;) {
+                std::sort(cand.begin(), cand.end(), [&](int x, int y) { return flsub[x] > flsub[y] || (flsub[x] == flsub[y] && x < y); });
+                double load[2] = {0.0, 0.0};
+                bin[0].clear();
+                bin[1].clear();
+                for (int t : cand) {
+                    const int b = (load[0] + flsub[t]) / sp[0] <= (load[1] + flsub[t]) / sp[1] ? 0 : 1;
+                    bin[b].push_back(t);
+                    load[b] += flsub[t];
+                }
+                const double mean = (load[0] + load[1]) / (sp[0] + sp[1]);
+                const double imb = mean > 0 ? std::max(load[0] / sp[0], load[1] / sp[1]) / mean : 1.0;
+                if (!bin[0].empty() && !bin[1].empty() && (imb <= 1.0 + opt.split_tol || (int)cand.size() >= opt.split_max)) break;
+                int best = -1;
+                for (size_t q = 0; q < cand.size(); q++)
+                    if (!nodes[cand[q]].children.empty() && (best < 0 || flsub[cand[q]] > flsub[cand[best]])) best = (int)q;
+                if (best < 0) break;
+                const int t = cand[best];
+                plan.is_top[t] = 1;
+                top_lo[t] = job.lo;
+                top_hi[t] = job.hi;
+                cand.erase(cand.begin() + best);
+                for (int c : nodes[t].children) cand.push_back(c);
+            }
+            jobs.push_back(Job{bin[0], job.lo, mid});
+            jobs.push_back(Job{bin[1], mid, job.hi});
         }
-        plan.subtree_roots = cand;
-        std::sort(plan.subtree_roots.begin(), plan.subtree_roots.end());
         // owners: subtree members inherit top-down
         for (int t = nf - 1; t >= 0; t--) {
             if (plan.is_top[t]) continue;
             if (cand_owner[t] >= 0) plan.owner[t] = cand_owner[t];
             else plan.owner[t] = plan.owner[plan.fronts[t].parent];
         }
+        // the rank-private subtrees: maximal subtrees without a top front
+        plan.subtree_roots.clear();
+        for (int t = 0; t < nf; t++)
+            if (!plan.is_top[t] && (plan.fronts[t].parent < 0 || plan.is_top[plan.fronts[t].parent])) plan.subtree_roots.push_back(t);
         // first permuted index of every subtree (postorder => contiguous ranges)
         std::vector<int> lo(nf);
         for (int t = 0; t < nf; t++) {
@@ -671,29 +706,21 @@ int analyse(int n, const int* rowptr, const int* colind, const int* const coords
         plan.subtree_lo.clear();
         for (int t : plan.subtree_roots) plan.subtree_lo.push_back(lo[t]);
     }
-    // groups of the top fronts: the ranks that own something below them (children come first in postorder)
+    // groups of the top fronts: the rank range that factors them (children come first in postorder)
     plan.group_of.assign(nf, -1);
-    {
-        std::vector<std::vector<int>> grp(nf);
-        for (int t = 0; t < nf; t++) {
-            if (!plan.is_top[t]) continue;
-            std::vector<int>& g = grp[t];
-            for (int c : nodes[t].children) {
-                if (plan.is_top[c]) g.insert(g.end(), grp[c].begin(), grp[c].end());
-                else g.push_back(plan.owner[c]);
-            }
-            std::sort(g.begin(), g.end());
-            g.erase(std::unique(g.begin(), g.end()), g.end());
-            int gi = -1;
-            for (size_t q = 0; q < plan.groups.size(); q++)
-                if (plan.groups[q] == g) gi = (int)q;
-            if (gi < 0) {
-                gi = (int)plan.groups.size();
-                plan.groups.push_back(g);
-            }
-            plan.group_of[t] = gi;
-            plan.owner[t] = g[0];   // the member that publishes the front's part of the solution
+    for (int t = 0; t < nf; t++) {
+        if (!plan.is_top[t]) continue;
+        std::vector<int> g;
+        for (int r = top_lo[t]; r < top_hi[t]; r++) g.push_back(r);
+        int gi = -1;
+        for (size_t q = 0; q < plan.groups.size(); q++)
+            if (plan.groups[q] == g) gi = (int)q;
+        if (gi < 0) {
+            gi = (int)plan.groups.size();
+            plan.groups.push_back(g);
         }
+        plan.group_of[t] = gi;
+        plan.owner[t] = g[0];   // the member that publishes the front's part of the solution
     }
     auto in_group = [&](int t, int r) {
         const std::vector<int>& g = plan.groups[plan.group_of[t]];
@@ -1228,6 +1255,18 @@ int analyse(int n, const int* rowptr, const int* colind, const int* const coords
                 "heap=%.2f GB flops=%.3e  t(order,symb,plan)=%.2f,%.2f,%.2f s\n",
                 n, (long long)plan.nnz, nf, plan.nlevels, plan.max_front, (long long)plan.nnz_lu,
                 plan.nnz_lu * 8e-9, plan.heap_len * 8e-9, plan.flops, plan.t_order, plan.t_symbolic, plan.t_plan);
+    }
+    if (opt.verbose && plan.nranks > 1) {
+        std::vector<int> hist(plan.nranks + 1, 0);
+        for (const auto& g : plan.groups) hist[g.size()]++;
+        fprintf(stderr, "[nkp] partition: %d top fronts, %d groups (by size:", (int)plan.top_fronts.size(), (int)plan.groups.size());
+        for (int q = 1; q <= plan.nranks; q++)
+            if (hist[q]) fprintf(stderr, " %dx%d", hist[q], q);
+        double tops = 0;
+        for (int t = 0; t < nf; t++)
+            if (plan.is_top[t]) tops += fl[t];
+        fprintf(stderr, "), %.1f %% of the flops in top fronts, %d rank-private subtrees\n", 100.0 * tops / plan.flops,
+                (int)plan.subtree_roots.size());
     }
     if (opt.verbose >= 2) {
         // per level: fronts, big fronts, largest pivot count / front size, factor bytes (L + U^T panels)

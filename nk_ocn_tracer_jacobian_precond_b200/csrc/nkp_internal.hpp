@@ -223,6 +223,8 @@ struct Options {
     int64_t big_entries = 1 << 15;  // fronts with m*s >= this use the multi-CTA dataflow sweeps
     int big_rows = 768;             // ... and so do tall fronts (few pivots, long boundary): one warp would crawl
     int rank = 0, nranks = 1;       // multi-GPU: this process' rank (one GPU per rank)
+    double split_tol = 0.03;        // multi-GPU: accepted flop imbalance (max / mean - 1) of the two halves of a rank range
+    int split_max = 8;              // ... and the largest number of candidate subtrees the splitting may produce per range
 };
 
 struct Plan {

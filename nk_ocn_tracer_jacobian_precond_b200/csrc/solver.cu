@@ -178,6 +178,8 @@ struct nkp_solver {
     std::vector<ncclComm_t> gcomm;   // per Plan::groups entry: communicator of the group (null: this rank is not in it, or size 1)
     cudaStream_t cstream = nullptr;  // high-priority stream of the panel / update-matrix broadcasts (top fronts)
     cudaEvent_t ev_p = nullptr, ev_b = nullptr;   // main -> comm ("data ready"), comm -> main ("broadcast done")
+    PubRange* d_slab = nullptr;      // nkp_solve_dist: row slabs of all ranks (+ one slot for this rank's own)
+    std::vector<PubRange> h_slab;
     PubRange* d_pub = nullptr;       // Plan::pub
     double* d_pack = nullptr;        // n x MAX_NR staging of the published solution ranges
     double* d_W = nullptr;      // solve work vectors, MAX_NR columns
@@ -211,6 +213,8 @@ struct nkp_solver {
     double t_cls[5] = {0, 0, 0, 0, 0};
     int64_t n_cls[5] = {0, 0, 0, 0, 0};
     double t_sweeps = 0;
+    std::vector<cudaEvent_t> trace_ev;   // verbose >= 2: timeline of the last factorisation
+    std::vector<std::string> trace_name;
 };
 
 enum { KC_OTHER = 0, KC_ADD = 1, KC_DIAG = 2, KC_TRSM = 3, KC_GEMM = 4 };
@@ -315,6 +319,8 @@ static int create_impl(nkp_solver** out, int n, const int* rowptr, const int* co
     if (getenv("NKP_BIG_ENTRIES")) po.big_entries = atoll(getenv("NKP_BIG_ENTRIES"));
     if (getenv("NKP_BIG_ROWS")) po.big_rows = atoi(getenv("NKP_BIG_ROWS"));
     if (getenv("NKP_OUTER")) po.outer = std::max(1, atoi(getenv("NKP_OUTER")));
+    if (getenv("NKP_SPLIT_TOL")) po.split_tol = atof(getenv("NKP_SPLIT_TOL"));
+    if (getenv("NKP_SPLIT_MAX")) po.split_max = std::max(1, atoi(getenv("NKP_SPLIT_MAX")));
     const int* coords[3] = {ci, cj, ck};
     auto t0 = std::chrono::steady_clock::now();
     int rc = analyse(n, rowptr, colind, (ci || cj || ck) ? coords : nullptr, po, s->plan);
@@ -474,10 +480,23 @@ int nkp_comm_unique_id(void* unique_id) {
 // blocks each member owns -- the block that is factored next first, so that its panel and its broadcast overlap
 // everybody's remaining update.  All NCCL calls go to the high-priority communication stream; events carry the
 // dependencies between it and the compute stream.
+// verbose >= 2: timeline marks on the compute stream (name, event), printed after the factorisation
+static void trace_mark(nkp_solver* s, const char* what, int a, int b) {
+    if (s->opt.verbose < 2) return;
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return;
+    cudaEventRecord(e, s->stream);
+    char buf[96];
+    snprintf(buf, sizeof buf, "%s %d/%d", what, a, b);
+    s->trace_ev.push_back(e);
+    s->trace_name.push_back(buf);
+}
+
 static int factor_top_front(nkp_solver* s, const TopFront& tf, double tiny) {
     if (!tf.member) return 0;
     Plan& P = s->plan;
     cudaStream_t st = s->stream, cs = s->cstream;
+    trace_mark(s, "top front start", tf.front, P.fronts[tf.front].s);
     const int nb = P.opt.nb;
     const std::vector<int>& grp = P.groups[tf.group];
     const int g = (int)grp.size();
@@ -497,6 +516,7 @@ static int factor_top_front(nkp_solver* s, const TopFront& tf, double tiny) {
         CK(cudaEventRecord(s->ev_b, cs));
         CK(cudaStreamWaitEvent(st, s->ev_b, 0));
         prof_mark(s, KC_OTHER);
+        trace_mark(s, "  children bcast", tf.front, tf.cb_end - tf.cb_begin);
     }
     for (size_t pass = 0; pass + 1 < tf.add_begin.size(); pass++) {
         const int nt = tf.add_begin[pass + 1] - tf.add_begin[pass];
@@ -525,10 +545,12 @@ static int factor_top_front(nkp_solver* s, const TopFront& tf, double tiny) {
             }
         }
     };
+    trace_mark(s, "  extend-add", tf.front, 0);
     const int nK = tf.block_end - tf.block_begin;
     for (int K = 0; K < nK; K++) {
         const TopBlock& tb = P.top_blocks[tf.block_begin + K];
         const bool own = tb.owner == s->rank;
+        if (s->opt.verbose >= 3) trace_mark(s, "    block", K, nK);
         if (K == 0 && own) {
             panel(tb);
             if (g > 1) CK(cudaEventRecord(s->ev_p, st));
@@ -559,6 +581,7 @@ static int factor_top_front(nkp_solver* s, const TopFront& tf, double tiny) {
     // every broadcast of this front (our own sends included) is complete before anything changes the panels again
     // (k_invert_diag) or reuses the children's update matrices
     if (g > 1) CK(cudaStreamWaitEvent(st, s->ev_b, 0));
+    trace_mark(s, "  blocks", tf.front, nK);
     return 0;
 }
 
@@ -592,6 +615,10 @@ static int do_factor(nkp_solver* s) {
     prof_mark(s, KC_OTHER);
     // with equilibration every row/column max is in [1,2): threshold relative to ||A|| ~ 1
     double tiny = std::sqrt(2.220446049250313e-16) * (s->opt.equil ? 1.0 : s->amax);
+    for (cudaEvent_t e : s->trace_ev) cudaEventDestroy(e);
+    s->trace_ev.clear();
+    s->trace_name.clear();
+    trace_mark(s, "scatter done", 0, 0);
     for (int l = P.nlevels - 1; l >= 0; l--) {
         const LevelPlan& L = P.levels[l];
         if (L.f22_zero_len > 0) {
@@ -626,6 +653,7 @@ static int do_factor(nkp_solver* s) {
                 prof_mark(s, KC_GEMM);
             }
         }
+        if (!L.mine.empty()) trace_mark(s, "level (rank-private fronts)", l, (int)L.mine.size());
         // the top fronts of this level: factored together with the other members of their groups
         for (int ti : L.tops)
             if (int rc = factor_top_front(s, P.top_fronts[ti], tiny)) return rc;
@@ -652,8 +680,15 @@ static int do_factor(nkp_solver* s) {
     s->factored = true;
     if (s->prof_on) prof_collect(s);
     if (s->opt.verbose)
-        fprintf(stderr, "[nkp] factor: %.3f ms (scatter %.3f ms), %.2f TFLOP/s, tiny pivots replaced: %d\n",
+        fprintf(stderr, "[nkp] rank %d factor: %.3f ms (scatter %.3f ms), %.2f TFLOP/s, tiny pivots replaced: %d\n", s->rank,
                 ms02, ms01, P.flops / (ms02 * 1e-3) * 1e-12, nrepl);
+    for (size_t i = 1; i < s->trace_ev.size(); i++) {
+        float ms = 0, tot = 0;
+        cudaEventElapsedTime(&ms, s->trace_ev[i - 1], s->trace_ev[i]);
+        cudaEventElapsedTime(&tot, s->trace_ev[0], s->trace_ev[i]);
+        if (ms >= 0.5f || s->opt.verbose >= 3)
+            fprintf(stderr, "[nkp] rank %d   %-40s %9.3f ms  (at %9.3f)\n", s->rank, s->trace_name[i].c_str(), ms, tot);
+    }
     return NKP_OK;
 }
 
@@ -1045,6 +1080,94 @@ int nkp_solve(nkp_solver* s, double* B, int ldb, int nrhs, double* berr) {
     return NKP_OK;
 }
 
+int nkp_solve_dist(nkp_solver* s, double* B, int ldb, int nrhs, int fst_row, int m_loc, double* berr) {
+    if (!s || !B || nrhs < 0 || fst_row < 0 || m_loc < 0 || fst_row + (int64_t)m_loc > s->n || ldb < m_loc) {
+        g_err = "nkp_solve_dist: invalid argument";
+        return NKP_EINVAL;
+    }
+    if (s->nranks == 1) {
+        if (fst_row != 0 || m_loc != s->n) {
+            g_err = "nkp_solve_dist: one rank must hold all rows";
+            return NKP_EINVAL;
+        }
+        return nkp_solve(s, B, ldb, nrhs, berr);
+    }
+    if (!s->factored) {
+        g_err = "nkp_solve: matrix not factored";
+        return NKP_ESTATE;
+    }
+    CK(cudaSetDevice(s->opt.device));
+    const int n = s->n, P = s->nranks;
+    cudaStream_t st = s->stream;
+    // who holds which rows (slab table of all ranks)
+    if (!s->d_slab) {
+        CK(cudaMalloc((void**)&s->d_slab, sizeof(PubRange) * (size_t)(P + 1)));
+        s->h_slab.assign(P, PubRange{0, 0, 0});
+    }
+    const PubRange mine{fst_row, fst_row + m_loc, s->rank};
+    CK(cudaMemcpyAsync(s->d_slab + P, &mine, sizeof(PubRange), cudaMemcpyHostToDevice, st));
+    CKN(ncclAllGather(s->d_slab + P, s->d_slab, sizeof(PubRange), ncclChar, s->comm, st));
+    CK(cudaMemcpyAsync(s->h_slab.data(), s->d_slab, sizeof(PubRange) * (size_t)P, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    {
+        std::vector<PubRange> t = s->h_slab;
+        std::sort(t.begin(), t.end(), [](const PubRange& a, const PubRange& b) { return a.lo < b.lo || (a.lo == b.lo && a.hi < b.hi); });
+        int pos = 0;
+        for (const PubRange& r : t) {
+            if (r.lo != pos || r.hi < r.lo) {
+                g_err = "nkp_solve_dist: the row slabs of the ranks do not tile [0, n)";
+                return NKP_EINVAL;
+            }
+            pos = r.hi;
+        }
+        if (pos != n) {
+            g_err = "nkp_solve_dist: the row slabs of the ranks do not tile [0, n)";
+            return NKP_EINVAL;
+        }
+    }
+    int maxsteps = 0;
+    double tsum = 0;
+    const bool pinned = host_is_pinned(B);
+    for (int c0 = 0; c0 < nrhs; c0 += MAX_NR) {
+        const int nr = std::min(MAX_NR, nrhs - c0);
+        for (int c = 0; c < nr; c++) {
+            const double* src = B + (size_t)(c0 + c) * ldb;
+            if (!pinned) {
+                par_memcpy(s->h_pinned + (size_t)c * m_loc, src, sizeof(double) * m_loc);
+                src = s->h_pinned + (size_t)c * m_loc;
+            }
+            CK(cudaMemcpyAsync(s->d_xb + (size_t)c * n + fst_row, src, sizeof(double) * m_loc, cudaMemcpyHostToDevice, st));
+        }
+        // slabs -> every GPU: packed per slab, one broadcast per rank, one group call (NVLink instead of P x PCIe)
+        k_pub_pack<<<dim3(64, P), 256, 0, st>>>(s->d_slab, s->rank, 0, s->d_xb, n, nr, s->d_pack);
+        CKN(ncclGroupStart());
+        for (const PubRange& r : s->h_slab) {
+            if (r.hi <= r.lo) continue;
+            double* p = s->d_pack + (size_t)r.lo * nr;
+            CKN(ncclBroadcast(p, p, (size_t)(r.hi - r.lo) * nr, ncclDouble, r.root, s->comm, st));
+        }
+        CKN(ncclGroupEnd());
+        k_pub_pack<<<dim3(64, P), 256, 0, st>>>(s->d_slab, s->rank, 1, s->d_xb, n, nr, s->d_pack);
+        s->launches += 2;
+        int rc = nkp_solve_device(s, s->d_xb, n, nr, berr ? berr + c0 : nullptr);
+        if (rc) return rc;
+        tsum += s->t_solve;
+        maxsteps = std::max(maxsteps, s->refine_steps);
+        for (int c = 0; c < nr; c++) {
+            double* dst = pinned ? B + (size_t)(c0 + c) * ldb : s->h_pinned + (size_t)c * m_loc;
+            CK(cudaMemcpyAsync(dst, s->d_xb + (size_t)c * n + fst_row, sizeof(double) * m_loc, cudaMemcpyDeviceToHost, st));
+            CK(cudaEventRecord(s->ev_col[c], st));
+        }
+        for (int c = 0; c < nr; c++) {
+            CK(cudaEventSynchronize(s->ev_col[c]));
+            if (!pinned) par_memcpy(B + (size_t)(c0 + c) * ldb, s->h_pinned + (size_t)c * m_loc, sizeof(double) * m_loc);
+        }
+    }
+    s->t_solve = tsum;
+    s->refine_steps = maxsteps;
+    return NKP_OK;
+}
+
 int nkp_set_tracer_maps(nkp_solver* s, int tracer_state_len, int coupled_tracer_cnt, const int* ind_i, const int* ind_j,
                         const int* ind_k, int imt, int jmt, int km) {
     if (!s || tracer_state_len <= 0 || coupled_tracer_cnt <= 0 || !ind_i || !ind_j || !ind_k || imt <= 0 || jmt <= 0 ||
@@ -1230,6 +1353,12 @@ int nkp_set_refine_rule(nkp_solver* s, int rule) {
     return NKP_OK;
 }
 
+int nkp_set_verbose(nkp_solver* s, int level) {
+    if (!s) return NKP_EINVAL;
+    s->opt.verbose = level;
+    return NKP_OK;
+}
+
 int nkp_set_residual_extra(nkp_solver* s, int on) {
     if (!s) return NKP_EINVAL;
     s->opt.residual_extra = on != 0;
@@ -1254,6 +1383,7 @@ void nkp_destroy(nkp_solver* s) {
     if (s->ev_p) cudaEventDestroy(s->ev_p);
     if (s->ev_b) cudaEventDestroy(s->ev_b);
     if (s->d_pub) cudaFree(s->d_pub);
+    if (s->d_slab) cudaFree(s->d_slab);
     if (s->d_pack) cudaFree(s->d_pack);
     void* ptrs[] = {s->heap,   s->d_rowptr, s->d_colind, s->d_rowidx, s->d_val,  s->d_scatter, s->d_perm,
                     s->d_bidx, s->d_rel,    s->d_R,      s->d_C,      s->d_diag, s->d_trsm,    s->d_gemm,

@@ -63,6 +63,7 @@ def load_library():
     lib.nkp_factor_device.argtypes = [vp, vp]
     lib.nkp_solve.argtypes = [vp, P(C.c_double), C.c_int, C.c_int, P(C.c_double)]
     lib.nkp_solve_device.argtypes = [vp, vp, C.c_int, C.c_int, P(C.c_double)]
+    lib.nkp_solve_dist.argtypes = [vp, P(C.c_double), C.c_int, C.c_int, C.c_int, C.c_int, P(C.c_double)]
     lib.nkp_set_tracer_maps.argtypes = [vp, C.c_int, C.c_int, P(C.c_int), P(C.c_int), P(C.c_int), C.c_int, C.c_int, C.c_int]
     lib.nkp_solve_fields.argtypes = [vp, P(P(C.c_double)), C.c_int, P(C.c_double)]
     lib.nkp_residual_device.argtypes = [vp, vp, vp, vp, C.c_int]
@@ -74,6 +75,7 @@ def load_library():
     lib.nkp_set_profile.argtypes = [vp, C.c_int]
     lib.nkp_set_refine_rule.argtypes = [vp, C.c_int]
     lib.nkp_set_residual_extra.argtypes = [vp, C.c_int]
+    lib.nkp_set_verbose.argtypes = [vp, C.c_int]
     lib.nkp_destroy.argtypes = [vp]
     lib.nkp_destroy.restype = None
     lib.nkp_last_error.restype = C.c_char_p
@@ -172,6 +174,22 @@ class TracerJacobianSolver:
         berr = np.zeros(max(nrhs, 1))
         _check(self._lib.nkp_solve(self._h, B.ctypes.data_as(C.POINTER(C.c_double)), ldb, nrhs,
                                    berr.ctypes.data_as(C.POINTER(C.c_double))), "nkp_solve")
+        return berr
+
+    def solve_dist(self, B_loc, fst_row):
+        """Multi-GPU solve with a row-distributed right-hand side (solve_ABdist, src/solve_ABdist.c:141-144): B_loc is
+        this rank's slab of rows [fst_row, fst_row + m_loc), Fortran order m_loc x nrhs, overwritten by the same rows
+        of X.  Returns berr[nrhs]."""
+        assert B_loc.dtype == np.float64
+        if B_loc.ndim == 1:
+            m_loc, nrhs = B_loc.shape[0], 1
+            assert B_loc.flags.c_contiguous
+        else:
+            assert B_loc.flags.f_contiguous
+            m_loc, nrhs = B_loc.shape
+        berr = np.zeros(max(nrhs, 1))
+        _check(self._lib.nkp_solve_dist(self._h, B_loc.ctypes.data_as(C.POINTER(C.c_double)), max(m_loc, 1), nrhs,
+                                        int(fst_row), m_loc, berr.ctypes.data_as(C.POINTER(C.c_double))), "nkp_solve_dist")
         return berr
 
     def solve_device(self, d_ptr, ldb, nrhs):

@@ -160,6 +160,8 @@ int nkp_sim_run_dist(int n, const int* rowptr, const int* colind, const double* 
     opt.leaf = leaf;
     if (opt.tn > nb) opt.tn = nb;
     if (getenv("NKP_OUTER")) opt.outer = atoi(getenv("NKP_OUTER"));
+    if (getenv("NKP_SPLIT_TOL")) opt.split_tol = atof(getenv("NKP_SPLIT_TOL"));
+    if (getenv("NKP_SPLIT_MAX")) opt.split_max = atoi(getenv("NKP_SPLIT_MAX"));
     if (getenv("NKP_SIM_TM")) opt.tm = atoi(getenv("NKP_SIM_TM"));
     if (getenv("NKP_SIM_TN")) opt.tn = atoi(getenv("NKP_SIM_TN"));
     opt.verbose = getenv("NKP_SIM_VERBOSE") ? atoi(getenv("NKP_SIM_VERBOSE")) : 0;
@@ -450,6 +452,8 @@ int nkp_sim_partition(int n, const int* rowptr, const int* colind, const int* ci
     opt.rank = rank;
     opt.nranks = nranks;
     if (getenv("NKP_OUTER")) opt.outer = atoi(getenv("NKP_OUTER"));
+    if (getenv("NKP_SPLIT_TOL")) opt.split_tol = atof(getenv("NKP_SPLIT_TOL"));
+    if (getenv("NKP_SPLIT_MAX")) opt.split_max = atoi(getenv("NKP_SPLIT_MAX"));
     const int* coords[3] = {ci, cj, ck};
     Plan P;
     int rc = analyse(n, rowptr, colind, (ci || cj || ck) ? coords : nullptr, opt, P);

@@ -424,12 +424,53 @@ def test_solve_fields_with_two_coupled_tracers(golden_matrix):
     s.close()
 
 
+def test_reference_options_at_gx3v7_scale():
+    """The reference's OWN operand at scale: gx3v7-shape grid, option set of
+    test/test_gen_A.csh:21-24 (upwind3 + isop_file + vmix file, up to 21-point rows), matrix file written by the
+    unchanged gen_A.  8.5e12 flop, 11.6 GB of factors: far beyond the oracle, so properties -- residual and
+    manufactured solution at the BASELINE.json tolerances, static pivoting without any replaced pivot, the
+    refinement step count, a second factorisation replaying the first bitwise."""
+    import bench
+    if not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "gen_A")):
+        pytest.skip("oracle/_ref/gen_A not built")
+    b = bench.build_case("gx3v7_ref")
+    c = dict(n=b["n"], rowptr=b["rowptr"], colind=b["colind"], nzval=b["nzval"], i=b["coords"][0], j=b["coords"][1], k=b["coords"][2])
+    assert np.diff(c["rowptr"]).max() > 15            # really the wide stencil
+    s = _solver(c)
+    s.factor(c["nzval"])
+    A = _A(c)
+    xs = np.random.default_rng(0).standard_normal((c["n"], 8))
+    B = bench.spmv_extended(c["rowptr"], c["colind"], c["nzval"], xs)
+    X = B.copy(order="F")
+    berr = s.solve(X)
+    st = s.stats()
+    print(f"gx3v7_ref: n={c['n']} nnz={len(c['nzval'])} flops={st['factor_flops']:.3e} factor {st['t_factor']:.3f} s "
+          f"refine steps {st['refine_steps']} tiny pivots {st['tiny_pivots']} berr {berr.max():.2e}")
+    assert (np.linalg.norm(A @ X - B, axis=0) / np.linalg.norm(B, axis=0)).max() <= RES_TOL
+    assert (np.linalg.norm(X - xs, axis=0) / np.linalg.norm(xs, axis=0)).max() <= SOL_TOL
+    assert berr.max() <= 4 * oracle_solve.EPS and st["refine_steps"] <= 4 and st["tiny_pivots"] == 0
+    assert st["factor_flops"] > 5e12 and st["max_front"] > 10000
+    s.factor(c["nzval"])
+    X2 = B.copy(order="F"); s.solve(X2)
+    assert np.array_equal(X, X2)
+    s.close()
+
+
 def test_full_size_gx1v6_properties():
-    """BASELINE.json configs[3] shape (320x384x60, n = 3.8 M, 128 GB of device memory): far beyond the
-    oracle, so size-independent properties -- residual at the tolerance, manufactured solution recovered
-    to the conditioning floor of this operand, linearity of the solve, a refactorisation with the same
-    values reproducing the first one bitwise (KAT-5), batched == single."""
+    """BASELINE.json configs[3] shape (320x384x60, n = 3.8 M, 128 GB of device memory): far beyond the oracle, so
+    size-independent properties.
+
+    Accuracy.  This operand is ill-conditioned (A = I - dt T for a one-year step of a transport operator whose only
+    damping is a surface sink: cond ~ 1e8; profiles/r02_refine_probe_gx1v6.log).  ANY double-precision right-hand side
+    of a manufactured x* carries half an ulp of rounding, which cond(A) turns into ~1e-8 of solution error -- for this
+    solver, for SuperLU_DIST, for anything.  So (1) b = A x* is formed in extended precision and rounded once
+    (bench.spmv_extended), and x* must be recovered to 3e-8 (the floor of the rounded b, measured 0.9e-8..2e-8);
+    (2) the BASELINE.json criterion proper -- solution relative DIFFERENCE between two solvers of the same system
+    <= 1e-8 -- is checked between two factorisations with different elimination trees and scalings (leaf 96 with
+    equilibration vs leaf 48 without): with the extra-precise residual both converge to the solution of the
+    double-precision system and must agree to 1e-10."""
     import torch
+    import bench
     if torch.cuda.get_device_properties(0).total_memory < 150e9:
         pytest.skip("needs a 180 GB GPU")
     c = synth_case(320, 384, 60, seed=1)
@@ -438,22 +479,33 @@ def test_full_size_gx1v6_properties():
     A = _A(c)
     rng = np.random.default_rng(0)
     xs = rng.standard_normal((c["n"], 3))
-    B = np.asfortranarray(A @ xs)
+    B = bench.spmv_extended(c["rowptr"], c["colind"], c["nzval"], xs)
     X = B.copy(order="F")
     berr = s.solve(X)
+    st = s.stats()
+    err = (np.linalg.norm(X - xs, axis=0) / np.linalg.norm(xs, axis=0)).max()
+    print(f"gx1v6: refine steps {st['refine_steps']} berr {berr.max():.2e} error vs x* {err:.3e}")
     assert (np.linalg.norm(A @ X - B, axis=0) / np.linalg.norm(B, axis=0)).max() <= RES_TOL
-    assert (np.linalg.norm(X - xs, axis=0) / np.linalg.norm(xs, axis=0)).max() <= 1e-6   # cond(A) * eps of b = A x*
-    assert berr.max() <= 1e-13
-    # linearity: solve(2 b0 - b1) == 2 x0 - x1 up to the same floor
+    assert err <= 3e-8
+    assert berr.max() <= 2 * oracle_solve.EPS and st["refine_steps"] <= 5
+    # linearity: solve(2 b0 - b1) == 2 x0 - x1 (all three are solutions of double-precision systems: 1e-8 applies)
     y = np.ascontiguousarray(2.0 * B[:, 0] - B[:, 1]); s.solve(y)
     ref = 2.0 * X[:, 0] - X[:, 1]
-    assert np.linalg.norm(y - ref) / np.linalg.norm(ref) <= 1e-6
+    assert np.linalg.norm(y - ref) / np.linalg.norm(ref) <= SOL_TOL
     x1 = B[:, 2].copy(); s.solve(x1)
     assert np.array_equal(x1, X[:, 2])
     # same values again: the static plan replays the same arithmetic
     s.factor(c["nzval"])
     X2 = B.copy(order="F"); s.solve(X2)
     assert np.array_equal(X, X2)
-    st = s.stats()
     assert st["n_levels"] >= 15 and st["factor_flops"] > 5e13 and st["tiny_pivots"] == 0
     s.close()
+    # a second, independent factorisation of the same system
+    s2 = _solver(c, leaf=48, equil=0)
+    s2.factor(c["nzval"])
+    X3 = B.copy(order="F"); s2.solve(X3)
+    diff = (np.linalg.norm(X3 - X, axis=0) / np.linalg.norm(X, axis=0)).max()
+    print(f"gx1v6: two independent factorisations differ by {diff:.3e}")
+    assert diff <= 1e-10
+    assert s2.stats()["n_fronts"] != st["n_fronts"]
+    s2.close()

@@ -198,3 +198,30 @@ def test_analysis_is_independent_of_the_thread_count(tmp_path):
         subprocess.check_call([sys.executable, str(script), libpath, str(out)], env=dict(os.environ, OMP_NUM_THREADS=str(nt)))
         perms.append(np.load(out))
     assert np.array_equal(perms[0], perms[1]) and np.array_equal(perms[0], perms[2])
+
+
+@pytest.mark.parametrize("shape", [(40, 46, 24), (64, 74, 38)])
+def test_oracle_floor_of_the_manufactured_solution(shape):
+    """Where is the floor of ||x - x*|| / ||x*|| for the PIVOTED oracle (scipy SuperLU + pdgsrfs refinement) when
+    b = A x* is formed in working precision and when it is formed in extended precision and rounded once
+    ?  At these sizes cond(A) * eps is ~1e-11..1e-10, both floors sit there, and the extended b
+    is never worse.  The floor grows with the grid (cond ~ 1e8 at gx1v6-shape: ~1e-8, measured on the GPU in
+    profiles/r02_refine_probe_gx1v6.log) -- the reason tests/test_gpu_parity.py::test_full_size_gx1v6_properties
+    checks the solution DIFFERENCE of two factorisations at 1e-10 and x* at 3e-8."""
+    import bench
+    from conftest import synth_case
+    c = synth_case(*shape, seed=1)
+    n = c["n"]
+    A = oracle_solve.csr(n, c["rowptr"], c["colind"], c["nzval"])
+    xs = np.random.default_rng(0).standard_normal((n, 2))
+    b_dbl = np.asfortranarray(A @ xs)
+    b_ext = bench.spmv_extended(c["rowptr"], c["colind"], c["nzval"], xs)
+    assert 0 < np.abs(b_dbl - b_ext).max() <= 4 * oracle_solve.EPS * np.abs(b_ext).max()
+    lu = oracle_solve.factor(n, c["rowptr"], c["colind"], c["nzval"])
+    err = {}
+    for name, b in (("double", b_dbl), ("extended", b_ext)):
+        X = oracle_solve.solve(n, c["rowptr"], c["colind"], c["nzval"], b, lu=lu)
+        err[name] = float((np.linalg.norm(X - xs, axis=0) / np.linalg.norm(xs, axis=0)).max())
+    print(f"oracle floor {shape}: n={n} double b {err['double']:.2e}, extended b {err['extended']:.2e}")
+    assert err["double"] <= 1e-9 and err["extended"] <= 1e-9
+    assert err["extended"] <= 1.5 * err["double"]
