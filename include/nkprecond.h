@@ -112,6 +112,13 @@ int nkp_create(nkp_solver** out, int n, const int* rowptr, const int* colind,
                const int* coord_i, const int* coord_j, const int* coord_k,
                const nkp_options* opt);
 
+/* Same as nkp_create with the pattern in FILE byte order: the big-endian NC_INT bytes of the `rowptr` (n + 1 values)
+ * and `colind` (nnz values) variables exactly as they lie in the NetCDF-3 matrix file (src/matrix.c:3884,3888; locate
+ * them with nkp_nc3_inq_var_extent).  The bytes are converted on the device; replaces the host loops behind
+ * nc_get_var_int in get_sparse_matrix (src/matrix.c:3944-4031).  Coordinates stay host-order ints. */
+int nkp_create_be(nkp_solver** out, int n, long long nnz, const void* rowptr_be, const void* colind_be,
+                  const int* coord_i, const int* coord_j, const int* coord_k, const nkp_options* opt);
+
 /* Multi-GPU (one process per GPU): every rank calls nkp_create_dist with the
  * same pattern; rank 0 obtains `unique_id` (NKP_UNIQUE_ID_BYTES bytes) from
  * nkp_comm_unique_id and ships it to the other ranks by any means (the bench uses
@@ -166,6 +173,17 @@ int nkp_solve_dist(nkp_solver* s, double* B_loc, int ldb, int nrhs, int fst_row,
 int nkp_set_tracer_maps(nkp_solver* s, int tracer_state_len, int coupled_tracer_cnt, const int* ind_i,
                         const int* ind_j, const int* ind_k, int imt, int jmt, int km);
 int nkp_solve_fields(nkp_solver* s, double* const* fields, int nfields, double* berr);
+
+/* The post-processing that ends every assembly of the reference's generator (gen_sparse_matrix, src/matrix.c:3775-3840)
+ * on a CRS held in DEVICE memory, in place: sum_dup_vals (src/matrix.c:3621-3650; same order of additions: bit-exact),
+ * then -- if strip_zeros != 0 -- strip_matrix_zeros (:3657-3688; rowptr is rebuilt, *nnz_out receives the new count),
+ * then sort_cols_all_rows (:3753-3765).  strip_zeros = 0 keeps explicit zeros, i.e. the slot pattern, which is what a
+ * refactorisation with new values on the same analysis needs.  dup_cnt_out (may be NULL) receives the reference's
+ * dup_cnt.  Uses the current CUDA device. */
+int nkp_crs_finalize_device(int n, int* d_rowptr, int* d_colind, double* d_val, int strip_zeros, long long* nnz_out,
+                            int* dup_cnt_out);
+/* count big-endian 32-bit integers in device memory -> host byte order, in place (NC_INT arrays of the matrix file). */
+int nkp_bswap32_device(void* d_data, long long count);
 
 /* Residual r = b - A x for the currently loaded values (device pointers, column-major
  * with leading dimension n); the refinement SpMV exposed for testing and measurement. */

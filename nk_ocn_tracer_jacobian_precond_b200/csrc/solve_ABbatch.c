@@ -150,7 +150,30 @@ typedef struct {
    int *rowptr, *colind;
    double *nzval;               /* host byte order, or ... */
    int nzval_is_file_order;     /* ... 1: the raw big-endian bytes of the file (swapped on the GPU) */
+   int index_is_file_order;     /* 1: rowptr / colind hold the raw big-endian NC_INT bytes of the file, too */
 } matrix_file_t;
+
+#ifndef NKP_NO_NC3_EXTENT
+/* Matrix-file ingest without the host conversion loops of nc_get_var_* (src/matrix.c:3978-4000): the bytes of a
+ * fixed-size variable exactly as they lie in the file; the GPU converts them (nkp_create_be / nkp_factor_be). */
+static int
+read_raw_var (const char *fname, int ncid, const char *name, int want_type, size_t want_bytes, void *dst)
+{
+   long long off = 0, nbytes = 0;
+   int xtype = 0, varid, ok = 0;
+   FILE *fp;
+
+   if (nc_inq_varid (ncid, name, &varid) != NC_NOERR)
+      return 0;
+   if (nkp_nc3_inq_var_extent (ncid, varid, &off, &nbytes, &xtype) != NC_NOERR || xtype != want_type
+       || nbytes != (long long) want_bytes || (fp = fopen (fname, "rb")) == NULL)
+      return 0;
+   if (fseeko (fp, (off_t) off, SEEK_SET) == 0 && fread (dst, 1, want_bytes, fp) == want_bytes)
+      ok = 1;
+   fclose (fp);
+   return ok;
+}
+#endif
 
 static int
 read_matrix_file (const char *fname, matrix_file_t * mf)
@@ -197,25 +220,20 @@ read_matrix_file (const char *fname, matrix_file_t * mf)
       return 1;
    }
    if (read_int_var (ncid, "tracer_state_ind_to_i", mf->ind_i) || read_int_var (ncid, "tracer_state_ind_to_j", mf->ind_j)
-       || read_int_var (ncid, "tracer_state_ind_to_k", mf->ind_k) || read_int_var (ncid, "rowptr", mf->rowptr)
-       || read_int_var (ncid, "colind", mf->colind))
+       || read_int_var (ncid, "tracer_state_ind_to_k", mf->ind_k))
+      return 1;
+#ifndef NKP_NO_NC3_EXTENT
+   if (read_raw_var (fname, ncid, "rowptr", NC_INT, sizeof (int) * ((size_t) mf->flat_len + 1), mf->rowptr)
+       && read_raw_var (fname, ncid, "colind", NC_INT, sizeof (int) * (size_t) mf->nnz, mf->colind))
+      mf->index_is_file_order = 1;
+#endif
+   if (!mf->index_is_file_order && (read_int_var (ncid, "rowptr", mf->rowptr) || read_int_var (ncid, "colind", mf->colind)))
       return 1;
    if ((status = nc_inq_varid (ncid, "nzval_row_wise", &varid)) != NC_NOERR)
       return nc_fail (status, "nc_inq_varid", "nzval_row_wise");
 #ifndef NKP_NO_NC3_EXTENT
-   {
-      /* matrix-file ingest without the host byte-swap loop: read the variable's bytes as they are */
-      long long off = 0, nbytes = 0;
-      int xtype = 0;
-      FILE *fp;
-
-      if (nkp_nc3_inq_var_extent (ncid, varid, &off, &nbytes, &xtype) == NC_NOERR && xtype == NC_DOUBLE
-          && nbytes == (long long) sizeof (double) * mf->nnz && (fp = fopen (fname, "rb")) != NULL) {
-         if (fseeko (fp, (off_t) off, SEEK_SET) == 0 && fread (mf->nzval, 1, (size_t) nbytes, fp) == (size_t) nbytes)
-            mf->nzval_is_file_order = 1;
-         fclose (fp);
-      }
-   }
+   if (read_raw_var (fname, ncid, "nzval_row_wise", NC_DOUBLE, sizeof (double) * (size_t) mf->nnz, mf->nzval))
+      mf->nzval_is_file_order = 1;
 #endif
    if (!mf->nzval_is_file_order && (status = nc_get_var_double (ncid, varid, mf->nzval)) != NC_NOERR)
       return nc_fail (status, "nc_get_var_double", "nzval_row_wise");
@@ -270,7 +288,10 @@ main (int argc, char **argv)
    /* analysis + numeric factorisation: the nrhs = 0 call of the reference (src/solve_ABglobal.c:353) */
    nkp_default_options (&opt);
    opt.verbose = dbg_lvl;
-   rc = nkp_create (&solver, mf.flat_len, mf.rowptr, mf.colind, ci, cj, ck, &opt);
+   if (dbg_lvl)
+      printf ("(%d) calling %s\n", iam, mf.index_is_file_order ? "nkp_create_be (rowptr, colind in file byte order)" : "nkp_create");
+   rc = mf.index_is_file_order ? nkp_create_be (&solver, mf.flat_len, mf.nnz, mf.rowptr, mf.colind, ci, cj, ck, &opt)
+      : nkp_create (&solver, mf.flat_len, mf.rowptr, mf.colind, ci, cj, ck, &opt);
    if (rc != NKP_OK) {
       fprintf (stderr, "(%d) nkp_create failed: %s\n", iam, nkp_last_error ());
       exit (EXIT_FAILURE);

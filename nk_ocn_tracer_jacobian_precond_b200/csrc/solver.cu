@@ -279,7 +279,7 @@ void nkp_default_options(nkp_options* o) {
 
 static int create_impl(nkp_solver** out, int n, const int* rowptr, const int* colind, const int* ci,
                        const int* cj, const int* ck, const nkp_options* opt_in, int rank, int nranks,
-                       const void* unique_id) {
+                       const void* unique_id, int* d_rowptr_adopt = nullptr, int* d_colind_adopt = nullptr) {
     if (!out || n <= 0 || !rowptr || !colind || rank < 0 || nranks < 1 || rank >= nranks ||
         (nranks > 1 && !unique_id)) {
         g_err = "nkp_create: invalid argument";
@@ -380,8 +380,13 @@ static int create_impl(nkp_solver** out, int n, const int* rowptr, const int* co
         std::vector<int> rp(rowptr, rowptr + n + 1), cidx(colind, colind + s->nnz), ridx((size_t)s->nnz);
         for (int i = 0; i < n; i++)
             for (int p = rowptr[i]; p < rowptr[i + 1]; p++) ridx[p] = i;
-        if (upload(&s->d_rowptr, rp)) return NKP_ECUDA;
-        if (upload(&s->d_colind, cidx)) return NKP_ECUDA;
+        if (d_rowptr_adopt && d_colind_adopt) {   // already on the device (nkp_create_be)
+            s->d_rowptr = d_rowptr_adopt;
+            s->d_colind = d_colind_adopt;
+        } else {
+            if (upload(&s->d_rowptr, rp)) return NKP_ECUDA;
+            if (upload(&s->d_colind, cidx)) return NKP_ECUDA;
+        }
         if (upload(&s->d_rowidx, ridx)) return NKP_ECUDA;
         if (upload(&s->d_scatter, P.scatter)) return NKP_ECUDA;
         if (upload(&s->d_perm, P.perm)) return NKP_ECUDA;
@@ -452,6 +457,58 @@ static int create_impl(nkp_solver** out, int n, const int* rowptr, const int* co
 int nkp_create(nkp_solver** out, int n, const int* rowptr, const int* colind, const int* ci,
                const int* cj, const int* ck, const nkp_options* opt_in) {
     return create_impl(out, n, rowptr, colind, ci, cj, ck, opt_in, 0, 1, nullptr);
+}
+
+extern "C" int nkp_bswap32_device(void* d_data, long long count);
+
+// Pattern arrays in FILE byte order: the big-endian NC_INT bytes of `rowptr` and `colind` as they lie in the matrix
+// file go to the device unchanged and are converted there (k_bswap32); the host-order copy the analysis needs comes
+// back from the device.  Replaces the host loops behind nc_get_var_int in get_sparse_matrix (src/matrix.c:3944-4031).
+int nkp_create_be(nkp_solver** out, int n, long long nnz, const void* rowptr_be, const void* colind_be, const int* ci,
+                  const int* cj, const int* ck, const nkp_options* opt_in) {
+    if (!out || n <= 0 || nnz <= 0 || nnz > 2147483647LL || !rowptr_be || !colind_be) {
+        g_err = "nkp_create_be: invalid argument";
+        return NKP_EINVAL;
+    }
+    nkp_options o;
+    if (opt_in) o = *opt_in;
+    else nkp_default_options(&o);
+    CK(cudaSetDevice(o.device));
+    int *d_rp = nullptr, *d_ci = nullptr;
+    CK(cudaMalloc((void**)&d_rp, sizeof(int) * ((size_t)n + 1)));
+    CK(cudaMalloc((void**)&d_ci, sizeof(int) * (size_t)nnz));
+    std::vector<int> rp((size_t)n + 1), cidx((size_t)nnz);
+    auto body = [&]() -> int {
+        CK(cudaMemcpy(d_rp, rowptr_be, sizeof(int) * ((size_t)n + 1), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(d_ci, colind_be, sizeof(int) * (size_t)nnz, cudaMemcpyHostToDevice));
+        if (nkp_bswap32_device(d_rp, (long long)n + 1) || nkp_bswap32_device(d_ci, nnz)) {
+            g_err = "nkp_create_be: byte-swap kernel failed";
+            return NKP_ECUDA;
+        }
+        CK(cudaMemcpy(rp.data(), d_rp, sizeof(int) * ((size_t)n + 1), cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(cidx.data(), d_ci, sizeof(int) * (size_t)nnz, cudaMemcpyDeviceToHost));
+        if (rp[0] != 0 || rp[n] != nnz) {
+            g_err = "nkp_create_be: rowptr does not match nnz (wrong byte order or variable?)";
+            return NKP_EINVAL;
+        }
+        return 0;
+    };
+    int rc = body();
+    if (rc) {
+        cudaFree(d_rp);
+        cudaFree(d_ci);
+        return rc;
+    }
+    rc = create_impl(out, n, rp.data(), cidx.data(), ci, cj, ck, &o, 0, 1, nullptr, d_rp, d_ci);
+    if (rc) {
+        // create_impl frees adopted arrays through nkp_destroy once they are attached; before that they are still ours
+        // (analysis failure happens before attachment)
+        if (rc == NKP_EANALYSIS || rc == NKP_EINVAL) {
+            cudaFree(d_rp);
+            cudaFree(d_ci);
+        }
+    }
+    return rc;
 }
 
 int nkp_create_dist(nkp_solver** out, int n, const int* rowptr, const int* colind, const int* ci,
@@ -532,16 +589,19 @@ static int factor_top_front(nkp_solver* s, const TopFront& tf, double tiny) {
                 k_diag<<<ts.diag_end - ts.diag_begin, 256, 0, st>>>(s->d_diag + ts.diag_begin, s->heap, tiny, s->d_nrepl);
                 s->launches++;
                 prof_mark(s, KC_DIAG);
+                if (s->opt.verbose >= 4) trace_mark(s, "      diag", q - tb.step_begin, 0);
             }
             if (ts.trsm_ctas > 0) {
                 k_trsm<<<ts.trsm_ctas, TRSM_THREADS, TRSM_SMEM, st>>>(s->d_trsm + ts.trsm_begin, ts.trsm_end - ts.trsm_begin, s->heap);
                 s->launches++;
                 prof_mark(s, KC_TRSM);
+                if (s->opt.verbose >= 4) trace_mark(s, "      trsm ctas", q - tb.step_begin, ts.trsm_ctas);
             }
             if (ts.gemm_tiles > 0) {
                 k_gemm<<<ts.gemm_tiles, 256, G_SMEM, st>>>(s->d_gemm + ts.gemm_begin, ts.gemm_end - ts.gemm_begin, s->heap, nb);
                 s->launches++;
                 prof_mark(s, KC_GEMM);
+                if (s->opt.verbose >= 4) trace_mark(s, "      narrow gemm tiles", q - tb.step_begin, ts.gemm_tiles);
             }
         }
     };
@@ -563,10 +623,12 @@ static int factor_top_front(nkp_solver* s, const TopFront& tf, double tiny) {
             CK(cudaEventRecord(s->ev_b, cs));
             if (!own) CK(cudaStreamWaitEvent(st, s->ev_b, 0));   // the owner already has what it sends
         }
+        if (s->opt.verbose >= 4) trace_mark(s, "      wait bcast", K, own);
         if (tb.next_tiles > 0) {
             k_gemm<<<tb.next_tiles, 256, G_SMEM, st>>>(s->d_gemm + tb.next_begin, tb.next_end - tb.next_begin, s->heap, nb);
             s->launches++;
             prof_mark(s, KC_GEMM);
+            if (s->opt.verbose >= 4) trace_mark(s, "      next gemm tiles", K, tb.next_tiles);
         }
         if (K + 1 < nK && P.top_blocks[tf.block_begin + K + 1].owner == s->rank) {
             panel(P.top_blocks[tf.block_begin + K + 1]);
@@ -576,6 +638,7 @@ static int factor_top_front(nkp_solver* s, const TopFront& tf, double tiny) {
             k_gemm<<<tb.rest_tiles, 256, G_SMEM, st>>>(s->d_gemm + tb.rest_begin, tb.rest_end - tb.rest_begin, s->heap, nb);
             s->launches++;
             prof_mark(s, KC_GEMM);
+            if (s->opt.verbose >= 4) trace_mark(s, "      rest gemm tiles", K, tb.rest_tiles);
         }
     }
     // every broadcast of this front (our own sends included) is complete before anything changes the panels again

@@ -58,6 +58,9 @@ def load_library():
     lib.nkp_create_dist.argtypes = [P(vp), C.c_int, P(C.c_int), P(C.c_int), P(C.c_int), P(C.c_int), P(C.c_int),
                                     P(NkpOptions), C.c_int, C.c_int, C.c_char_p]
     lib.nkp_comm_unique_id.argtypes = [C.c_char_p]
+    lib.nkp_create_be.argtypes = [P(vp), C.c_int, C.c_longlong, vp, vp, P(C.c_int), P(C.c_int), P(C.c_int), P(NkpOptions)]
+    lib.nkp_crs_finalize_device.argtypes = [C.c_int, vp, vp, vp, C.c_int, P(C.c_longlong), P(C.c_int)]
+    lib.nkp_bswap32_device.argtypes = [vp, C.c_longlong]
     lib.nkp_factor.argtypes = [vp, P(C.c_double)]
     lib.nkp_factor_be.argtypes = [vp, vp]
     lib.nkp_factor_device.argtypes = [vp, vp]
@@ -113,6 +116,15 @@ def _iptr(a):
     return a.ctypes.data_as(C.POINTER(C.c_int)) if a is not None else None
 
 
+def crs_finalize_device(n, d_rowptr, d_colind, d_val, strip_zeros=True):
+    """sum_dup_vals + (strip_matrix_zeros) + sort_cols_all_rows (src/matrix.c:3621-3770) on device arrays, in place;
+    arguments are device addresses.  Returns (nnz, dup_cnt)."""
+    nnz, dup = C.c_longlong(), C.c_int()
+    _check(load_library().nkp_crs_finalize_device(int(n), C.c_void_p(d_rowptr), C.c_void_p(d_colind), C.c_void_p(d_val),
+                                                  int(bool(strip_zeros)), C.byref(nnz), C.byref(dup)), "nkp_crs_finalize_device")
+    return nnz.value, dup.value
+
+
 class TracerJacobianSolver:
     """Analysis handle + numeric factors for one sparsity pattern (CRS, 0-based).
 
@@ -120,14 +132,22 @@ class TracerJacobianSolver:
     src/matrix.c:322-329) enabling the geometric nested dissection.
     """
 
-    def __init__(self, n, rowptr, colind, coords=None, comm=None, **opts):
-        """comm: None (one GPU) or (rank, nranks, unique_id_bytes) for one-process-per-GPU runs."""
+    def __init__(self, n, rowptr, colind, coords=None, comm=None, file_byte_order=False, **opts):
+        """comm: None (one GPU) or (rank, nranks, unique_id_bytes) for one-process-per-GPU runs.
+        file_byte_order=True: rowptr / colind are the big-endian NC_INT bytes of the matrix file (bytes-like, n + 1 and
+        nnz values); they are converted on the device (nkp_create_be)."""
         lib = load_library()
         self._lib = lib
         self.n = int(n)
-        rowptr = np.ascontiguousarray(rowptr, dtype=np.int32)
-        colind = np.ascontiguousarray(colind, dtype=np.int32)
-        self.nnz = int(rowptr[-1])
+        if file_byte_order:
+            rp_raw = np.frombuffer(rowptr, dtype=np.uint8)
+            ci_raw = np.frombuffer(colind, dtype=np.uint8)
+            assert rp_raw.size == 4 * (self.n + 1) and comm is None
+            self.nnz = ci_raw.size // 4
+        else:
+            rowptr = np.ascontiguousarray(rowptr, dtype=np.int32)
+            colind = np.ascontiguousarray(colind, dtype=np.int32)
+            self.nnz = int(rowptr[-1])
         o = NkpOptions()
         lib.nkp_default_options(C.byref(o))
         for k, v in opts.items():
@@ -136,7 +156,10 @@ class TracerJacobianSolver:
         if coords is not None:
             ci, cj, ck = (np.ascontiguousarray(c, dtype=np.int32) if c is not None else None for c in coords)
         self._h = C.c_void_p()
-        if comm is None:
+        if file_byte_order:
+            _check(lib.nkp_create_be(C.byref(self._h), self.n, self.nnz, C.c_void_p(rp_raw.ctypes.data), C.c_void_p(ci_raw.ctypes.data),
+                                     _iptr(ci), _iptr(cj), _iptr(ck), C.byref(o)), "nkp_create_be")
+        elif comm is None:
             _check(lib.nkp_create(C.byref(self._h), self.n, _iptr(rowptr), _iptr(colind), _iptr(ci), _iptr(cj),
                                   _iptr(ck), C.byref(o)), "nkp_create")
         else:

@@ -367,11 +367,15 @@ def index_maps(KMT: np.ndarray, km: int):
 
 
 def assemble_crs(grid: dict, circ: dict, day_cnt: float = 365.0,
-                 sink_rate: float = 365.0, sink_depth: float = 10.0e2):
+                 sink_rate: float = 365.0, sink_depth: float = 10.0e2, raw: bool = False):
     """numpy restatement of gen_sparse_matrix for centered / const / const / const_shallow.
 
     Returns (n, rowptr[int32 n+1], colind[int32 nnz], nzval[float64 nnz], maps) where
     maps = (i, j, k, int3_to_tracer_state_ind).
+    raw=True returns the matrix as it stands BEFORE the post-processing of gen_sparse_matrix (sum_dup_vals,
+    strip_matrix_zeros, sort_cols_all_rows, src/matrix.c:3829-3835): every stencil slot of a row in slot order
+    (self, k-1, k+1, east, west, north, south), exact zeros kept, columns unsorted -- the input of
+    nkp_crs_finalize_device.
     Operation order per slot follows src/matrix.c:
       add_UTE_coeffs :1239-1273, add_VTN_coeffs :1320-1360, add_WVEL_coeffs :1401-1430,
       adv_enforce_divfree :2094-2206, add_hmix_const :2656-2710, add_vmix_const :2978-3004,
@@ -478,15 +482,23 @@ def assemble_crs(grid: dict, circ: dict, day_cnt: float = 365.0,
     rows = []
     cols = []
     vals = []
-    for present, c, v in ((np.ones(n, bool), me, v_self), (has_up, c_up, v_up), (has_dn, c_dn, v_dn),
-                          (has_e, c_e, v_e), (has_w, c_w, v_w), (has_n, c_n, v_n), (has_s, c_s, v_s)):
-        keep = present & (v != 0.0)  # strip_matrix_zeros drops exact zeros
+    slots = []
+    for slot, (present, c, v) in enumerate(((np.ones(n, bool), me, v_self), (has_up, c_up, v_up), (has_dn, c_dn, v_dn),
+                                            (has_e, c_e, v_e), (has_w, c_w, v_w), (has_n, c_n, v_n), (has_s, c_s, v_s))):
+        keep = present if raw else present & (v != 0.0)  # strip_matrix_zeros drops exact zeros
         rows.append(me[keep])
         cols.append(c[keep])
         vals.append(v[keep])
+        slots.append(np.full(int(keep.sum()), slot))
     rows = np.concatenate(rows)
     cols = np.concatenate(cols)
     vals = np.concatenate(vals)
+    if raw:
+        order = np.lexsort((np.concatenate(slots), rows))
+        rows, cols, vals = rows[order], cols[order], vals[order]
+        rowptr = np.zeros(n + 1, dtype=np.int64)
+        np.add.at(rowptr, rows + 1, 1)
+        return n, np.cumsum(rowptr).astype(np.int32), cols.astype(np.int32), vals, (ii, jj, kk, int3)
     # east and west may name the same column on a 2-wide periodic grid; the reference
     # would merge them in sum_dup_vals -- not reproduced: require imt >= 3
     assert imt >= 3

@@ -509,3 +509,61 @@ def test_full_size_gx1v6_properties():
     assert diff <= 1e-10
     assert s2.stats()["n_fronts"] != st["n_fronts"]
     s2.close()
+
+
+def test_crs_finalize_device_matches_reference_postprocessing(golden_matrix):
+    """nkp_crs_finalize_device (sum_dup_vals + strip_matrix_zeros + sort_cols_all_rows on the device, SURVEY.md 8(f)
+    rank 3): bit-exact against (a) the CRS the reference's gen_A wrote for the golden case, from its pre-processing
+    form, and (b) the CPU restatement on a random CRS with duplicates, cancelling sums and explicit zeros -- with and
+    without stripping (the same-pattern path keeps explicit zeros)."""
+    import torch
+    from nk_ocn_tracer_jacobian_precond_b200 import solver, synth
+    from oracle import crs_post
+    c = synth_case(20, 24, 10, seed=1)
+    n, rp, ci, nz, _ = synth.assemble_crs(c["grid"], c["circ"], raw=True)
+
+    def run(n, rp, ci, nz, strip):
+        drp, dci, dv = (torch.tensor(a, device="cuda") for a in (rp, ci, nz))
+        nnz, dup = solver.crs_finalize_device(n, drp.data_ptr(), dci.data_ptr(), dv.data_ptr(), strip)
+        return drp.cpu().numpy(), dci.cpu().numpy()[:nnz], dv.cpu().numpy()[:nnz], nnz, dup
+
+    rp2, ci2, nz2, nnz, dup = run(n, rp, ci, nz, True)
+    assert nnz == len(golden_matrix["colind"]) and dup == 0
+    assert np.array_equal(rp2, golden_matrix["rowptr"]) and np.array_equal(ci2, golden_matrix["colind"])
+    assert np.array_equal(nz2, golden_matrix["nzval_row_wise"])
+    # random rows of up to 21 slots drawn from few columns (many duplicates), values that cancel, explicit zeros
+    rng = np.random.default_rng(5)
+    nr = 5000
+    lens = rng.integers(0, 22, nr)
+    rp = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    ci = rng.integers(0, 12, rp[-1]).astype(np.int32) + np.repeat(rng.integers(0, nr - 12, nr), lens).astype(np.int32)
+    v = rng.choice(np.array([0.0, 1.0, -1.0, 1e16, -1e16, 0.1, 0.2, -0.3]), rp[-1])
+    for strip in (True, False):
+        ro, co, vo, dupo = crs_post.finalize(rp, ci, v, strip_zeros=strip)
+        rd, cd, vd, nnz, dupd = run(nr, rp, ci, v, strip)
+        assert nnz == ro[-1] and dupd == dupo and dupo > 0
+        assert np.array_equal(rd, ro) and np.array_equal(cd, co) and np.array_equal(vd, vo)
+    assert ro[-1] == rp[-1]          # without stripping the slot pattern is unchanged
+
+
+def test_create_from_file_byte_order(golden_matrix):
+    """nkp_create_be: the big-endian NC_INT bytes of rowptr / colind as they lie in the matrix file, converted on the
+    device (second half) -- same analysis, bitwise the same solution as nkp_create."""
+    from nk_ocn_tracer_jacobian_precond_b200 import solver
+    c = _golden_case(golden_matrix)
+    b = np.random.default_rng(12).standard_normal(c["n"])
+    s = _solver(c)
+    s.factor(c["nzval"])
+    x0 = b.copy(); s.solve(x0)
+    p0 = s.perm()
+    s.close()
+    s = solver.TracerJacobianSolver(c["n"], c["rowptr"].astype(">i4").tobytes(), c["colind"].astype(">i4").tobytes(),
+                                    coords=(c["i"], c["j"], c["k"]), file_byte_order=True)
+    assert np.array_equal(s.perm(), p0)
+    s.factor(c["nzval"])
+    x1 = b.copy(); s.solve(x1)
+    assert np.array_equal(x0, x1)
+    s.close()
+    with pytest.raises(solver.NkpError):     # host-order bytes are not a valid big-endian rowptr
+        solver.TracerJacobianSolver(c["n"], c["rowptr"].astype("<i4").tobytes(), c["colind"].astype("<i4").tobytes(),
+                                    coords=(c["i"], c["j"], c["k"]), file_byte_order=True)

@@ -225,3 +225,35 @@ def test_oracle_floor_of_the_manufactured_solution(shape):
     print(f"oracle floor {shape}: n={n} double b {err['double']:.2e}, extended b {err['extended']:.2e}")
     assert err["double"] <= 1e-9 and err["extended"] <= 1e-9
     assert err["extended"] <= 1.5 * err["double"]
+
+
+def test_crs_post_reproduces_gen_A(golden_matrix):
+    """oracle/crs_post.py (restatement of sum_dup_vals / strip_matrix_zeros / sort_cols_all_rows, src/matrix.c:3621-3770)
+    turns the pre-processing form of the golden operand into exactly the CRS the reference's gen_A wrote."""
+    from conftest import synth_case
+    from nk_ocn_tracer_jacobian_precond_b200 import synth
+    from oracle import crs_post
+    c = synth_case(20, 24, 10, seed=1)
+    n, rp, ci, nz, _ = synth.assemble_crs(c["grid"], c["circ"], raw=True)
+    assert np.any(np.diff(ci)[np.diff(np.repeat(np.arange(n), np.diff(rp))) == 0] < 0)     # really unsorted
+    rp2, ci2, nz2, dup = crs_post.finalize(rp, ci, nz)
+    assert dup == 0
+    assert np.array_equal(rp2, golden_matrix["rowptr"]) and np.array_equal(ci2, golden_matrix["colind"])
+    assert np.array_equal(nz2, golden_matrix["nzval_row_wise"])
+
+
+def test_crs_post_known_answers():
+    """Hand-checkable case: duplicates are summed INTO THE FIRST occurrence in order, a sum that cancels is stripped,
+    zeros left by merged duplicates are stripped, columns end up ascending."""
+    from oracle import crs_post
+    rp = np.array([0, 5, 7, 9], dtype=np.int32)
+    ci = np.array([2, 0, 2, 1, 2, 1, 1, 2, 0], dtype=np.int32)
+    v = np.array([1e16, 3.0, 1.0, 0.0, -1e16, 2.0, -2.0, 5.0, 4.0])
+    rp2, ci2, v2, dup = crs_post.finalize(rp, ci, v)
+    # row 0: column 2 = (1e16 + 1.0) + -1e16 = 0.0 in double (the reference's order), stripped; explicit 0 stripped
+    # the second and third entry of column 2 also match each other: dup_cnt counts that pair too (3 + 1)
+    assert dup == 4
+    assert rp2.tolist() == [0, 1, 1, 3] and ci2.tolist() == [0, 0, 2] and v2.tolist() == [3.0, 4.0, 5.0]
+    rp3, ci3, v3, _ = crs_post.finalize(rp, ci, v, strip_zeros=False)
+    assert rp3.tolist() == rp.tolist() and ci3.tolist() == [0, 1, 2, 2, 2, 1, 1, 0, 2]
+    assert v3.tolist() == [3.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 4.0, 5.0]
