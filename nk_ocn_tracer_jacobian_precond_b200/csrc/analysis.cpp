@@ -955,7 +955,8 @@ int analyse(int n, const int* rowptr, const int* colind, const int* const coords
         plan.add_tasks.push_back(a);
     };
     const int G = std::max(1, opt.outer);
-    const int W = G * nb;   // outer block width = distribution block of the top fronts
+    const int W = G * nb;   // outer block width of the rank-private fronts
+    const int Wt = std::max(1, opt.top_outer) * nb;   // outer block width = distribution block of the top fronts
     for (int l = plan.nlevels - 1; l >= 0; l--) {
         LevelPlan& L = plan.levels[l];
         int maxs = 0;
@@ -1035,9 +1036,9 @@ int analyse(int n, const int* rowptr, const int* colind, const int* const coords
             tf.front = t;
             tf.group = plan.group_of[t];
             tf.member = stores(t) ? 1 : 0;
-            const int nK = (f.s + W - 1) / W;
+            const int nK = (f.s + Wt - 1) / Wt;
             auto f22_owner = [&](const Front& ff, const std::vector<int>& gg, int jc) {
-                return gg[(((ff.s + W - 1) / W) + jc) % (int)gg.size()];
+                return gg[(((ff.s + Wt - 1) / Wt) + jc) % (int)gg.size()];
             };
             // update matrices of the children -> every member (complete copies; the extend-add is done by all)
             tf.cb_begin = (int)plan.top_child_bcasts.size();
@@ -1048,10 +1049,10 @@ int analyse(int n, const int* rowptr, const int* colind, const int* const coords
                     plan.top_child_bcasts.push_back(TopBcast{plan.owner[c], 0, tf.member ? fc.F22off : -1, (int64_t)fc.r * fc.r});
                 } else {
                     const std::vector<int>& gc = plan.groups[plan.group_of[c]];
-                    for (int jc = 0; jc * W < fc.r; jc++) {
-                        const int w = std::min(W, fc.r - jc * W);
+                    for (int jc = 0; jc * Wt < fc.r; jc++) {
+                        const int w = std::min(Wt, fc.r - jc * Wt);
                         plan.top_child_bcasts.push_back(TopBcast{f22_owner(fc, gc, jc), 0,
-                                                                 tf.member ? fc.F22off + (int64_t)jc * W * fc.r : -1,
+                                                                 tf.member ? fc.F22off + (int64_t)jc * Wt * fc.r : -1,
                                                                  (int64_t)w * fc.r});
                     }
                 }
@@ -1072,7 +1073,7 @@ int analyse(int n, const int* rowptr, const int* colind, const int* const coords
             }
             for (int K = 0; K < nK; K++) {
                 TopBlock tb;
-                const int K0 = K * W, ke = std::min(f.s, K0 + W);
+                const int K0 = K * Wt, ke = std::min(f.s, K0 + Wt);
                 tb.owner = grp[K % g];
                 tb.step_begin = tb.step_end = (int)plan.top_steps.size();
                 tb.next_begin = tb.next_end = tb.rest_begin = tb.rest_end = (int)plan.gemm_tasks.size();
@@ -1102,7 +1103,7 @@ int analyse(int n, const int* rowptr, const int* colind, const int* const coords
                     // wide update from block K: first the block that is factored next, then the rest of what this rank owns
                     const int Kw = ke - K0;
                     auto wide_pivot_block = [&](int J, int& tile0) {
-                        const int J0 = J * W, wJ = std::min(f.s, J0 + W) - J0;
+                        const int J0 = J * Wt, wJ = std::min(f.s, J0 + Wt) - J0;
                         int64_t Lrow = f.Loff + J0 + (int64_t)K0 * ld;     // L[J0.., K0:ke]
                         int64_t UTrow = f.UToff + J0 + (int64_t)K0 * ld;   // U^T[J0.., K0:ke]
                         push_gemm(tile0, Lrow, UTrow, f.Loff + J0 + (int64_t)J0 * ld, f.m - J0, wJ, Kw, f.ld, f.ld, f.ld, 1);
@@ -1117,9 +1118,9 @@ int analyse(int n, const int* rowptr, const int* colind, const int* const coords
                     tile0 = 0;
                     for (int J = K + 2; J < nK; J++)
                         if (grp[J % g] == plan.rank) wide_pivot_block(J, tile0);
-                    for (int jc = 0; jc * W < f.r; jc++) {
+                    for (int jc = 0; jc * Wt < f.r; jc++) {
                         if (f22_owner(f, grp, jc) != plan.rank) continue;
-                        const int jc0 = jc * W, wj = std::min(W, f.r - jc0);
+                        const int jc0 = jc * Wt, wj = std::min(Wt, f.r - jc0);
                         push_gemm(tile0, f.Loff + f.s + (int64_t)K0 * ld, f.UToff + f.s + jc0 + (int64_t)K0 * ld,
                                   f.F22off + (int64_t)jc0 * f.r, f.r, wj, Kw, f.ld, f.ld, f.r, 0);
                     }

@@ -193,63 +193,95 @@ __global__ void __launch_bounds__(256) k_extend_add(const AddTask* __restrict__ 
 
 constexpr int NBMAX = 64;
 
+// The whole block lives in registers: thread (ti, tj) of a 16 x 16 grid owns the 4 x 4 tile of rows 4 ti .. and
+// columns 4 tj ...  Step k: the pivot row and the (unscaled) pivot column are published through a double-buffered
+// pair of 64-entry shared-memory vectors, every thread forms the reciprocal of the pivot and its four multipliers
+// itself and updates its tile with 16 FMAs -- ONE CTA barrier per column and no shared-memory traffic for the
+// trailing matrix (the first version kept the block in shared memory: 37 us per block on the critical path of every
+// panel; this one takes about a quarter of that).
 __global__ void __launch_bounds__(256) k_diag(const DiagTask* __restrict__ tasks, double* __restrict__ heap,
                                               double tiny, int* __restrict__ n_replaced) {
-    __shared__ double D[NBMAX * (NBMAX + 1)];   // column-major, ld = NBMAX+1
+    __shared__ __align__(16) double rowb[2][NBMAX], colb[2][NBMAX];
     const DiagTask tk = tasks[blockIdx.x];
     const int kb = tk.kb, ld = tk.ld;
     double* G = heap + tk.Doff;
-    const int LDS = NBMAX + 1;
-    for (int e = threadIdx.x; e < NBMAX * NBMAX; e += blockDim.x) {
-        int i = e % NBMAX, j = e / NBMAX;
-        D[i + j * LDS] = (i < kb && j < kb) ? G[i + (int64_t)j * ld] : (i == j ? 1.0 : 0.0);
-    }
+    const int ti = threadIdx.x & 15, tj = threadIdx.x >> 4;
+    const int i0 = 4 * ti, j0 = 4 * tj;
+    double a[4][4];   // a[r][c] = entry (i0 + r, j0 + c); outside kb x kb: identity
+#pragma unroll
+    for (int c = 0; c < 4; c++)
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            const int i = i0 + r, j = j0 + c;
+            a[r][c] = (i < kb && j < kb) ? G[i + (int64_t)j * ld] : (i == j ? 1.0 : 0.0);
+        }
+    if (ti == 0)
+#pragma unroll
+        for (int c = 0; c < 4; c++) rowb[0][j0 + c] = a[0][c];
+    if (tj == 0)
+#pragma unroll
+        for (int r = 0; r < 4; r++) colb[0][i0 + r] = a[r][0];
     __syncthreads();
-    const int i = threadIdx.x & 63;      // row owned by this thread
-    const int seg = threadIdx.x >> 6;    // 16-column segment
+    int nrep = 0;
     for (int k = 0; k < kb; k++) {
-        // row k and column k are final here; nobody writes them during this step
-        double p = D[k + k * LDS];
+        const int cur = k & 1;
+        double p = rowb[cur][k];
         if (fabs(p) < tiny) {
             p = p < 0 ? -tiny : tiny;
-            if (threadIdx.x == 0) atomicAdd(n_replaced, 1);
+            nrep++;
         }
-        double l = 0.0;
-        const int j0 = seg * 16;
-        if (i > k && i < kb && j0 + 15 > k) {
-            l = D[i + k * LDS] / p;
-            // stage both operands in registers first: the compiler cannot prove that the stores
-            // below do not alias the loads of the next iteration and would serialise them
-            double own[16], piv[16];
+        const double inv = 1.0 / p;
+        const int kq = k >> 2, kr = k & 3;
+        double l[4], u[4];
 #pragma unroll
-            for (int jj = 0; jj < 16; jj++) {
-                own[jj] = D[i + (j0 + jj) * LDS];
-                piv[jj] = D[k + (j0 + jj) * LDS];
-            }
+        for (int r = 0; r < 4; r++) l[r] = colb[cur][i0 + r] * inv;
 #pragma unroll
-            for (int jj = 0; jj < 16; jj++) {
-                int j = j0 + jj;
-                if (j > k && j < kb) D[i + j * LDS] = own[jj] - l * piv[jj];
-            }
-        } else if (i > k && i < kb) {
-            l = D[i + k * LDS] / p;
+        for (int c = 0; c < 4; c++) u[c] = rowb[cur][j0 + c];
+#pragma unroll
+        for (int r = 0; r < 4; r++)
+#pragma unroll
+            for (int c = 0; c < 4; c++)
+                if (i0 + r > k && j0 + c > k) a[r][c] -= l[r] * u[c];
+        if (tj == kq) {   // column k: multipliers below the diagonal, the (possibly replaced) pivot on it
+#pragma unroll
+            for (int r = 0; r < 4; r++)
+#pragma unroll
+                for (int c = 0; c < 4; c++)
+                    if (c == kr) {
+                        if (i0 + r > k) a[r][c] = l[r];
+                        else if (i0 + r == k) a[r][c] = p;
+                    }
+        }
+        if (k + 1 < kb) {   // publish row k + 1 and column k + 1 (final after this step's update)
+            const int nq = (k + 1) >> 2, nr = (k + 1) & 3;
+            if (ti == nq)
+#pragma unroll
+                for (int r = 0; r < 4; r++)
+                    if (r == nr)
+#pragma unroll
+                        for (int c = 0; c < 4; c++) rowb[cur ^ 1][j0 + c] = a[r][c];
+            if (tj == nq)
+#pragma unroll
+                for (int c = 0; c < 4; c++)
+                    if (c == nr)
+#pragma unroll
+                        for (int r = 0; r < 4; r++) colb[cur ^ 1][i0 + r] = a[r][c];
         }
         __syncthreads();
-        // column k is dead for the elimination now: store the multipliers / the (replaced) pivot
-        if (seg == 0 && i < kb) {
-            if (i > k) D[i + k * LDS] = l;
-            else if (i == k) D[k + k * LDS] = p;
-        }
     }
-    __syncthreads();
+    if (threadIdx.x == 0 && nrep) atomicAdd(n_replaced, nrep);
     // write back packed LU to Larr, U_kk^T to the UTarr diagonal block
     double* GU = heap + tk.UTDoff;
-    for (int e = threadIdx.x; e < kb * kb; e += blockDim.x) {
-        int a = e % kb, b = e / kb;
-        double v = D[a + b * LDS];
-        G[a + (int64_t)b * ld] = v;
-        if (a <= b) GU[b + (int64_t)a * ld] = v;   // U(a,b) -> UT[b,a]
-    }
+#pragma unroll
+    for (int c = 0; c < 4; c++)
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            const int i = i0 + r, j = j0 + c;
+            if (i < kb && j < kb) {
+                G[i + (int64_t)j * ld] = a[r][c];
+                if (i <= j) GU[j + (int64_t)i * ld] = a[r][c];   // U(i,j) -> UT[j,i]
+            }
+        }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -818,6 +850,385 @@ __global__ void __launch_bounds__(32 * SMALL_WARPS, NKP_SMALL_MINB) k_bwd_small(
             }
         }
         __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// small fronts, second generation: PERSISTENT CTAs, one front at a time per CTA, the panel streamed through shared
+// memory by 1-D bulk async copies (cp.async.bulk + mbarrier complete_tx -- the TMA engine without a tensor map: every
+// column of a panel is contiguous and 16-byte aligned because ld is even).
+//
+// A front is cut into JOBS; a job is what one ring stage holds: cc consecutive columns of pivot block k, rows from the
+// top of the block's diagonal block to the end of the front (one bulk copy per column, 1-6 KB each).
+//   forward : blocks and columns ascending.  The inverted diagonal block is lower triangular, so the columns of a job
+//             complete y_k for exactly their own rows (yk accumulates the contributions of the columns seen so far), and
+//             the rows below the block can be updated with those columns at once.
+//   backward: blocks and columns descending.  The job's rows below the block give z for its own columns; (U_kk^-1)(p, .)
+//             lies in column p and needs z of the same and of later columns, which are complete.
+// Thread 0 issues the copies of job q + SF_NST - 1 while the CTA works on job q; the job stream runs across front
+// boundaries (factor data are read-only), so the next front's first stages are already in flight when a front ends.
+// The work vector of the front (m x 8 right-hand sides) stays in shared memory; all products are DMMA m8n8k4 with
+// the right-hand sides as the N dimension, as in the other sweep kernels.  Two CTA barriers per job.
+// The first generation (k_fwd_small / k_bwd_small: one warp per front, fragments straight from global memory) was
+// latency bound: 0.8-2.3 TB/s at gx1v6-shape, 0.15 ms for a level of 20 fronts at gx3v7-shape.
+// ------------------------------------------------------------------------------------------
+
+// Two launch shapes of the same kernels:
+//   wide   256 threads, 4 stages of 36 KB, persistent (one CTA per SM): levels with few, larger fronts -- the pipeline
+//          inside a front and across consecutive fronts hides the latency;
+//   narrow 128 threads, 2 stages of 12 KB, one CTA per front, 3-4 CTAs per SM: levels with thousands of leaf-sized
+//          fronts, where several fronts in flight per SM hide each other's start-up and barrier latencies.
+constexpr int SF_MAXNST = 4;               // ring stages (upper bound)
+constexpr int SF_STAGE_WIDE = 4608, SF_NST_WIDE = 4, SF_STAGE_NARROW = 1536, SF_NST_NARROW = 2;
+constexpr int SF_MAXLD = 1024;             // fronts up to this leading dimension (work vector and >= 4 columns per wide stage)
+constexpr int SF_NARROW_MAXLD = 320;       // ... for the narrow shape (>= 4 columns per narrow stage)
+
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}\n" ::"r"(
+                     (unsigned)__cvta_generic_to_shared(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, unsigned bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                     (unsigned)__cvta_generic_to_shared(smem_dst)),
+                 "l"(gsrc), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+
+// column stride of a staged chunk with `rows` (even) rows: >= rows, == 4 (mod 16): conflict-light fragment loads both ways
+__host__ __device__ __forceinline__ int sf_cs(int rows) { return ((rows + 11) & ~15) + 4; }
+
+// Job iterator over the fronts of one CTA (task indices t0, t0 + stride, ...).  Used twice per CTA with identical
+// results: by the producer (thread 0, running ahead) and by all threads as consumers.
+template <bool FWD>
+struct SfJobs {
+    const SolveTask* tasks;
+    int ntasks, stride;
+    int t;                 // current task index (>= ntasks: exhausted)
+    int s, m, ld;
+    int64_t base;          // Loff (forward) / UToff (backward)
+    int k0, kb;            // current pivot block
+    int nch, ich;          // chunks of the block, current chunk
+    int j0, cc;            // first column of the chunk inside the block, number of columns
+    int cs, ccmax;
+    int stage, cccap;      // doubles per ring stage; largest number of columns per job (8 per warp of the CTA)
+    bool first_of_front;
+
+    __device__ void load_front() {
+        if (t >= ntasks) return;
+        const SolveTask& tk = tasks[t];
+        s = tk.s;
+        m = tk.m;
+        ld = tk.ld;
+        base = FWD ? tk.Loff : tk.UToff;
+        k0 = FWD ? 0 : ((s - 1) / 64) * 64;
+        enter_block();
+        first_of_front = true;
+    }
+    __device__ void enter_block() {
+        kb = min(64, s - k0);
+        cs = sf_cs(ld - k0);
+        ccmax = min(cccap, (stage / cs) & ~3);
+        nch = (kb + ccmax - 1) / ccmax;
+        ich = FWD ? 0 : nch - 1;
+        set_chunk();
+    }
+    __device__ void set_chunk() {
+        j0 = ich * ccmax;
+        cc = min(ccmax, kb - j0);
+    }
+    __device__ bool valid() const { return t < ntasks; }
+    __device__ bool first_of_block() const { return FWD ? ich == 0 : ich == nch - 1; }
+    __device__ bool last_job() const { return FWD ? (k0 + 64 >= s && ich == nch - 1) : (k0 == 0 && ich == 0); }
+    __device__ void next() {
+        first_of_front = false;
+        if (FWD) {
+            if (++ich < nch) {
+                set_chunk();
+                return;
+            }
+            if (k0 + 64 < s) {
+                k0 += 64;
+                enter_block();
+                return;
+            }
+        } else {
+            if (--ich >= 0) {
+                set_chunk();
+                return;
+            }
+            if (k0 > 0) {
+                k0 -= 64;
+                enter_block();
+                return;
+            }
+        }
+        t += stride;
+        load_front();
+    }
+};
+
+// copies of one job into a ring stage (called by thread 0 only): cc columns, rows [k0, ld)
+template <bool FWD>
+__device__ __forceinline__ void sf_issue(const SfJobs<FWD>& jb, const double* __restrict__ heap, double* stage, uint64_t* bar) {
+    const double* src = heap + jb.base + jb.k0 + (int64_t)(jb.k0 + jb.j0) * jb.ld;
+    const unsigned bytes = (unsigned)((jb.ld - jb.k0) * 8);
+    mbar_expect_tx(bar, (unsigned)jb.cc * bytes);
+    for (int c = 0; c < jb.cc; c++) bulk_g2s(stage + c * jb.cs, src + (int64_t)c * jb.ld, bytes, bar);
+}
+
+// FORWARD.  W, y as in the other sweep kernels.  Dynamic shared memory: w[wcap][8] | yk[64][8] | ring.
+template <int SF_THREADS, int MINB>
+__global__ void __launch_bounds__(SF_THREADS, MINB) k_fwd_front(const SolveTask* __restrict__ tasks, int ntasks,
+                                                             const SolveChild* __restrict__ children,
+                                                             const int* __restrict__ rel, const double* __restrict__ heap,
+                                                             double* W, double* y, int n, int nr, int nrtot, int wcap,
+                                                             int SF_NST, int SF_STAGE) {
+    constexpr int NW = SF_THREADS / 32;
+    extern __shared__ __align__(128) double sfm[];
+    __shared__ uint64_t full_bar[SF_MAXNST];
+    double* w = sfm;                       // w[a * 8 + c]
+    double* yk = w + (size_t)wcap * 8;     // y of the current pivot block: rows below the current chunk still accumulate
+    double* ring = yk + 512;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, lr = lane >> 2, lc = lane & 3;
+    if (tid == 0) {
+        for (int q = 0; q < SF_NST; q++) mbar_init(&full_bar[q], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
+    SfJobs<true> prod, jb;
+    prod.tasks = jb.tasks = tasks;
+    prod.ntasks = jb.ntasks = ntasks;
+    prod.stride = jb.stride = gridDim.x;
+    prod.t = jb.t = blockIdx.x;
+    prod.stage = jb.stage = SF_STAGE;
+    prod.cccap = jb.cccap = 8 * NW;
+    prod.load_front();
+    jb.load_front();
+    unsigned issued = 0, q = 0;
+    if (tid == 0)
+        for (; (int)issued < SF_NST - 1 && prod.valid(); issued++, prod.next())
+            sf_issue(prod, heap, ring + (issued % SF_NST) * SF_STAGE, &full_bar[issued % SF_NST]);
+    for (; jb.valid(); jb.next(), q++) {
+        const SolveTask tk = tasks[jb.t];
+        const int s = tk.s, m = tk.m;
+        if (jb.first_of_front) {
+            // right-hand side of the pivots, zero boundary part, then the children's update vectors (fixed order)
+            for (int a = tid; a < m; a += SF_THREADS)
+#pragma unroll
+                for (int c = 0; c < 8; c++) w[a * 8 + c] = (a < s && c < nr) ? y[tk.first + a + (int64_t)c * n] : 0.0;
+            for (int ch = 0; ch < tk.nchild; ch++) {
+                __syncthreads();
+                const SolveChild sc = children[tk.child_list + ch];
+                const int mc = sc.s + sc.r;
+                const double* wc = W + sc.woff * nrtot + sc.s;
+                const int* rl = rel + sc.rel_off;
+                for (int a = tid; a < sc.r; a += SF_THREADS) {
+                    const int d = rl[a];
+                    for (int c = 0; c < nr; c++) w[d * 8 + c] += wc[a + (int64_t)c * mc];
+                }
+            }
+        }
+        if (jb.first_of_block())
+            for (int e = tid; e < 512; e += SF_THREADS) yk[e] = 0.0;
+        __syncthreads();
+        // keep the ring full: the stage of job q - 1 is free (barrier at the end of that job)
+        if (tid == 0 && prod.valid()) {
+            fence_proxy_async();
+            sf_issue(prod, heap, ring + (issued % SF_NST) * SF_STAGE, &full_bar[issued % SF_NST]);
+            issued++;
+            prod.next();
+        }
+        const double* st = ring + (q % SF_NST) * SF_STAGE;
+        mbar_wait(&full_bar[q % SF_NST], (q / SF_NST) & 1);
+        const int k0 = jb.k0, kb = jb.kb, j0 = jb.j0, cc = jb.cc, cs = jb.cs;
+        const int nks = (cc + 3) >> 2;
+        // (1) yk[p] += sum over the job's columns q of Linv(p, q) v[q] for the rows p >= j0 of the block
+        //     (unit lower triangular inverse: Linv(p, p) = 1, Linv(p, q > p) = 0); warp -> rows 8 warp .. 8 warp + 7
+        for (int g8 = warp; g8 < 8; g8 += NW) {
+            if (8 * g8 + 7 < j0) continue;
+            const int p = 8 * g8 + lr;
+            double a0 = yk[p * 8 + 2 * lc], a1 = yk[p * 8 + 2 * lc + 1];
+#pragma unroll
+            for (int ks = 0; ks < 16; ks++) {
+                if (ks < nks) {
+                    const int col = 4 * ks + lc, qq = j0 + col;
+                    double av = 0.0;
+                    if (col < cc && p < kb) av = p == qq ? 1.0 : (p > qq ? st[col * cs + p] : 0.0);
+                    const double bv = col < cc ? w[(k0 + qq) * 8 + lr] : 0.0;
+                    dmma884(a0, a1, av, bv);
+                }
+            }
+            yk[p * 8 + 2 * lc] = a0;
+            yk[p * 8 + 2 * lc + 1] = a1;
+            if (p >= j0 && p < j0 + cc) {   // final for the rows of this job's own columns
+                if (2 * lc < nr) y[tk.first + k0 + p + (int64_t)(2 * lc) * n] = a0;
+                if (2 * lc + 1 < nr) y[tk.first + k0 + p + (int64_t)(2 * lc + 1) * n] = a1;
+            }
+        }
+        __syncthreads();
+        // (2) rows below the pivot block: w -= L[rows, j0 .. j0 + cc) y_k[j0 ..]
+        const int R0 = k0 + kb;
+        if (m > R0) {
+            double bneg[16];
+#pragma unroll
+            for (int ks = 0; ks < 16; ks++) {
+                const int col = 4 * ks + lc;
+                bneg[ks] = (ks < nks && col < cc) ? -yk[(j0 + col) * 8 + lr] : 0.0;
+            }
+            const int ngr = (m - R0 + 7) >> 3;
+            for (int g = warp; g < ngr; g += NW) {
+                const int row = R0 + 8 * g + lr;
+                const bool rok = row < m;
+                double c0 = rok ? w[row * 8 + 2 * lc] : 0.0, c1 = rok ? w[row * 8 + 2 * lc + 1] : 0.0;
+                const double* ap = st + (row - k0);
+#pragma unroll
+                for (int ks = 0; ks < 16; ks++) {
+                    if (ks < nks) {
+                        const int col = 4 * ks + lc;
+                        const double av = (rok && col < cc) ? ap[col * cs] : 0.0;
+                        dmma884(c0, c1, av, bneg[ks]);
+                    }
+                }
+                if (rok) {
+                    w[row * 8 + 2 * lc] = c0;
+                    w[row * 8 + 2 * lc + 1] = c1;
+                }
+            }
+        }
+        if (jb.last_job()) {
+            __syncthreads();
+            // boundary part of the work vector -> global (the parent's extend-add reads it)
+            double* wg = W + tk.woff * nrtot;
+            for (int a = s + tid; a < m; a += SF_THREADS)
+                for (int c = 0; c < nr; c++) wg[a + (int64_t)c * m] = w[a * 8 + c];
+        }
+        __syncthreads();
+    }
+}
+
+// BACKWARD.  Dynamic shared memory: w[wcap][8] | zk[64][8] | red[8][64] | ring.
+template <int SF_THREADS, int MINB>
+__global__ void __launch_bounds__(SF_THREADS, MINB) k_bwd_front(const SolveTask* __restrict__ tasks, int ntasks,
+                                                             const int* __restrict__ bidx, const double* __restrict__ heap,
+                                                             double* W, double* y, int n, int nr, int nrtot, int wcap,
+                                                             int SF_NST, int SF_STAGE) {
+    constexpr int NW = SF_THREADS / 32;
+    extern __shared__ __align__(128) double sfm[];
+    __shared__ uint64_t full_bar[SF_MAXNST];
+    double* w = sfm;
+    double* zk = w + (size_t)wcap * 8;     // z of the current pivot block (rows of finished columns)
+    double* red = zk + 512;                // one 8 x 8 partial block per warp
+    double* ring = red + 512;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, lr = lane >> 2, lc = lane & 3;
+    if (tid == 0) {
+        for (int q = 0; q < SF_NST; q++) mbar_init(&full_bar[q], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
+    SfJobs<false> prod, jb;
+    prod.tasks = jb.tasks = tasks;
+    prod.ntasks = jb.ntasks = ntasks;
+    prod.stride = jb.stride = gridDim.x;
+    prod.t = jb.t = blockIdx.x;
+    prod.stage = jb.stage = SF_STAGE;
+    prod.cccap = jb.cccap = 8 * NW;
+    prod.load_front();
+    jb.load_front();
+    unsigned issued = 0, q = 0;
+    if (tid == 0)
+        for (; (int)issued < SF_NST - 1 && prod.valid(); issued++, prod.next())
+            sf_issue(prod, heap, ring + (issued % SF_NST) * SF_STAGE, &full_bar[issued % SF_NST]);
+    for (; jb.valid(); jb.next(), q++) {
+        const SolveTask tk = tasks[jb.t];
+        const int s = tk.s, m = tk.m;
+        if (jb.first_of_front) {
+            // boundary values (solutions of the ancestors); the pivot part is filled block by block
+            const int* bi = bidx + tk.bidx_off;
+            for (int a = tid; a < tk.r; a += SF_THREADS) {
+                const int g = bi[a];
+#pragma unroll
+                for (int c = 0; c < 8; c++) w[(s + a) * 8 + c] = c < nr ? y[g + (int64_t)c * n] : 0.0;
+            }
+            __syncthreads();
+        }
+        if (tid == 0 && prod.valid()) {
+            fence_proxy_async();
+            sf_issue(prod, heap, ring + (issued % SF_NST) * SF_STAGE, &full_bar[issued % SF_NST]);
+            issued++;
+            prod.next();
+        }
+        const double* st = ring + (q % SF_NST) * SF_STAGE;
+        mbar_wait(&full_bar[q % SF_NST], (q / SF_NST) & 1);
+        const int k0 = jb.k0, kb = jb.kb, j0 = jb.j0, cc = jb.cc, cs = jb.cs;
+        const int R0 = k0 + kb;
+        const int ng = (cc + 7) >> 3;                          // column groups of 8 in this job (<= 8)
+        // (1) z[p] = y[p] - sum over the rows below the block of UT[row, p] x_row, for the job's columns p:
+        //     warp = (column group, row slice); the slices are added through shared memory in a fixed order
+        const int nsl = ng <= 1 ? NW : (ng <= 2 ? NW / 2 : (ng <= 4 ? (NW >= 4 ? NW / 4 : 1) : 1));   // row slices per group (ng <= NW)
+        {
+            const int grp = warp / nsl, sl = warp - grp * nsl;
+            double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
+            if (grp < ng && m > R0) {
+                const int p = 8 * grp + lr;                        // column inside the job
+                const int nst4 = (m - R0 + 3) >> 2;                // steps of 4 rows
+                const double* ap = st + (p < cc ? p : 0) * cs + kb;
+                for (int kk = sl; kk < nst4; kk += 2 * nsl) {
+                    {
+                        const int row = R0 + 4 * kk + lc;
+                        const double av = (p < cc && row < m) ? ap[4 * kk + lc] : 0.0;
+                        const double bv = row < m ? w[row * 8 + lr] : 0.0;
+                        dmma884(a0, a1, av, bv);
+                    }
+                    const int k2 = kk + nsl;
+                    if (k2 < nst4) {
+                        const int row = R0 + 4 * k2 + lc;
+                        const double av = (p < cc && row < m) ? ap[4 * k2 + lc] : 0.0;
+                        const double bv = row < m ? w[row * 8 + lr] : 0.0;
+                        dmma884(b0, b1, av, bv);
+                    }
+                }
+                a0 += b0;
+                a1 += b1;
+            }
+            red[warp * 64 + lr * 8 + 2 * lc] = a0;
+            red[warp * 64 + lr * 8 + 2 * lc + 1] = a1;
+        }
+        __syncthreads();
+        for (int e = tid; e < ng * 64; e += SF_THREADS) {
+            const int g2 = e >> 6, rc = e & 63;
+            const int p = 8 * g2 + (rc >> 3), c = rc & 7;
+            if (p < cc) {
+                double sum = 0.0;
+                for (int s2 = 0; s2 < nsl; s2++) sum += red[(g2 * nsl + s2) * 64 + rc];
+                zk[(j0 + p) * 8 + c] = (c < nr ? y[tk.first + k0 + j0 + p + (int64_t)c * n] : 0.0) - sum;
+            }
+        }
+        __syncthreads();
+        // (2) x[p] = sum over q >= p of Uinv(p, q) z[q] for the job's columns p; Uinv(p, q) is row q of staged column p
+        if (warp < ng) {
+            const int pl = 8 * warp + lr, p = j0 + pl;             // column inside the job / inside the block
+            double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+            for (int ks = 0; ks < 16; ks++) {
+                if (4 * ks + 3 >= j0 + 8 * warp) {
+                    const int qq = 4 * ks + lc;
+                    double av = 0.0;
+                    if (pl < cc && qq < kb && qq >= p) av = st[pl * cs + qq];
+                    const double bv = (qq < kb && qq >= j0) ? zk[qq * 8 + lr] : 0.0;   // rows before j0: not computed yet
+                    dmma884(a0, a1, av, bv);
+                }
+            }
+            if (pl < cc) {
+                w[(k0 + p) * 8 + 2 * lc] = a0;
+                w[(k0 + p) * 8 + 2 * lc + 1] = a1;
+                if (2 * lc < nr) y[tk.first + k0 + p + (int64_t)(2 * lc) * n] = a0;
+                if (2 * lc + 1 < nr) y[tk.first + k0 + p + (int64_t)(2 * lc + 1) * n] = a1;
+            }
+        }
+        __syncthreads();
     }
 }
 

@@ -214,6 +214,7 @@ struct LevelPlan {
 struct Options {
     int nb = 64;           // pivot block width (inner panel)
     int outer = 8;         // inner panels per outer block (wide Schur updates use K = outer*nb)
+    int top_outer = 8;     // the same for the distributed top fronts (multi-GPU): width of a distribution block / nb
     int leaf = 96;         // stop dissecting below this many unknowns
     int tm = 128, tn = 64; // GEMM tile (must match the kernel)
     int trsm_rows = 128;   // rows per TRSM CTA

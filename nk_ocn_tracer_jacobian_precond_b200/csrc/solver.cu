@@ -173,6 +173,10 @@ struct nkp_solver {
     DiagTask* d_inv = nullptr;            // diagonal blocks inverted after the factorisation
     int epoch = 0;
     int coop_ctas = 0;          // co-resident CTAs for the dataflow sweeps
+    int num_sms = 0;
+    int small_v1 = 0;           // NKP_SMALL_V1: bit 0 / bit 1 = first-generation warp-per-front kernel for the forward /
+                                // backward sweep of the small fronts (A/B against k_fwd_front / k_bwd_front)
+    std::vector<int> small_wcap;   // per level: largest m of its small fronts (shared-memory work vector of k_*_front)
     ncclComm_t comm = nullptr;  // multi-GPU only
     int rank = 0, nranks = 1;
     std::vector<ncclComm_t> gcomm;   // per Plan::groups entry: communicator of the group (null: this rank is not in it, or size 1)
@@ -318,7 +322,8 @@ static int create_impl(nkp_solver** out, int n, const int* rowptr, const int* co
     s->nranks = nranks;
     if (getenv("NKP_BIG_ENTRIES")) po.big_entries = atoll(getenv("NKP_BIG_ENTRIES"));
     if (getenv("NKP_BIG_ROWS")) po.big_rows = atoi(getenv("NKP_BIG_ROWS"));
-    if (getenv("NKP_OUTER")) po.outer = std::max(1, atoi(getenv("NKP_OUTER")));
+    if (getenv("NKP_OUTER")) po.outer = po.top_outer = std::max(1, atoi(getenv("NKP_OUTER")));
+    if (getenv("NKP_TOP_OUTER")) po.top_outer = std::max(1, atoi(getenv("NKP_TOP_OUTER")));
     if (getenv("NKP_SPLIT_TOL")) po.split_tol = atof(getenv("NKP_SPLIT_TOL"));
     if (getenv("NKP_SPLIT_MAX")) po.split_max = std::max(1, atoi(getenv("NKP_SPLIT_MAX")));
     const int* coords[3] = {ci, cj, ck};
@@ -424,6 +429,26 @@ static int create_impl(nkp_solver** out, int n, const int* rowptr, const int* co
                 return NKP_ECUDA;
             }
             s->coop_ctas = prop.multiProcessorCount * std::min(minocc, 2);
+            s->num_sms = prop.multiProcessorCount;
+            s->small_v1 = getenv("NKP_SMALL_V1") ? atoi(getenv("NKP_SMALL_V1")) : 0;
+            s->small_wcap.assign(P.nlevels, 0);
+            int wmax = 0;
+            for (int l = 0; l < P.nlevels; l++) {
+                int w = 0;
+                for (int q = P.levels[l].small_begin; q < P.levels[l].small_end; q++) w = std::max(w, P.solve_small[q].ld);
+                s->small_wcap[l] = (w + 15) & ~15;
+                wmax = std::max(wmax, s->small_wcap[l]);
+            }
+            if (wmax > SF_MAXLD || sf_cs(wmax) * 4 > SF_STAGE_WIDE) {
+                g_err = "a small front exceeds the shared-memory work vector of the front sweep kernels";
+                return NKP_EANALYSIS;
+            }
+            const int sf_smem = (int)(sizeof(double) * ((size_t)wmax * 8 + 1024 + (size_t)SF_NST_WIDE * SF_STAGE_WIDE));
+            const int sf_smem_n = (int)(sizeof(double) * ((size_t)SF_NARROW_MAXLD * 8 + 1024 + (size_t)SF_NST_NARROW * SF_STAGE_NARROW));
+            CK(cudaFuncSetAttribute(k_fwd_front<256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, sf_smem));
+            CK(cudaFuncSetAttribute(k_bwd_front<256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, sf_smem));
+            CK(cudaFuncSetAttribute(k_fwd_front<128, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, sf_smem_n));
+            CK(cudaFuncSetAttribute(k_bwd_front<128, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, sf_smem_n));
         }
         CK(cudaMalloc((void**)&s->d_val, sizeof(double) * (size_t)s->nnz));
         CK(cudaMalloc((void**)&s->d_R, sizeof(double) * n));
@@ -872,8 +897,22 @@ static int sweeps(nkp_solver* s) {
         }
         int nsmall = L.small_end - L.small_begin;
         if (nsmall > 0) {
-            k_fwd_small<<<(nsmall + SMALL_WARPS - 1) / SMALL_WARPS, 32 * SMALL_WARPS, 0, st>>>(
-                s->d_small + L.small_begin, nsmall, s->d_children, s->d_rel, s->heap, s->d_W, s->d_y, s->n, nr, nrtot);
+            if (s->small_v1 & 1) {
+                k_fwd_small<<<(nsmall + SMALL_WARPS - 1) / SMALL_WARPS, 32 * SMALL_WARPS, 0, st>>>(
+                    s->d_small + L.small_begin, nsmall, s->d_children, s->d_rel, s->heap, s->d_W, s->d_y, s->n, nr, nrtot);
+            } else {
+                const int wcap = s->small_wcap[l];
+                if (nsmall > 4 * s->num_sms && wcap <= SF_NARROW_MAXLD) {
+                    const size_t smem = sizeof(double) * ((size_t)wcap * 8 + 512 + (size_t)SF_NST_NARROW * SF_STAGE_NARROW);
+                    k_fwd_front<128, 4><<<nsmall, 128, smem, st>>>(s->d_small + L.small_begin, nsmall, s->d_children, s->d_rel, s->heap,
+                                                                   s->d_W, s->d_y, s->n, nr, nrtot, wcap, SF_NST_NARROW, SF_STAGE_NARROW);
+                } else {
+                    const size_t smem = sizeof(double) * ((size_t)wcap * 8 + 512 + (size_t)SF_NST_WIDE * SF_STAGE_WIDE);
+                    k_fwd_front<256, 1><<<std::min(nsmall, s->num_sms), 256, smem, st>>>(
+                        s->d_small + L.small_begin, nsmall, s->d_children, s->d_rel, s->heap, s->d_W, s->d_y, s->n, nr, nrtot, wcap,
+                        SF_NST_WIDE, SF_STAGE_WIDE);
+                }
+            }
             s->launches++;
             mark("fwd small", l, nsmall);
         }
@@ -899,8 +938,22 @@ static int sweeps(nkp_solver* s) {
         const LevelPlan& L = P.levels[l];
         int nsmall = L.small_end - L.small_begin;
         if (nsmall > 0) {
-            k_bwd_small<<<(nsmall + SMALL_WARPS - 1) / SMALL_WARPS, 32 * SMALL_WARPS, 0, st>>>(
-                s->d_small + L.small_begin, nsmall, s->d_bidx, s->heap, s->d_W, s->d_y, s->n, nr, nrtot);
+            if (s->small_v1 & 2) {
+                k_bwd_small<<<(nsmall + SMALL_WARPS - 1) / SMALL_WARPS, 32 * SMALL_WARPS, 0, st>>>(
+                    s->d_small + L.small_begin, nsmall, s->d_bidx, s->heap, s->d_W, s->d_y, s->n, nr, nrtot);
+            } else {
+                const int wcap = s->small_wcap[l];
+                if (nsmall > 4 * s->num_sms && wcap <= SF_NARROW_MAXLD) {
+                    const size_t smem = sizeof(double) * ((size_t)wcap * 8 + 1024 + (size_t)SF_NST_NARROW * SF_STAGE_NARROW);
+                    k_bwd_front<128, 4><<<nsmall, 128, smem, st>>>(s->d_small + L.small_begin, nsmall, s->d_bidx, s->heap, s->d_W, s->d_y,
+                                                                   s->n, nr, nrtot, wcap, SF_NST_NARROW, SF_STAGE_NARROW);
+                } else {
+                    const size_t smem = sizeof(double) * ((size_t)wcap * 8 + 1024 + (size_t)SF_NST_WIDE * SF_STAGE_WIDE);
+                    k_bwd_front<256, 1><<<std::min(nsmall, s->num_sms), 256, smem, st>>>(
+                        s->d_small + L.small_begin, nsmall, s->d_bidx, s->heap, s->d_W, s->d_y, s->n, nr, nrtot, wcap, SF_NST_WIDE,
+                        SF_STAGE_WIDE);
+                }
+            }
             s->launches++;
             mark("bwd small", l, nsmall);
         }

@@ -159,7 +159,8 @@ int nkp_sim_run_dist(int n, const int* rowptr, const int* colind, const double* 
     opt.nb = nb;
     opt.leaf = leaf;
     if (opt.tn > nb) opt.tn = nb;
-    if (getenv("NKP_OUTER")) opt.outer = atoi(getenv("NKP_OUTER"));
+    if (getenv("NKP_OUTER")) opt.outer = opt.top_outer = atoi(getenv("NKP_OUTER"));
+    if (getenv("NKP_TOP_OUTER")) opt.top_outer = atoi(getenv("NKP_TOP_OUTER"));
     if (getenv("NKP_SPLIT_TOL")) opt.split_tol = atof(getenv("NKP_SPLIT_TOL"));
     if (getenv("NKP_SPLIT_MAX")) opt.split_max = atoi(getenv("NKP_SPLIT_MAX"));
     if (getenv("NKP_SIM_TM")) opt.tm = atoi(getenv("NKP_SIM_TM"));
@@ -451,7 +452,8 @@ int nkp_sim_partition(int n, const int* rowptr, const int* colind, const int* ci
     if (opt.tn > nb) opt.tn = nb;
     opt.rank = rank;
     opt.nranks = nranks;
-    if (getenv("NKP_OUTER")) opt.outer = atoi(getenv("NKP_OUTER"));
+    if (getenv("NKP_OUTER")) opt.outer = opt.top_outer = atoi(getenv("NKP_OUTER"));
+    if (getenv("NKP_TOP_OUTER")) opt.top_outer = atoi(getenv("NKP_TOP_OUTER"));
     if (getenv("NKP_SPLIT_TOL")) opt.split_tol = atof(getenv("NKP_SPLIT_TOL"));
     if (getenv("NKP_SPLIT_MAX")) opt.split_max = atoi(getenv("NKP_SPLIT_MAX"));
     const int* coords[3] = {ci, cj, ck};
