@@ -193,95 +193,112 @@ __global__ void __launch_bounds__(256) k_extend_add(const AddTask* __restrict__ 
 
 constexpr int NBMAX = 64;
 
-// The whole block lives in registers: thread (ti, tj) of a 16 x 16 grid owns the 4 x 4 tile of rows 4 ti .. and
-// columns 4 tj ...  Step k: the pivot row and the (unscaled) pivot column are published through a double-buffered
-// pair of 64-entry shared-memory vectors, every thread forms the reciprocal of the pivot and its four multipliers
-// itself and updates its tile with 16 FMAs -- ONE CTA barrier per column and no shared-memory traffic for the
-// trailing matrix (the first version kept the block in shared memory: 37 us per block on the critical path of every
-// panel; this one takes about a quarter of that).
+// Blocked right-looking LU with 8-column micro-panels: the micro-panel (rows below included) is factored by ONE warp in
+// registers (lane = two rows, pivot row broadcast by shuffles, no barrier inside), the 8 x rest row block of U by one
+// thread per column, the rank-8 trailing update by 4 x 4 register tiles: 3 CTA barriers per 8 columns.
+// scripts/diag_bench.cu measured four designs on B200 (one CTA, 8 dependent launches, per launch): column-by-column in
+// shared memory 35 us (round 1), 4 x 4 register tiles with one barrier per column 46-50 us, one warp holding the
+// whole block 56 us, this one 27 us.  The floor is the chain of dependent FP64 operations per pivot (update of the
+// next pivot, reciprocal, multiplier, update), which costs several hundred cycles on this part.
 __global__ void __launch_bounds__(256) k_diag(const DiagTask* __restrict__ tasks, double* __restrict__ heap,
                                               double tiny, int* __restrict__ n_replaced) {
-    __shared__ __align__(16) double rowb[2][NBMAX], colb[2][NBMAX];
+    __shared__ double D[NBMAX * (NBMAX + 1)];
     const DiagTask tk = tasks[blockIdx.x];
     const int kb = tk.kb, ld = tk.ld;
     double* G = heap + tk.Doff;
-    const int ti = threadIdx.x & 15, tj = threadIdx.x >> 4;
-    const int i0 = 4 * ti, j0 = 4 * tj;
-    double a[4][4];   // a[r][c] = entry (i0 + r, j0 + c); outside kb x kb: identity
-#pragma unroll
-    for (int c = 0; c < 4; c++)
-#pragma unroll
-        for (int r = 0; r < 4; r++) {
-            const int i = i0 + r, j = j0 + c;
-            a[r][c] = (i < kb && j < kb) ? G[i + (int64_t)j * ld] : (i == j ? 1.0 : 0.0);
-        }
-    if (ti == 0)
-#pragma unroll
-        for (int c = 0; c < 4; c++) rowb[0][j0 + c] = a[0][c];
-    if (tj == 0)
-#pragma unroll
-        for (int r = 0; r < 4; r++) colb[0][i0 + r] = a[r][0];
+    constexpr int LDS = NBMAX + 1;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int e = tid; e < NBMAX * NBMAX; e += 256) {
+        int i = e % NBMAX, j = e / NBMAX;
+        D[i + j * LDS] = (i < kb && j < kb) ? G[i + (int64_t)j * ld] : (i == j ? 1.0 : 0.0);
+    }
     __syncthreads();
     int nrep = 0;
-    for (int k = 0; k < kb; k++) {
-        const int cur = k & 1;
-        double p = rowb[cur][k];
-        if (fabs(p) < tiny) {
-            p = p < 0 ? -tiny : tiny;
-            nrep++;
+    for (int j0 = 0; j0 < kb; j0 += 8) {
+        if (warp == 0) {
+            const int r0 = j0 + lane, r1 = j0 + lane + 32;
+            double a0[8], a1[8];
+#pragma unroll
+            for (int c = 0; c < 8; c++) {
+                a0[c] = r0 < NBMAX ? D[r0 + (j0 + c) * LDS] : 0.0;
+                a1[c] = r1 < NBMAX ? D[r1 + (j0 + c) * LDS] : 0.0;
+            }
+#pragma unroll
+            for (int c = 0; c < 8; c++) {
+                double p = __shfl_sync(0xffffffffu, a0[c], c);
+                if (fabs(p) < tiny) {
+                    p = p < 0 ? -tiny : tiny;
+                    nrep++;
+                }
+                const double inv = 1.0 / p;
+                const double l0 = lane > c ? a0[c] * inv : 0.0, l1 = a1[c] * inv;
+                if (lane == c) a0[c] = p;
+                if (lane > c) a0[c] = l0;
+                a1[c] = l1;
+#pragma unroll
+                for (int j = c + 1; j < 8; j++) {
+                    const double u = __shfl_sync(0xffffffffu, a0[j], c);
+                    a0[j] -= l0 * u;
+                    a1[j] -= l1 * u;
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < 8; c++) {
+                if (r0 < NBMAX) D[r0 + (j0 + c) * LDS] = a0[c];
+                if (r1 < NBMAX) D[r1 + (j0 + c) * LDS] = a1[c];
+            }
         }
-        const double inv = 1.0 / p;
-        const int kq = k >> 2, kr = k & 3;
-        double l[4], u[4];
+        __syncthreads();
+        const int nrem = NBMAX - j0 - 8;   // rows / columns beyond the micro-panel
+        if (tid < nrem) {   // U12 = L11^-1 A12, one column per thread
+            const int j = j0 + 8 + tid;
+            double x[8];
 #pragma unroll
-        for (int r = 0; r < 4; r++) l[r] = colb[cur][i0 + r] * inv;
+            for (int i = 0; i < 8; i++) x[i] = D[j0 + i + j * LDS];
 #pragma unroll
-        for (int c = 0; c < 4; c++) u[c] = rowb[cur][j0 + c];
+            for (int i = 1; i < 8; i++)
 #pragma unroll
-        for (int r = 0; r < 4; r++)
+                for (int k = 0; k < i; k++) x[i] -= D[j0 + i + (j0 + k) * LDS] * x[k];
+#pragma unroll
+            for (int i = 1; i < 8; i++) D[j0 + i + j * LDS] = x[i];
+        }
+        __syncthreads();
+        const int nt = nrem >> 2;
+        if (tid < nt * nt) {   // A22 -= L21 U12, 4 x 4 tile per thread
+            const int ti = tid % nt, tj = tid / nt;
+            const int i0 = j0 + 8 + 4 * ti, c0 = j0 + 8 + 4 * tj;
+            double acc[4][4];
 #pragma unroll
             for (int c = 0; c < 4; c++)
-                if (i0 + r > k && j0 + c > k) a[r][c] -= l[r] * u[c];
-        if (tj == kq) {   // column k: multipliers below the diagonal, the (possibly replaced) pivot on it
 #pragma unroll
-            for (int r = 0; r < 4; r++)
+                for (int r = 0; r < 4; r++) acc[r][c] = D[i0 + r + (c0 + c) * LDS];
 #pragma unroll
-                for (int c = 0; c < 4; c++)
-                    if (c == kr) {
-                        if (i0 + r > k) a[r][c] = l[r];
-                        else if (i0 + r == k) a[r][c] = p;
-                    }
-        }
-        if (k + 1 < kb) {   // publish row k + 1 and column k + 1 (final after this step's update)
-            const int nq = (k + 1) >> 2, nr = (k + 1) & 3;
-            if (ti == nq)
+            for (int k = 0; k < 8; k++) {
+                double l[4], u[4];
+#pragma unroll
+                for (int r = 0; r < 4; r++) l[r] = D[i0 + r + (j0 + k) * LDS];
+#pragma unroll
+                for (int c = 0; c < 4; c++) u[c] = D[j0 + k + (c0 + c) * LDS];
 #pragma unroll
                 for (int r = 0; r < 4; r++)
-                    if (r == nr)
 #pragma unroll
-                        for (int c = 0; c < 4; c++) rowb[cur ^ 1][j0 + c] = a[r][c];
-            if (tj == nq)
+                    for (int c = 0; c < 4; c++) acc[r][c] -= l[r] * u[c];
+            }
 #pragma unroll
-                for (int c = 0; c < 4; c++)
-                    if (c == nr)
+            for (int c = 0; c < 4; c++)
 #pragma unroll
-                        for (int r = 0; r < 4; r++) colb[cur ^ 1][i0 + r] = a[r][c];
+                for (int r = 0; r < 4; r++) D[i0 + r + (c0 + c) * LDS] = acc[r][c];
         }
         __syncthreads();
     }
-    if (threadIdx.x == 0 && nrep) atomicAdd(n_replaced, nrep);
-    // write back packed LU to Larr, U_kk^T to the UTarr diagonal block
+    if (tid == 0 && nrep) atomicAdd(n_replaced, nrep);
     double* GU = heap + tk.UTDoff;
-#pragma unroll
-    for (int c = 0; c < 4; c++)
-#pragma unroll
-        for (int r = 0; r < 4; r++) {
-            const int i = i0 + r, j = j0 + c;
-            if (i < kb && j < kb) {
-                G[i + (int64_t)j * ld] = a[r][c];
-                if (i <= j) GU[j + (int64_t)i * ld] = a[r][c];   // U(i,j) -> UT[j,i]
-            }
-        }
+    for (int e = tid; e < kb * kb; e += 256) {
+        int a = e % kb, b = e / kb;
+        double v = D[a + b * LDS];
+        G[a + (int64_t)b * ld] = v;
+        if (a <= b) GU[b + (int64_t)a * ld] = v;
+    }
 }
 
 // ------------------------------------------------------------------------------------------

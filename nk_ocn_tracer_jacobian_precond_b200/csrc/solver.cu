@@ -176,6 +176,7 @@ struct nkp_solver {
     int num_sms = 0;
     int small_v1 = 0;           // NKP_SMALL_V1: bit 0 / bit 1 = first-generation warp-per-front kernel for the forward /
                                 // backward sweep of the small fronts (A/B against k_fwd_front / k_bwd_front)
+    bool small_force = false;   // NKP_SMALL_FORCE=1: k_*_front for every level of small fronts (tests)
     std::vector<int> small_wcap;   // per level: largest m of its small fronts (shared-memory work vector of k_*_front)
     ncclComm_t comm = nullptr;  // multi-GPU only
     int rank = 0, nranks = 1;
@@ -431,6 +432,7 @@ static int create_impl(nkp_solver** out, int n, const int* rowptr, const int* co
             s->coop_ctas = prop.multiProcessorCount * std::min(minocc, 2);
             s->num_sms = prop.multiProcessorCount;
             s->small_v1 = getenv("NKP_SMALL_V1") ? atoi(getenv("NKP_SMALL_V1")) : 0;
+            s->small_force = getenv("NKP_SMALL_FORCE") && atoi(getenv("NKP_SMALL_FORCE"));
             s->small_wcap.assign(P.nlevels, 0);
             int wmax = 0;
             for (int l = 0; l < P.nlevels; l++) {
@@ -897,7 +899,9 @@ static int sweeps(nkp_solver* s) {
         }
         int nsmall = L.small_end - L.small_begin;
         if (nsmall > 0) {
-            if (s->small_v1 & 1) {
+            // few, larger fronts: persistent CTAs + bulk-copy ring; thousands of leaf-sized fronts: one warp per front
+            // (measured: gx3v7-shape 20 fronts 0.150 -> 0.035 ms, 520 fronts 0.129 -> 0.088 ms; 2 093 leaves 0.114 vs 0.148 ms)
+            if ((s->small_v1 & 1) || (!s->small_force && nsmall > 4 * s->num_sms)) {
                 k_fwd_small<<<(nsmall + SMALL_WARPS - 1) / SMALL_WARPS, 32 * SMALL_WARPS, 0, st>>>(
                     s->d_small + L.small_begin, nsmall, s->d_children, s->d_rel, s->heap, s->d_W, s->d_y, s->n, nr, nrtot);
             } else {
@@ -938,7 +942,7 @@ static int sweeps(nkp_solver* s) {
         const LevelPlan& L = P.levels[l];
         int nsmall = L.small_end - L.small_begin;
         if (nsmall > 0) {
-            if (s->small_v1 & 2) {
+            if ((s->small_v1 & 2) || (!s->small_force && nsmall > 4 * s->num_sms)) {
                 k_bwd_small<<<(nsmall + SMALL_WARPS - 1) / SMALL_WARPS, 32 * SMALL_WARPS, 0, st>>>(
                     s->d_small + L.small_begin, nsmall, s->d_bidx, s->heap, s->d_W, s->d_y, s->n, nr, nrtot);
             } else {

@@ -174,6 +174,110 @@ __global__ void __launch_bounds__(32) diag_v2(const DiagTask* __restrict__ tasks
     }
 }
 
+
+// ---- v3: blocked right-looking LU, 8-column micro-panels: the panel is factored by ONE warp in registers (shuffles,
+// no barrier inside), the row block of U by one thread per column, the rank-8 trailing update by 4 x 4 register tiles.
+// 3 barriers per 8 columns instead of 8.
+__global__ void __launch_bounds__(256) diag_v3(const DiagTask* __restrict__ tasks, double* __restrict__ heap, double tiny, int* __restrict__ n_replaced) {
+    __shared__ double D[NBMAX * (NBMAX + 1)];
+    const DiagTask tk = tasks[blockIdx.x];
+    const int kb = tk.kb, ld = tk.ld;
+    double* G = heap + tk.Doff;
+    constexpr int LDS = NBMAX + 1;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int e = tid; e < NBMAX * NBMAX; e += 256) {
+        int i = e % NBMAX, j = e / NBMAX;
+        D[i + j * LDS] = (i < kb && j < kb) ? G[i + (int64_t)j * ld] : (i == j ? 1.0 : 0.0);
+    }
+    __syncthreads();
+    int nrep = 0;
+    for (int j0 = 0; j0 < kb; j0 += 8) {
+        if (warp == 0) {
+            const int r0 = j0 + lane, r1 = j0 + lane + 32;
+            double a0[8], a1[8];
+#pragma unroll
+            for (int c = 0; c < 8; c++) {
+                a0[c] = r0 < NBMAX ? D[r0 + (j0 + c) * LDS] : 0.0;
+                a1[c] = r1 < NBMAX ? D[r1 + (j0 + c) * LDS] : 0.0;
+            }
+#pragma unroll
+            for (int c = 0; c < 8; c++) {
+                double p = __shfl_sync(0xffffffffu, a0[c], c);
+                if (fabs(p) < tiny) {
+                    p = p < 0 ? -tiny : tiny;
+                    nrep++;
+                }
+                const double inv = 1.0 / p;
+                const double l0 = lane > c ? a0[c] * inv : 0.0, l1 = a1[c] * inv;
+                if (lane == c) a0[c] = p;
+                if (lane > c) a0[c] = l0;
+                a1[c] = l1;
+#pragma unroll
+                for (int j = c + 1; j < 8; j++) {
+                    const double u = __shfl_sync(0xffffffffu, a0[j], c);
+                    a0[j] -= l0 * u;
+                    a1[j] -= l1 * u;
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < 8; c++) {
+                if (r0 < NBMAX) D[r0 + (j0 + c) * LDS] = a0[c];
+                if (r1 < NBMAX) D[r1 + (j0 + c) * LDS] = a1[c];
+            }
+        }
+        __syncthreads();
+        const int nrem = NBMAX - j0 - 8;   // rows / columns beyond the micro-panel
+        if (tid < nrem) {   // U12 = L11^-1 A12, one column per thread
+            const int j = j0 + 8 + tid;
+            double x[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) x[i] = D[j0 + i + j * LDS];
+#pragma unroll
+            for (int i = 1; i < 8; i++)
+#pragma unroll
+                for (int k = 0; k < i; k++) x[i] -= D[j0 + i + (j0 + k) * LDS] * x[k];
+#pragma unroll
+            for (int i = 1; i < 8; i++) D[j0 + i + j * LDS] = x[i];
+        }
+        __syncthreads();
+        const int nt = nrem >> 2;
+        if (tid < nt * nt) {   // A22 -= L21 U12, 4 x 4 tile per thread
+            const int ti = tid % nt, tj = tid / nt;
+            const int i0 = j0 + 8 + 4 * ti, c0 = j0 + 8 + 4 * tj;
+            double acc[4][4];
+#pragma unroll
+            for (int c = 0; c < 4; c++)
+#pragma unroll
+                for (int r = 0; r < 4; r++) acc[r][c] = D[i0 + r + (c0 + c) * LDS];
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                double l[4], u[4];
+#pragma unroll
+                for (int r = 0; r < 4; r++) l[r] = D[i0 + r + (j0 + k) * LDS];
+#pragma unroll
+                for (int c = 0; c < 4; c++) u[c] = D[j0 + k + (c0 + c) * LDS];
+#pragma unroll
+                for (int r = 0; r < 4; r++)
+#pragma unroll
+                    for (int c = 0; c < 4; c++) acc[r][c] -= l[r] * u[c];
+            }
+#pragma unroll
+            for (int c = 0; c < 4; c++)
+#pragma unroll
+                for (int r = 0; r < 4; r++) D[i0 + r + (c0 + c) * LDS] = acc[r][c];
+        }
+        __syncthreads();
+    }
+    if (tid == 0 && nrep) atomicAdd(n_replaced, nrep);
+    double* GU = heap + tk.UTDoff;
+    for (int e = tid; e < kb * kb; e += 256) {
+        int a = e % kb, b = e / kb;
+        double v = D[a + b * LDS];
+        G[a + (int64_t)b * ld] = v;
+        if (a <= b) GU[b + (int64_t)a * ld] = v;
+    }
+}
+
 __global__ void k_empty(const DiagTask*, double*, double, int*) {}
 
 int main() {
@@ -195,7 +299,7 @@ int main() {
     typedef void (*kern_t)(const DiagTask*, double*, double, int*);
     struct V { const char* name; kern_t k; int threads; } vs[] = {
         {"empty", k_empty, 32}, {"v0 smem", diag_v0, 256}, {"v1 reg div", diag_v1<0>, 256}, {"v1 reg drcp", diag_v1<1>, 256},
-        {"v1 reg approx+newton", diag_v1<2>, 256}, {"v2 one warp", diag_v2, 32}};
+        {"v1 reg approx+newton", diag_v1<2>, 256}, {"v2 one warp", diag_v2, 32}, {"v3 blocked 8", diag_v3, 256}};
     for (auto& v : vs) {
         for (int grid : {1, 8, 2048}) {
             float best = 1e9;
