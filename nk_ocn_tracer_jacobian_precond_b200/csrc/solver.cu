@@ -169,9 +169,12 @@ struct nkp_solver {
     BigItem* d_bwd_items = nullptr;
     BigItem* d_rect_items = nullptr;
     double* d_part = nullptr;   // 64 x 8 partial products of the backward sweep's rectangular part
+    cudaGraphExec_t sweep_graph[4] = {nullptr, nullptr, nullptr, nullptr};   // per NR in {1, 2, 4, 8}
+    int64_t sweep_graph_launches[4] = {0, 0, 0, 0};
+    bool use_graphs = false;   // NKP_GRAPHS=1: replay the single-GPU sweep sequence as a CUDA graph (experimental, see sweeps())
+    unsigned* d_queue = nullptr;          // item queues of the dataflow sweep launches (3 per level)
     unsigned long long* d_cnt = nullptr;  // progress counters of the big fronts: [0, nbig) forward, [nbig, 2 nbig) backward
     DiagTask* d_inv = nullptr;            // diagonal blocks inverted after the factorisation
-    int epoch = 0;
     int coop_ctas = 0;          // co-resident CTAs for the dataflow sweeps
     int num_sms = 0;
     int small_v1 = 0;           // NKP_SMALL_V1: bit 0 / bit 1 = first-generation warp-per-front kernel for the forward /
@@ -414,6 +417,7 @@ static int create_impl(nkp_solver** out, int n, const int* rowptr, const int* co
         if (upload(&s->d_inv, P.inv_tasks)) return NKP_ECUDA;
         CK(cudaMalloc((void**)&s->d_cnt, sizeof(unsigned long long) * (2 * P.big_fronts.size() + 2)));
         CK(cudaMemset(s->d_cnt, 0, sizeof(unsigned long long) * (2 * P.big_fronts.size() + 2)));
+        CK(cudaMalloc((void**)&s->d_queue, sizeof(unsigned) * 3 * (size_t)std::max(P.nlevels, 1)));
         {
             cudaDeviceProp prop;
             CK(cudaGetDeviceProperties(&prop, o.device));
@@ -433,6 +437,7 @@ static int create_impl(nkp_solver** out, int n, const int* rowptr, const int* co
             s->num_sms = prop.multiProcessorCount;
             s->small_v1 = getenv("NKP_SMALL_V1") ? atoi(getenv("NKP_SMALL_V1")) : 0;
             s->small_force = getenv("NKP_SMALL_FORCE") && atoi(getenv("NKP_SMALL_FORCE"));
+            if (getenv("NKP_GRAPHS")) s->use_graphs = atoi(getenv("NKP_GRAPHS")) != 0;
             s->small_wcap.assign(P.nlevels, 0);
             int wmax = 0;
             for (int l = 0; l < P.nlevels; l++) {
@@ -851,12 +856,17 @@ int nkp_factor_be(nkp_solver* s, const void* nzval_be) {
 }
 
 // forward + backward sweeps on d_y (n x nr, permuted, scaled), in place
+// The launch sequence of one forward + backward sweep pair (static for a given plan and NR).
 template <int NR>
-static int sweeps(nkp_solver* s) {
+static int sweeps_launch(nkp_solver* s) {
     Plan& P = s->plan;
     cudaStream_t st = s->stream;
-    s->epoch++;
-    int epoch = s->epoch;
+    // progress counters and item queues start from zero in every sweep, so that every kernel argument is the same from
+    // call to call and the whole sequence can be replayed as a CUDA graph (the tag in the counters' upper half stays 1)
+    const int epoch = 1;
+    // which dataflow launches take their items from a device-wide queue (bit 0 forward, bit 2 backward triangles); the
+    // independent, equally sized rectangle items keep the static round-robin
+    const int dyn = getenv("NKP_SWEEP_DYN") ? atoi(getenv("NKP_SWEEP_DYN")) : 5;
     int n = s->n;
     const bool trace = s->opt.verbose >= 3;
     std::vector<cudaEvent_t> tev;
@@ -874,6 +884,9 @@ static int sweeps(nkp_solver* s) {
     mark("start", -1, 0);
     unsigned long long* cnt_f = s->d_cnt;
     unsigned long long* cnt_b = s->d_cnt + P.big_fronts.size();
+    // item queues of the dataflow launches: [level] forward, [2 nlevels + level] backward triangles
+    CK(cudaMemsetAsync(s->d_queue, 0, sizeof(unsigned) * 3 * (size_t)P.nlevels, st));
+    CK(cudaMemsetAsync(s->d_cnt, 0, sizeof(unsigned long long) * (2 * P.big_fronts.size() + 2), st));
     unsigned uepoch = (unsigned)epoch;
     int nr = NR, nrtot = NR;
     const double* heap = s->heap;
@@ -930,8 +943,9 @@ static int sweeps(nkp_solver* s) {
             double* y = s->d_y;
             double* part = s->d_part;
             const int* clo = s->d_clo;
+            unsigned* queue = (dyn & 1) ? s->d_queue + l : nullptr;
             void* args[] = {(void*)&bfs, (void*)&items, (void*)&nitems, (void*)&ch,    (void*)&rel,   (void*)&clo,   (void*)&heap, (void*)&W,
-                            (void*)&y,   (void*)&part,  (void*)&n,      (void*)&nr,    (void*)&nrtot, (void*)&cnt_f, (void*)&uepoch};
+                            (void*)&y,   (void*)&part,  (void*)&n,      (void*)&nr,    (void*)&nrtot, (void*)&cnt_f, (void*)&uepoch, (void*)&queue};
             int grid = std::min(nitems, s->coop_ctas);
             CK(cudaLaunchCooperativeKernel((void*)k_sweep_big<SWEEP_FWD>, dim3(grid), dim3(256), args, SW_SMEM, st));
             s->launches++;
@@ -983,13 +997,14 @@ static int sweeps(nkp_solver* s) {
                 // rectangular part: independent items, plain launch
                 k_sweep_big<SWEEP_BWD_RECT><<<std::min(nrect, 8 * s->coop_ctas), 256, SW_SMEM, st>>>(
                     s->d_big, s->d_rect_items + L.rect_item_begin, nrect, ch, rel, s->d_clo, heap, W, y, part, n, nr, nrtot,
-                    cnt_b, uepoch);
+                    cnt_b, uepoch, nullptr);
                 s->launches++;
                 mark("bwd rect", l, nrect);
             }
             const int* clo = s->d_clo;
+            unsigned* queue = (dyn & 4) ? s->d_queue + 2 * P.nlevels + l : nullptr;
             void* args[] = {(void*)&bfs, (void*)&items, (void*)&nitems, (void*)&ch,    (void*)&rel,   (void*)&clo,   (void*)&heap, (void*)&W,
-                            (void*)&y,   (void*)&part,  (void*)&n,      (void*)&nr,    (void*)&nrtot, (void*)&cnt_b, (void*)&uepoch};
+                            (void*)&y,   (void*)&part,  (void*)&n,      (void*)&nr,    (void*)&nrtot, (void*)&cnt_b, (void*)&uepoch, (void*)&queue};
             int grid = std::min(nitems, s->coop_ctas);
             CK(cudaLaunchCooperativeKernel((void*)k_sweep_big<SWEEP_BWD_TRI>, dim3(grid), dim3(256), args, SW_SMEM, st));
             s->launches++;
@@ -1023,6 +1038,40 @@ static int sweeps(nkp_solver* s) {
         }
         for (cudaEvent_t e : tev) cudaEventDestroy(e);
     }
+    return 0;
+}
+
+// One GPU: the sweep pair is about 60 launches whose arguments never change; with NKP_GRAPHS=1 it is captured once
+// per NR into a CUDA graph and replayed.  Measured (profiles/r02_sweep_graph_experiment.txt): gx3v7-shape sweep pair
+// 2.65 -> 2.54 ms, all parity tests green; gx1v6-shape NO gain (23.4 ms either way) and replays produced NaNs there
+// that the plain launches of the same kernels with the same arguments never do -- not understood yet, so the graph
+// path is OFF by default.  Several GPUs (NCCL calls in the sequence), tracing, or a failed capture: plain launches.
+template <int NR>
+static int sweeps(nkp_solver* s) {
+    const int slot = NR == 1 ? 0 : (NR == 2 ? 1 : (NR == 4 ? 2 : 3));
+    const bool want_graph = s->nranks == 1 && s->opt.verbose < 3 && s->use_graphs;
+    if (!want_graph) return sweeps_launch<NR>(s);
+    if (!s->sweep_graph[slot]) {
+        cudaGraph_t g = nullptr;
+        const int64_t launches0 = s->launches;
+        bool ok = cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+        int rc = ok ? sweeps_launch<NR>(s) : NKP_ECUDA;
+        if (ok && cudaStreamEndCapture(s->stream, &g) != cudaSuccess) rc = NKP_ECUDA;
+        if (rc == 0 && g && cudaGraphInstantiate(&s->sweep_graph[slot], g, 0) != cudaSuccess) rc = NKP_ECUDA;
+        if (g) cudaGraphDestroy(g);
+        if (rc != 0 || !s->sweep_graph[slot]) {
+            cudaGetLastError();      // capture is not available here: remember that and launch directly
+            s->sweep_graph[slot] = nullptr;
+            s->use_graphs = false;
+            s->launches = launches0;
+            if (s->opt.verbose) fprintf(stderr, "[nkp] CUDA graph capture of the sweeps failed; using plain launches\n");
+            return sweeps_launch<NR>(s);
+        }
+        s->sweep_graph_launches[slot] = s->launches - launches0;
+        s->launches = launches0;
+    }
+    CK(cudaGraphLaunch(s->sweep_graph[slot], s->stream));
+    s->launches += s->sweep_graph_launches[slot];
     return 0;
 }
 
@@ -1495,6 +1544,8 @@ void nkp_destroy(nkp_solver* s) {
     if (!s) return;
     cudaSetDevice(s->opt.device);
     if (s->stream) cudaStreamSynchronize(s->stream);
+    for (cudaGraphExec_t& ge : s->sweep_graph)
+        if (ge) cudaGraphExecDestroy(ge);
     if (s->cstream) cudaStreamSynchronize(s->cstream);
     for (ncclComm_t c : s->gcomm)
         if (c && c != s->comm) ncclCommDestroy(c);
@@ -1509,7 +1560,7 @@ void nkp_destroy(nkp_solver* s) {
                     s->d_bidx, s->d_rel,    s->d_R,      s->d_C,      s->d_diag, s->d_trsm,    s->d_gemm,
                     s->d_add,  s->d_solve,  s->d_children, s->d_W,    s->d_y,    s->d_r,       s->d_x,
                     s->d_xb,   s->d_berr,   s->d_nrepl,  s->d_small,  s->d_big,  s->d_fwd_items, s->d_bwd_items,
-                    s->d_cnt,  s->d_inv,    s->d_rect_items, s->d_part, s->d_clo, s->d_sumsq};
+                    s->d_cnt,  s->d_inv,    s->d_rect_items, s->d_part, s->d_clo, s->d_sumsq, s->d_queue};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (s->h_pinned) cudaFreeHost(s->h_pinned);
