@@ -84,18 +84,28 @@ def build_case(name, seed=1):
     if optset == "min":
         n, rp, ci, nz, (ii, jj, kk, _) = synth.assemble_crs(g, c)
     else:
-        gen_a = os.path.join(ROOT, "oracle", "_ref", "gen_A")
-        if not os.path.exists(gen_a):
-            raise RuntimeError("oracle/_ref/gen_A is missing (built by __graft_entry__.build() where /root/reference exists)")
-        full = synth.make_full_fields(g, c, seed=seed)
-        with tempfile.TemporaryDirectory(prefix="nkp_bench_") as td:
-            circ = os.path.join(td, "circ.nc")
-            synth.write_circ_file(circ, g, c, full)
-            del full
-            open(os.path.join(td, "opts.txt"), "w").write(synth.REFTEST_OPTS.format(circ=circ))
-            subprocess.check_call([gen_a, "-o", os.path.join(td, "opts.txt"), os.path.join(td, "A.nc")],
-                                  stdout=subprocess.DEVNULL)
-            m = synth.read_matrix_file(os.path.join(td, "A.nc"))
+        # one generation per node: local rank 0 writes the matrix file, the other ranks of a multi-GPU run read it
+        cache = os.path.join(tempfile.gettempdir(), f"nkp_case_{name}_seed{seed}.nc")
+        if int(os.environ.get("LOCAL_RANK", "0")) == 0 and not os.path.exists(cache):
+            gen_a = os.path.join(ROOT, "oracle", "_ref", "gen_A")
+            if not os.path.exists(gen_a):
+                raise RuntimeError("oracle/_ref/gen_A is missing (built by __graft_entry__.build() where /root/reference exists)")
+            full = synth.make_full_fields(g, c, seed=seed)
+            with tempfile.TemporaryDirectory(prefix="nkp_bench_") as td:
+                circ = os.path.join(td, "circ.nc")
+                synth.write_circ_file(circ, g, c, full)
+                del full
+                open(os.path.join(td, "opts.txt"), "w").write(synth.REFTEST_OPTS.format(circ=circ))
+                subprocess.check_call([gen_a, "-o", os.path.join(td, "opts.txt"), os.path.join(td, "A.nc")],
+                                      stdout=subprocess.DEVNULL)
+                os.replace(os.path.join(td, "A.nc"), cache + ".part")
+            os.replace(cache + ".part", cache)
+        t_wait = time.time()
+        while not os.path.exists(cache):
+            if time.time() - t_wait > 1800:
+                raise RuntimeError(f"{cache} did not appear (local rank 0 generates it)")
+            time.sleep(1.0)
+        m = synth.read_matrix_file(cache)
         rp, ci, nz = m["rowptr"].astype(np.int32), m["colind"].astype(np.int32), m["nzval_row_wise"].astype(np.float64)
         ii, jj, kk = (m["tracer_state_ind_to_" + q].astype(np.int32) for q in "ijk")
         n = len(rp) - 1

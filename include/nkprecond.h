@@ -182,6 +182,21 @@ int nkp_solve_fields(nkp_solver* s, double* const* fields, int nfields, double* 
  * dup_cnt.  Uses the current CUDA device. */
 int nkp_crs_finalize_device(int n, int* d_rowptr, int* d_colind, double* d_val, int strip_zeros, long long* nnz_out,
                             int* dup_cnt_out);
+/* Stencil values on the device for the generator's option set  adv_type centered / hmix_type const / vmix_type const /
+ * sink_type const_shallow <sink_rate> <sink_depth>  (what gen_sparse_matrix computes before its post-processing for
+ * that option set, src/matrix.c:3790-3827; bit-identical to gen_A after nkp_crs_finalize_device).  All pointers of
+ * nkp_min_fields are DEVICE pointers: KMT[jmt][imt]; the index maps of the matrix file (src/matrix.c:309-329);
+ * dz, z_t [km]; 2-D fields [jmt][imt]; velocities [km][jmt][imt] with fill_value marking land (src/matrix.c:984-1217).
+ * Writes rowptr (n + 1), colind and val in slot order (self, k-1, k+1, east, west, north, south), exact zeros kept;
+ * capacity = number of entries colind / val can hold (7 n always suffices); *nnz_out = entries written. */
+typedef struct nkp_min_fields {
+    int imt, jmt, km, n;
+    const int *KMT, *ind_i, *ind_j, *ind_k, *int3_to_tracer_state_ind;
+    const double *dz, *z_t, *TAREA, *HTE, *HUS, *HTN, *HUW, *DXU, *DYU, *UVEL, *VVEL, *WVEL;
+    double fill_value;
+} nkp_min_fields;
+int nkp_assemble_min_device(const nkp_min_fields* fields, double day_cnt, double sink_rate, double sink_depth,
+                            int* d_rowptr, int* d_colind, double* d_val, long long capacity, long long* nnz_out);
 /* count big-endian 32-bit integers in device memory -> host byte order, in place (NC_INT arrays of the matrix file). */
 int nkp_bswap32_device(void* d_data, long long count);
 

@@ -209,6 +209,165 @@ done:
     return rc;
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Stencil values on the device for the option set  adv_type centered / hmix_type const / vmix_type const /
+// sink_type const_shallow  (SURVEY.md appendix B "minimal input"): what gen_sparse_matrix computes between init_matrix and
+// sum_dup_vals (src/matrix.c:3790-3827) for that option set -- add_UTE_coeffs :1239-1273, add_VTN_coeffs :1320-1360,
+// add_WVEL_coeffs :1401-1430, adv_enforce_divfree :2094-2206, add_hmix_const :2656-2710, add_vmix_const :2978-3004,
+// add_sink_pure_diag :3084-3091 -- one thread per tracer-state entry, every floating-point operation in the reference's
+// order with explicit round-to-nearest intrinsics (no FMA contraction), so that the CRS after nkp_crs_finalize_device is
+// bit-identical to the file gen_A writes.  Rows come out in slot order (self, k-1, k+1, east, west, north, south;
+// absent neighbours skipped), exact zeros kept.  Two launches: slot counts (-> exclusive scan -> rowptr), then the fill.
+// With this, a Newton sequence on one sparsity pattern never leaves the GPU: new circulation fields -> values in
+// the same slots -> nkp_crs_finalize_device(strip_zeros = 0) -> nkp_factor_device.
+// ------------------------------------------------------------------------------------------------------------
+
+namespace {
+
+struct MinFields {
+    int imt, jmt, km, n;
+    const int *KMT, *ind_i, *ind_j, *ind_k, *int3;
+    const double *dz, *z_t, *TAREA, *HTE, *HUS, *HTN, *HUW, *DXU, *DYU, *UVEL, *VVEL, *WVEL;
+    double delta_t, year_cnt, sink_rate, sink_depth, fill;
+};
+
+__device__ __forceinline__ double fv0(double a, double fill) { return a == fill ? 0.0 : a; }
+__device__ __forceinline__ int kmu_of(const MinFields& f, int j, int i) {   // src/grid.c:187-203
+    if (j >= f.jmt - 1) return 0;
+    const int ip1 = i < f.imt - 1 ? i + 1 : 0;
+    const int a = f.KMT[j * f.imt + i], b = f.KMT[(j + 1) * f.imt + i];
+    const int c = f.KMT[j * f.imt + ip1], d = f.KMT[(j + 1) * f.imt + ip1];
+    return min(min(a, b), min(c, d));
+}
+// 0.5 * vel * len on U points below the sea floor of the U cell: 0
+__device__ __forceinline__ double half_transport(const MinFields& f, const double* vel, const double* len, int k, int j, int i) {
+    if (k >= kmu_of(f, j, i)) return 0.0;
+    const double v = fv0(vel[((int64_t)k * f.jmt + j) * f.imt + i], f.fill);
+    return __dmul_rn(__dmul_rn(0.5, v), len[j * f.imt + i]);
+}
+__device__ __forceinline__ double ute_at(const MinFields& f, int k, int j, int i) {   // load_UTE, src/matrix.c:1024-1031
+    if (j < 1 || j > f.jmt - 2) return 0.0;
+    return __dadd_rn(__dadd_rn(0.0, half_transport(f, f.UVEL, f.DYU, k, j, i)), half_transport(f, f.UVEL, f.DYU, k, j - 1, i));
+}
+__device__ __forceinline__ double vtn_at(const MinFields& f, int k, int j, int i) {   // load_VTN, src/matrix.c:1103-1111
+    if (j < 1 || j > f.jmt - 2) return 0.0;
+    const int im1 = i > 0 ? i - 1 : f.imt - 1;
+    return __dadd_rn(__dadd_rn(0.0, half_transport(f, f.VVEL, f.DXU, k, j, i)), half_transport(f, f.VVEL, f.DXU, k, j, im1));
+}
+__device__ __forceinline__ double w_at(const MinFields& f, int k, int j, int i) {   // load_WVEL, src/matrix.c:1168-1198
+    if (k >= f.km || k >= f.KMT[j * f.imt + i] || j == 0 || j == f.jmt - 1 || k == 0) return 0.0;
+    return __dadd_rn(0.0, fv0(f.WVEL[((int64_t)k * f.jmt + j) * f.imt + i], f.fill));
+}
+
+// MODE 0: number of slots of every row -> cnt;  MODE 1: fill colind / val at rowptr
+template <int MODE>
+__global__ void __launch_bounds__(256) k_assemble_min(MinFields f, int* __restrict__ cnt, const int* __restrict__ rowptr,
+                                                      int* __restrict__ colind, double* __restrict__ val) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= f.n) return;
+    const int i = f.ind_i[q], j = f.ind_j[q], k = f.ind_k[q];
+    const int imt = f.imt;
+    const int ip1 = i < imt - 1 ? i + 1 : 0, im1 = i > 0 ? i - 1 : imt - 1;
+    const bool has_up = k - 1 >= 0, has_dn = k + 1 < f.KMT[j * imt + i];
+    const bool has_e = k < f.KMT[j * imt + ip1], has_w = k < f.KMT[j * imt + im1];
+    const bool has_n = k < f.KMT[(j + 1) * imt + i], has_s = k < f.KMT[(j - 1) * imt + i];
+    if (MODE == 0) {
+        cnt[q] = 1 + has_up + has_dn + has_e + has_w + has_n + has_s;
+        return;
+    }
+    const double dt = f.delta_t, ta = f.TAREA[j * imt + i], dzk = f.dz[k];
+    auto adv = [&](double flux, double den, bool plus) {   // 0.0 -/+ (1 - w) * flux / den * delta_t, w = 0.5
+        const double t = __dmul_rn(__ddiv_rn(__dmul_rn(0.5, flux), den), dt);
+        return plus ? __dadd_rn(0.0, t) : __dsub_rn(0.0, t);
+    };
+    const double a_e = adv(ute_at(f, k, j, i), ta, false), a_w = adv(ute_at(f, k, j, im1), ta, true);
+    const double a_n = adv(vtn_at(f, k, j, i), ta, false), a_s = adv(vtn_at(f, k, j - 1, i), ta, true);
+    const double a_up = adv(w_at(f, k, j, i), dzk, false), a_dn = adv(w_at(f, k + 1, j, i), dzk, true);
+    // adv_enforce_divfree: self = -(sum of the present non-self slots in slot order)
+    double ssum = 0.0;
+    if (has_up) ssum = __dadd_rn(ssum, a_up);
+    if (has_dn) ssum = __dadd_rn(ssum, a_dn);
+    if (has_e) ssum = __dadd_rn(ssum, a_e);
+    if (has_w) ssum = __dadd_rn(ssum, a_w);
+    if (has_n) ssum = __dadd_rn(ssum, a_n);
+    if (has_s) ssum = __dadd_rn(ssum, a_s);
+    double v_self = -ssum;
+    // hmix const
+    const double ah = 4.0e6;
+    auto hm = [&](const double* num, const double* den, int jj, int ii) {
+        const double a = fv0(num[jj * imt + ii], f.fill), b = fv0(den[jj * imt + ii], f.fill);
+        return __dmul_rn(__ddiv_rn(__ddiv_rn(__dmul_rn(ah, a), b), ta), dt);
+    };
+    const double ce = has_e ? hm(f.HTE, f.HUS, j, i) : 0.0, cw = has_w ? hm(f.HTE, f.HUS, j, im1) : 0.0;
+    const double cn = has_n ? hm(f.HTN, f.HUW, j, i) : 0.0, cs = has_s ? hm(f.HTN, f.HUW, j - 1, i) : 0.0;
+    v_self = __dsub_rn(v_self, __dadd_rn(__dadd_rn(__dadd_rn(ce, cw), cn), cs));
+    // vmix const
+    const double vdc = 0.1;
+    const double dz_up = f.dz[max(k - 1, 0)], dz_dn = f.dz[min(k + 1, f.km - 1)];
+    const double ct = has_up ? __dmul_rn(__ddiv_rn(__ddiv_rn(vdc, __dmul_rn(0.5, __dadd_rn(dz_up, dzk))), dzk), dt) : 0.0;
+    const double cb = has_dn ? __dmul_rn(__ddiv_rn(__ddiv_rn(vdc, __dmul_rn(0.5, __dadd_rn(dzk, dz_dn))), dzk), dt) : 0.0;
+    v_self = __dsub_rn(v_self, __dadd_rn(ct, cb));
+    // sink const_shallow
+    if (f.z_t[k] < f.sink_depth) v_self = __dadd_rn(v_self, -__dmul_rn(f.year_cnt, f.sink_rate));
+    int p = rowptr[q];
+    auto put = [&](int col, double v) {
+        colind[p] = col;
+        val[p] = v;
+        p++;
+    };
+    auto nbr = [&](int jj, int ii) { return f.int3[((int64_t)k * f.jmt + jj) * imt + ii]; };
+    put(q, v_self);
+    if (has_up) put(q - 1, __dadd_rn(a_up, ct));
+    if (has_dn) put(q + 1, __dadd_rn(a_dn, cb));
+    if (has_e) put(nbr(j, ip1), __dadd_rn(a_e, ce));
+    if (has_w) put(nbr(j, im1), __dadd_rn(a_w, cw));
+    if (has_n) put(nbr(j + 1, i), __dadd_rn(a_n, cn));
+    if (has_s) put(nbr(j - 1, i), __dadd_rn(a_s, cs));
+}
+
+}  // namespace
+
+extern "C" int nkp_assemble_min_device(const nkp_min_fields* fd, double day_cnt, double sink_rate, double sink_depth,
+                                       int* d_rowptr, int* d_colind, double* d_val, long long capacity, long long* nnz_out) {
+    if (!fd || !d_rowptr || !d_colind || !d_val || fd->n <= 0 || fd->imt < 3 || fd->jmt < 3 || fd->km < 1) return NKP_EINVAL;
+    MinFields f;
+    f.imt = fd->imt; f.jmt = fd->jmt; f.km = fd->km; f.n = fd->n;
+    f.KMT = fd->KMT; f.ind_i = fd->ind_i; f.ind_j = fd->ind_j; f.ind_k = fd->ind_k; f.int3 = fd->int3_to_tracer_state_ind;
+    f.dz = fd->dz; f.z_t = fd->z_t; f.TAREA = fd->TAREA; f.HTE = fd->HTE; f.HUS = fd->HUS; f.HTN = fd->HTN; f.HUW = fd->HUW;
+    f.DXU = fd->DXU; f.DYU = fd->DYU; f.UVEL = fd->UVEL; f.VVEL = fd->VVEL; f.WVEL = fd->WVEL;
+    f.delta_t = 60.0 * 60.0 * 24.0 * day_cnt;
+    f.year_cnt = day_cnt / 365.0;
+    f.sink_rate = sink_rate;
+    f.sink_depth = sink_depth;
+    f.fill = fd->fill_value;
+    int rc = NKP_OK;
+    const int n = fd->n, g = (n + 255) / 256, nblocks = (n + SCAN_ITEMS - 1) / SCAN_ITEMS;
+    int *d_cnt = nullptr, *d_bsum = nullptr, *d_tot = nullptr;
+    int total = 0;
+    CKC(cudaMalloc((void**)&d_cnt, sizeof(int) * (size_t)n));
+    CKC(cudaMalloc((void**)&d_bsum, sizeof(int) * (size_t)nblocks));
+    CKC(cudaMalloc((void**)&d_tot, sizeof(int)));
+    k_assemble_min<0><<<g, 256>>>(f, d_cnt, nullptr, nullptr, nullptr);
+    k_scan_blocks<<<nblocks, SCAN_THREADS>>>(n, d_cnt, d_bsum);
+    k_scan_block_sums<<<1, SCAN_THREADS>>>(nblocks, d_bsum, d_tot);
+    k_scan_finish<<<(n + 1 + 255) / 256, 256>>>(n, d_cnt, d_bsum, d_tot, d_rowptr);
+    CKC(cudaMemcpy(&total, d_tot, sizeof(int), cudaMemcpyDeviceToHost));
+    if (nnz_out) *nnz_out = total;
+    if ((long long)total > capacity) {
+        g_crs_err = "nkp_assemble_min_device: colind / val capacity too small";
+        rc = NKP_ENOMEM;
+        goto done;
+    }
+    k_assemble_min<1><<<g, 256>>>(f, nullptr, d_rowptr, d_colind, d_val);
+    CKC(cudaGetLastError());
+    CKC(cudaDeviceSynchronize());
+done:
+    cudaFree(d_cnt);
+    cudaFree(d_bsum);
+    cudaFree(d_tot);
+    return rc;
+}
+
 extern "C" int nkp_bswap32_device(void* d_data, long long count) {
     if (!d_data || count < 0) return NKP_EINVAL;
     if (count == 0) return NKP_OK;

@@ -1325,8 +1325,7 @@ __global__ void __launch_bounds__(256, 2) k_sweep_big(const BigFront* __restrict
                                                       int nitems, const SolveChild* __restrict__ children,
                                                       const int* __restrict__ rel, const int* __restrict__ clo,
                                                       const double* __restrict__ heap, double* W, double* y, double* part,
-                                                      int n, int nr, int nrtot, unsigned long long* cnt, unsigned epoch,
-                                                      unsigned* queue) {
+                                                      int n, int nr, int nrtot, unsigned long long* cnt, unsigned epoch) {
     constexpr bool FWD = MODE == SWEEP_FWD;
     constexpr bool RECT = MODE == SWEEP_BWD_RECT;
     extern __shared__ __align__(16) double ring[];
@@ -1343,18 +1342,7 @@ __global__ void __launch_bounds__(256, 2) k_sweep_big(const BigFront* __restrict
     }
     __syncthreads();
     unsigned gbase = 0;   // tiles streamed by this CTA before the current item (ring position / barrier phase)
-    // queue != nullptr: items are handed out IN LIST ORDER from a device-wide queue: a CTA that waits for a chain link
-    // holds up only itself, the others keep streaming whatever is ready (with the static round-robin a waiting CTA also
-    // delays every later item it is going to process).  An item still only waits for items that precede it in the
-    // list, and those have been taken by CTAs that are resident (cooperative launch).  queue == nullptr: static
-    // round-robin (the independent rectangle items of the backward sweep).
-    __shared__ int s_item;
-    for (int it_static = blockIdx.x;; it_static += gridDim.x) {
-        __syncthreads();
-        if (tid == 0) s_item = queue ? (int)atomicAdd(queue, 1u) : it_static;
-        __syncthreads();
-        const int it = s_item;
-        if (it >= nitems) break;
+    for (int it = blockIdx.x; it < nitems; it += gridDim.x) {
         const BigItem item = items[it];
         const BigFront bf = bfs[item.front];
         const int s = bf.s, m = bf.m, ld = bf.ld;
@@ -1823,6 +1811,13 @@ __global__ void __launch_bounds__(256) k_pub_pack(const PubRange* __restrict__ r
             if (dir == 0) pk[(int64_t)c * len + i] = y[pr.lo + i + (int64_t)c * n];
             else y[pr.lo + i + (int64_t)c * n] = pk[(int64_t)c * len + i];
         }
+}
+
+// diagnostics (NKP_CHECK=1): number of non-finite entries
+__global__ void __launch_bounds__(256) k_count_nonfinite(const double* __restrict__ p, int64_t n, unsigned long long* __restrict__ out) {
+    unsigned long long c = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) c += !isfinite(p[i]);
+    if (c) atomicAdd(out, c);
 }
 
 // max |a| over the stored values (tiny-pivot threshold of an unequilibrated factorisation)

@@ -169,10 +169,7 @@ struct nkp_solver {
     BigItem* d_bwd_items = nullptr;
     BigItem* d_rect_items = nullptr;
     double* d_part = nullptr;   // 64 x 8 partial products of the backward sweep's rectangular part
-    cudaGraphExec_t sweep_graph[4] = {nullptr, nullptr, nullptr, nullptr};   // per NR in {1, 2, 4, 8}
-    int64_t sweep_graph_launches[4] = {0, 0, 0, 0};
-    bool use_graphs = false;   // NKP_GRAPHS=1: replay the single-GPU sweep sequence as a CUDA graph (experimental, see sweeps())
-    unsigned* d_queue = nullptr;          // item queues of the dataflow sweep launches (3 per level)
+    int epoch = 0;                        // sweep counter: tag in the upper half of the progress counters
     unsigned long long* d_cnt = nullptr;  // progress counters of the big fronts: [0, nbig) forward, [nbig, 2 nbig) backward
     DiagTask* d_inv = nullptr;            // diagonal blocks inverted after the factorisation
     int coop_ctas = 0;          // co-resident CTAs for the dataflow sweeps
@@ -417,7 +414,6 @@ static int create_impl(nkp_solver** out, int n, const int* rowptr, const int* co
         if (upload(&s->d_inv, P.inv_tasks)) return NKP_ECUDA;
         CK(cudaMalloc((void**)&s->d_cnt, sizeof(unsigned long long) * (2 * P.big_fronts.size() + 2)));
         CK(cudaMemset(s->d_cnt, 0, sizeof(unsigned long long) * (2 * P.big_fronts.size() + 2)));
-        CK(cudaMalloc((void**)&s->d_queue, sizeof(unsigned) * 3 * (size_t)std::max(P.nlevels, 1)));
         {
             cudaDeviceProp prop;
             CK(cudaGetDeviceProperties(&prop, o.device));
@@ -437,7 +433,6 @@ static int create_impl(nkp_solver** out, int n, const int* rowptr, const int* co
             s->num_sms = prop.multiProcessorCount;
             s->small_v1 = getenv("NKP_SMALL_V1") ? atoi(getenv("NKP_SMALL_V1")) : 0;
             s->small_force = getenv("NKP_SMALL_FORCE") && atoi(getenv("NKP_SMALL_FORCE"));
-            if (getenv("NKP_GRAPHS")) s->use_graphs = atoi(getenv("NKP_GRAPHS")) != 0;
             s->small_wcap.assign(P.nlevels, 0);
             int wmax = 0;
             for (int l = 0; l < P.nlevels; l++) {
@@ -569,6 +564,21 @@ int nkp_comm_unique_id(void* unique_id) {
 // blocks each member owns -- the block that is factored next first, so that its panel and its broadcast overlap
 // everybody's remaining update.  All NCCL calls go to the high-priority communication stream; events carry the
 // dependencies between it and the compute stream.
+// NKP_CHECK=1: count the non-finite entries of a device array and report them (diagnostics; synchronises)
+static void check_finite(nkp_solver* s, const char* what, const double* p, int64_t n) {
+    static const bool on = getenv("NKP_CHECK") != nullptr;
+    if (!on) return;
+    unsigned long long* d = nullptr;
+    unsigned long long h = 0;
+    cudaMalloc((void**)&d, sizeof(h));
+    cudaMemsetAsync(d, 0, sizeof(h), s->stream);
+    k_count_nonfinite<<<1024, 256, 0, s->stream>>>(p, n, d);
+    cudaMemcpyAsync(&h, d, sizeof(h), cudaMemcpyDeviceToHost, s->stream);
+    cudaStreamSynchronize(s->stream);
+    cudaFree(d);
+    if (h) fprintf(stderr, "[nkp] CHECK rank %d: %llu non-finite entries in %s\n", s->rank, h, what);
+}
+
 // verbose >= 2: timeline marks on the compute stream (name, event), printed after the factorisation
 static void trace_mark(nkp_solver* s, const char* what, int a, int b) {
     if (s->opt.verbose < 2) return;
@@ -763,6 +773,7 @@ static int do_factor(nkp_solver* s) {
     }
     CK(cudaEventRecord(s->ev[2], st));
     CK(cudaGetLastError());
+    check_finite(s, "the factors", s->heap, P.factor_len);
     int nrepl = 0;
     CK(cudaMemcpyAsync(&nrepl, s->d_nrepl, sizeof(int), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
@@ -856,17 +867,16 @@ int nkp_factor_be(nkp_solver* s, const void* nzval_be) {
 }
 
 // forward + backward sweeps on d_y (n x nr, permuted, scaled), in place
-// The launch sequence of one forward + backward sweep pair (static for a given plan and NR).
+// One forward + backward sweep pair.  The progress counters of the dataflow kernels carry the number of the sweep in
+// their upper half, so counters left over from earlier sweeps never have to be cleared.  (Handing the items out from a
+// device-wide queue and replaying the sequence as a CUDA graph were both tried this round and are NOT in the tree: the
+// item loop restructured for the queue produced intermittent NaNs at gx1v6-shape -- profiles/r02_sweep_graph_experiment.txt.)
 template <int NR>
-static int sweeps_launch(nkp_solver* s) {
+static int sweeps(nkp_solver* s) {
     Plan& P = s->plan;
     cudaStream_t st = s->stream;
-    // progress counters and item queues start from zero in every sweep, so that every kernel argument is the same from
-    // call to call and the whole sequence can be replayed as a CUDA graph (the tag in the counters' upper half stays 1)
-    const int epoch = 1;
-    // which dataflow launches take their items from a device-wide queue (bit 0 forward, bit 2 backward triangles); the
-    // independent, equally sized rectangle items keep the static round-robin
-    const int dyn = getenv("NKP_SWEEP_DYN") ? atoi(getenv("NKP_SWEEP_DYN")) : 5;
+    s->epoch++;
+    const int epoch = s->epoch;
     int n = s->n;
     const bool trace = s->opt.verbose >= 3;
     std::vector<cudaEvent_t> tev;
@@ -884,9 +894,6 @@ static int sweeps_launch(nkp_solver* s) {
     mark("start", -1, 0);
     unsigned long long* cnt_f = s->d_cnt;
     unsigned long long* cnt_b = s->d_cnt + P.big_fronts.size();
-    // item queues of the dataflow launches: [level] forward, [2 nlevels + level] backward triangles
-    CK(cudaMemsetAsync(s->d_queue, 0, sizeof(unsigned) * 3 * (size_t)P.nlevels, st));
-    CK(cudaMemsetAsync(s->d_cnt, 0, sizeof(unsigned long long) * (2 * P.big_fronts.size() + 2), st));
     unsigned uepoch = (unsigned)epoch;
     int nr = NR, nrtot = NR;
     const double* heap = s->heap;
@@ -943,9 +950,8 @@ static int sweeps_launch(nkp_solver* s) {
             double* y = s->d_y;
             double* part = s->d_part;
             const int* clo = s->d_clo;
-            unsigned* queue = (dyn & 1) ? s->d_queue + l : nullptr;
             void* args[] = {(void*)&bfs, (void*)&items, (void*)&nitems, (void*)&ch,    (void*)&rel,   (void*)&clo,   (void*)&heap, (void*)&W,
-                            (void*)&y,   (void*)&part,  (void*)&n,      (void*)&nr,    (void*)&nrtot, (void*)&cnt_f, (void*)&uepoch, (void*)&queue};
+                            (void*)&y,   (void*)&part,  (void*)&n,      (void*)&nr,    (void*)&nrtot, (void*)&cnt_f, (void*)&uepoch};
             int grid = std::min(nitems, s->coop_ctas);
             CK(cudaLaunchCooperativeKernel((void*)k_sweep_big<SWEEP_FWD>, dim3(grid), dim3(256), args, SW_SMEM, st));
             s->launches++;
@@ -997,14 +1003,13 @@ static int sweeps_launch(nkp_solver* s) {
                 // rectangular part: independent items, plain launch
                 k_sweep_big<SWEEP_BWD_RECT><<<std::min(nrect, 8 * s->coop_ctas), 256, SW_SMEM, st>>>(
                     s->d_big, s->d_rect_items + L.rect_item_begin, nrect, ch, rel, s->d_clo, heap, W, y, part, n, nr, nrtot,
-                    cnt_b, uepoch, nullptr);
+                    cnt_b, uepoch);
                 s->launches++;
                 mark("bwd rect", l, nrect);
             }
             const int* clo = s->d_clo;
-            unsigned* queue = (dyn & 4) ? s->d_queue + 2 * P.nlevels + l : nullptr;
             void* args[] = {(void*)&bfs, (void*)&items, (void*)&nitems, (void*)&ch,    (void*)&rel,   (void*)&clo,   (void*)&heap, (void*)&W,
-                            (void*)&y,   (void*)&part,  (void*)&n,      (void*)&nr,    (void*)&nrtot, (void*)&cnt_b, (void*)&uepoch, (void*)&queue};
+                            (void*)&y,   (void*)&part,  (void*)&n,      (void*)&nr,    (void*)&nrtot, (void*)&cnt_b, (void*)&uepoch};
             int grid = std::min(nitems, s->coop_ctas);
             CK(cudaLaunchCooperativeKernel((void*)k_sweep_big<SWEEP_BWD_TRI>, dim3(grid), dim3(256), args, SW_SMEM, st));
             s->launches++;
@@ -1038,40 +1043,6 @@ static int sweeps_launch(nkp_solver* s) {
         }
         for (cudaEvent_t e : tev) cudaEventDestroy(e);
     }
-    return 0;
-}
-
-// One GPU: the sweep pair is about 60 launches whose arguments never change; with NKP_GRAPHS=1 it is captured once
-// per NR into a CUDA graph and replayed.  Measured (profiles/r02_sweep_graph_experiment.txt): gx3v7-shape sweep pair
-// 2.65 -> 2.54 ms, all parity tests green; gx1v6-shape NO gain (23.4 ms either way) and replays produced NaNs there
-// that the plain launches of the same kernels with the same arguments never do -- not understood yet, so the graph
-// path is OFF by default.  Several GPUs (NCCL calls in the sequence), tracing, or a failed capture: plain launches.
-template <int NR>
-static int sweeps(nkp_solver* s) {
-    const int slot = NR == 1 ? 0 : (NR == 2 ? 1 : (NR == 4 ? 2 : 3));
-    const bool want_graph = s->nranks == 1 && s->opt.verbose < 3 && s->use_graphs;
-    if (!want_graph) return sweeps_launch<NR>(s);
-    if (!s->sweep_graph[slot]) {
-        cudaGraph_t g = nullptr;
-        const int64_t launches0 = s->launches;
-        bool ok = cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
-        int rc = ok ? sweeps_launch<NR>(s) : NKP_ECUDA;
-        if (ok && cudaStreamEndCapture(s->stream, &g) != cudaSuccess) rc = NKP_ECUDA;
-        if (rc == 0 && g && cudaGraphInstantiate(&s->sweep_graph[slot], g, 0) != cudaSuccess) rc = NKP_ECUDA;
-        if (g) cudaGraphDestroy(g);
-        if (rc != 0 || !s->sweep_graph[slot]) {
-            cudaGetLastError();      // capture is not available here: remember that and launch directly
-            s->sweep_graph[slot] = nullptr;
-            s->use_graphs = false;
-            s->launches = launches0;
-            if (s->opt.verbose) fprintf(stderr, "[nkp] CUDA graph capture of the sweeps failed; using plain launches\n");
-            return sweeps_launch<NR>(s);
-        }
-        s->sweep_graph_launches[slot] = s->launches - launches0;
-        s->launches = launches0;
-    }
-    CK(cudaGraphLaunch(s->sweep_graph[slot], s->stream));
-    s->launches += s->sweep_graph_launches[slot];
     return 0;
 }
 
@@ -1114,7 +1085,9 @@ static int solve_chunk(nkp_solver* s, double* dB, int ldb, int nr, double* berr_
     // x = 0-th solve
     if (nrp > nr) CK(cudaMemsetAsync(s->d_y, 0, sizeof(double) * (size_t)n * nrp, st));
     k_permute_in<<<g, 256, 0, st>>>(n, nr, s->d_perm, s->d_R, dB, ldb, s->d_y);
+    check_finite(s, "the right-hand side", s->d_y, (int64_t)n * nr);
     if (sweeps_nr(s, nrp)) return NKP_ECUDA;
+    check_finite(s, "the first sweep pair's result", s->d_y, (int64_t)n * nr);
     k_permute_out<<<g, 256, 0, st>>>(n, nr, s->d_perm, s->d_C, s->d_y, s->d_x, n, 0, 0xffu);
     s->launches += 2;
     double last[MAX_NR];
@@ -1161,7 +1134,9 @@ static int solve_chunk(nkp_solver* s, double* dB, int ldb, int nr, double* berr_
         if (!go || it >= s->opt.refine_max) break;
         it++;
         k_permute_in<<<g, 256, 0, st>>>(n, nr, s->d_perm, s->d_R, s->d_r, n, s->d_y);
+        check_finite(s, "a residual", s->d_y, (int64_t)n * nr);
         if (sweeps_nr(s, nrp)) return NKP_ECUDA;
+        check_finite(s, "a correction sweep's result", s->d_y, (int64_t)n * nr);
         unsigned active = 0;
         for (int c = 0; c < nr; c++)
             if (!done[c]) active |= 1u << c;
@@ -1544,8 +1519,6 @@ void nkp_destroy(nkp_solver* s) {
     if (!s) return;
     cudaSetDevice(s->opt.device);
     if (s->stream) cudaStreamSynchronize(s->stream);
-    for (cudaGraphExec_t& ge : s->sweep_graph)
-        if (ge) cudaGraphExecDestroy(ge);
     if (s->cstream) cudaStreamSynchronize(s->cstream);
     for (ncclComm_t c : s->gcomm)
         if (c && c != s->comm) ncclCommDestroy(c);
@@ -1560,7 +1533,7 @@ void nkp_destroy(nkp_solver* s) {
                     s->d_bidx, s->d_rel,    s->d_R,      s->d_C,      s->d_diag, s->d_trsm,    s->d_gemm,
                     s->d_add,  s->d_solve,  s->d_children, s->d_W,    s->d_y,    s->d_r,       s->d_x,
                     s->d_xb,   s->d_berr,   s->d_nrepl,  s->d_small,  s->d_big,  s->d_fwd_items, s->d_bwd_items,
-                    s->d_cnt,  s->d_inv,    s->d_rect_items, s->d_part, s->d_clo, s->d_sumsq, s->d_queue};
+                    s->d_cnt,  s->d_inv,    s->d_rect_items, s->d_part, s->d_clo, s->d_sumsq};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (s->h_pinned) cudaFreeHost(s->h_pinned);

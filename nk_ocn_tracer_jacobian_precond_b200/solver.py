@@ -24,6 +24,13 @@ class NkpOptions(C.Structure):
                 ("reserved", C.c_int * 8)]
 
 
+class NkpMinFields(C.Structure):
+    _fields_ = [("imt", C.c_int), ("jmt", C.c_int), ("km", C.c_int), ("n", C.c_int)] + \
+               [(k, C.c_void_p) for k in ("KMT", "ind_i", "ind_j", "ind_k", "int3_to_tracer_state_ind", "dz", "z_t", "TAREA",
+                                          "HTE", "HUS", "HTN", "HUW", "DXU", "DYU", "UVEL", "VVEL", "WVEL")] + \
+               [("fill_value", C.c_double)]
+
+
 class NkpStats(C.Structure):
     _fields_ = [("n", C.c_int), ("nnz", C.c_int64), ("n_fronts", C.c_int), ("n_levels", C.c_int),
                 ("max_front", C.c_int), ("nnz_lu", C.c_int64), ("factor_flops", C.c_double),
@@ -61,6 +68,8 @@ def load_library():
     lib.nkp_create_be.argtypes = [P(vp), C.c_int, C.c_longlong, vp, vp, P(C.c_int), P(C.c_int), P(C.c_int), P(NkpOptions)]
     lib.nkp_crs_finalize_device.argtypes = [C.c_int, vp, vp, vp, C.c_int, P(C.c_longlong), P(C.c_int)]
     lib.nkp_bswap32_device.argtypes = [vp, C.c_longlong]
+    lib.nkp_assemble_min_device.argtypes = [P(NkpMinFields), C.c_double, C.c_double, C.c_double, vp, vp, vp, C.c_longlong,
+                                            P(C.c_longlong)]
     lib.nkp_factor.argtypes = [vp, P(C.c_double)]
     lib.nkp_factor_be.argtypes = [vp, vp]
     lib.nkp_factor_device.argtypes = [vp, vp]
@@ -123,6 +132,23 @@ def crs_finalize_device(n, d_rowptr, d_colind, d_val, strip_zeros=True):
     _check(load_library().nkp_crs_finalize_device(int(n), C.c_void_p(d_rowptr), C.c_void_p(d_colind), C.c_void_p(d_val),
                                                   int(bool(strip_zeros)), C.byref(nnz), C.byref(dup)), "nkp_crs_finalize_device")
     return nnz.value, dup.value
+
+
+def assemble_min_device(shape, n, dev_ptrs, fill_value, d_rowptr, d_colind, d_val, capacity, day_cnt=365.0,
+                        sink_rate=365.0, sink_depth=10.0e2):
+    """nkp_assemble_min_device: stencil values of the centered / const / const / const_shallow option set on the device.
+    dev_ptrs maps the field names of nkp_min_fields to device addresses.  Returns the number of entries written."""
+    f = NkpMinFields()
+    f.imt, f.jmt, f.km = (int(v) for v in shape)
+    f.n = int(n)
+    for k, v in dev_ptrs.items():
+        setattr(f, k, int(v))
+    f.fill_value = float(fill_value)
+    nnz = C.c_longlong()
+    _check(load_library().nkp_assemble_min_device(C.byref(f), day_cnt, sink_rate, sink_depth, C.c_void_p(d_rowptr),
+                                                  C.c_void_p(d_colind), C.c_void_p(d_val), int(capacity), C.byref(nnz)),
+           "nkp_assemble_min_device")
+    return nnz.value
 
 
 class TracerJacobianSolver:

@@ -568,3 +568,55 @@ def test_create_from_file_byte_order(golden_matrix):
     with pytest.raises(solver.NkpError):     # host-order bytes are not a valid big-endian rowptr
         solver.TracerJacobianSolver(c["n"], c["rowptr"].astype("<i4").tobytes(), c["colind"].astype("<i4").tobytes(),
                                     coords=(c["i"], c["j"], c["k"]), file_byte_order=True)
+
+
+@pytest.mark.parametrize("shape,seed", [((20, 24, 10), 1), ((30, 34, 20), 2)])
+def test_device_assembly_is_bit_identical_to_gen_A(golden_matrix, shape, seed):
+    """nkp_assemble_min_device + nkp_crs_finalize_device: the value loops of gen_sparse_matrix (src/matrix.c:3790-3827) and
+    its post-processing for the centered / const / const / const_shallow option set, entirely on the device, give the
+    CRS the reference's gen_A writes bit for bit (golden file for 20x24x10; synth.assemble_crs, itself proved against
+    gen_A, for the second shape).  Then the Newton-sequence path: explicit zeros kept, same pattern, refactor from the
+    device arrays."""
+    import torch
+    from nk_ocn_tracer_jacobian_precond_b200 import solver, synth
+    c = synth_case(*shape, seed=seed)
+    g, circ = c["grid"], c["circ"]
+    n, km = c["n"], g["km"]
+    dev = {}
+    keep = []
+    def put(name, arr, dtype):
+        t = torch.tensor(np.ascontiguousarray(arr, dtype=dtype), device="cuda")
+        keep.append(t)
+        dev[name] = t.data_ptr()
+    put("KMT", g["KMT"], np.int32)
+    put("ind_i", c["i"], np.int32); put("ind_j", c["j"], np.int32); put("ind_k", c["k"], np.int32)
+    put("int3_to_tracer_state_ind", c["int3"], np.int32)
+    for name in ("dz", "z_t", "TAREA", "HTE", "HUS", "HTN", "HUW", "DXU", "DYU"):
+        put(name, g[name], np.float64)
+    for name in ("UVEL", "VVEL", "WVEL"):
+        put(name, circ[name], np.float64)
+    drp = torch.zeros(n + 1, dtype=torch.int32, device="cuda")
+    dci = torch.zeros(7 * n, dtype=torch.int32, device="cuda")
+    dv = torch.zeros(7 * n, dtype=torch.float64, device="cuda")
+    nnz_raw = solver.assemble_min_device((g["imt"], g["jmt"], km), n, dev, synth.FILL, drp.data_ptr(), dci.data_ptr(),
+                                         dv.data_ptr(), 7 * n)
+    n2, rp_raw, ci_raw, nz_raw, _ = synth.assemble_crs(g, circ, raw=True)
+    assert nnz_raw == len(nz_raw) and np.array_equal(drp.cpu().numpy(), rp_raw)
+    assert np.array_equal(dci.cpu().numpy()[:nnz_raw], ci_raw) and np.array_equal(dv.cpu().numpy()[:nnz_raw], nz_raw)
+    raw_v = dv.clone()
+    nnz, dup = solver.crs_finalize_device(n, drp.data_ptr(), dci.data_ptr(), dv.data_ptr(), True)
+    if shape == (20, 24, 10):
+        ref = dict(rowptr=golden_matrix["rowptr"], colind=golden_matrix["colind"], nzval=golden_matrix["nzval_row_wise"])
+    else:
+        ref = c
+    assert nnz == len(ref["nzval"]) and dup == 0
+    assert np.array_equal(drp.cpu().numpy(), ref["rowptr"]) and np.array_equal(dci.cpu().numpy()[:nnz], ref["colind"])
+    assert np.array_equal(dv.cpu().numpy()[:nnz], ref["nzval"])
+    # factor straight from the device-assembled values and solve
+    s = _solver(dict(c, rowptr=drp.cpu().numpy(), colind=dci.cpu().numpy()[:nnz]))
+    s.factor_device(dv.data_ptr())
+    b = np.random.default_rng(3).standard_normal(n)
+    x = b.copy(); s.solve(x)
+    xo = oracle_solve.solve(n, ref["rowptr"], ref["colind"], ref["nzval"], b)
+    assert np.linalg.norm(x - xo) / np.linalg.norm(xo) <= SOL_TOL
+    s.close()
