@@ -132,6 +132,30 @@ int nkp_create_dist(nkp_solver** out, int n, const int* rowptr, const int* colin
                     const int* coord_i, const int* coord_j, const int* coord_k,
                     const nkp_options* opt, int rank, int nranks, const void* unique_id);
 
+/* Static row permutation for a large diagonal -- what pdgssvx* does first under options->RowPerm = LargeDiag, the
+ * default that set_default_options_dist leaves and the reference keeps (src/solve_ABglobal.c:332-334,
+ * src/solve_ABdist.c:493-495): HSL MC64 job 5 (Duff & Koster 2001), independently implemented (csrc/rowperm.cpp).
+ * HOST function, no GPU involved.  rowmap[i] = the column whose diagonal position row i takes (the permutation that
+ * maximises the product of the diagonal magnitudes); row_scale / col_scale (may be NULL) receive the scalings from
+ * the dual variables: row_scale[i] * |a_ij| * col_scale[j] <= 1 everywhere, = 1 on the new diagonal.
+ * NKP_EANALYSIS: the matrix is structurally singular (empty row / column, no perfect matching). */
+int nkp_rowperm_largediag(int n, const int* rowptr, const int* colind, const double* nzval, int* rowmap,
+                          double* row_scale, double* col_scale);
+
+/* nkp_create / nkp_create_dist with a static row permutation: row i of the operand becomes row rowmap[i] of the
+ * matrix that is ordered and factored (from nkp_rowperm_largediag, or the caller's own -- SuperLU's MY_PERMR).
+ * row_scale / col_scale (both or neither) replace the solver's own equilibration in every factorisation of the
+ * handle -- SuperLU's SamePattern_SameRowPerm reuse of perm_r, R, C; they are rounded to powers of two.  Nothing
+ * else changes for the caller: values keep their CRS order, B, X, residuals and berr are in terms of the original
+ * rows.  nranks = 1: single GPU (unique_id may be NULL); otherwise as nkp_create_dist.
+ * The ordering then works on the pattern of the permuted matrix, which for this operator family is wider than the
+ * stencil (more fill); the default path (no row permutation, equilibration + tiny-pivot replacement + refinement)
+ * meets the reference's accuracy on every operand measured so far, see DESIGN.md section 2. */
+int nkp_create_rowperm(nkp_solver** out, int n, const int* rowptr, const int* colind,
+                       const int* coord_i, const int* coord_j, const int* coord_k, const nkp_options* opt,
+                       const int* rowmap, const double* row_scale, const double* col_scale,
+                       int rank, int nranks, const void* unique_id);
+
 /* Numeric factorisation from HOST values (nzval_row_wise, src/matrix.c:84), includes the
  * host->device copy.  Replaces pdgssvx*(nrhs = 0). */
 int nkp_factor(nkp_solver* s, const double* nzval);

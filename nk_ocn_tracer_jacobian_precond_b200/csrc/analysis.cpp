@@ -484,16 +484,36 @@ void set_analysis_cache_dir(const char* dir) {
     g_cache_dir = dir ? dir : "";
 }
 
-int analyse(int n, const int* rowptr, const int* colind, const int* const coords[3],
-            const Options& opt, Plan& plan) {
+int analyse(int n, const int* rowptr_in, const int* colind_in, const int* const coords[3],
+            const Options& opt, Plan& plan, const int* rowmap) {
     plan = Plan();
     plan.n = n;
-    plan.nnz = rowptr[n];
+    plan.nnz = rowptr_in[n];
     plan.opt = opt;
     const int nb = opt.nb;
     if (opt.tn > nb || nb % opt.tn != 0) return -2;
 
     double t0 = now_s();
+    // Static row permutation (rowperm.cpp): row i of A becomes row rowmap[i] of the matrix that is ordered and
+    // factored.  Ordering, symbolic phase and the ordering cache see the permuted pattern; the scatter map at the
+    // end is indexed by the caller's CRS, so the values never have to be reordered.
+    std::vector<int> rp2, ci2;
+    const int* rowptr = rowptr_in;
+    const int* colind = colind_in;
+    if (rowmap) {
+        std::vector<int> inv((size_t)n, -1);
+        for (int i = 0; i < n; i++) {
+            if (rowmap[i] < 0 || rowmap[i] >= n || inv[rowmap[i]] >= 0) return -8;   // not a permutation
+            inv[rowmap[i]] = i;
+        }
+        rp2.assign((size_t)n + 1, 0);
+        ci2.resize((size_t)plan.nnz);
+        for (int j = 0; j < n; j++) rp2[j + 1] = rp2[j] + (rowptr_in[inv[j] + 1] - rowptr_in[inv[j]]);
+        for (int j = 0; j < n; j++)
+            std::copy(colind_in + rowptr_in[inv[j]], colind_in + rowptr_in[inv[j] + 1], ci2.begin() + rp2[j]);
+        rowptr = rp2.data();
+        colind = ci2.data();
+    }
     Graph g;
     build_graph(n, rowptr, colind, g);
 
@@ -840,9 +860,9 @@ int analyse(int n, const int* rowptr, const int* colind, const int* const coords
         bool bad = false;
 #pragma omp parallel for schedule(dynamic, 8192) reduction(|| : bad)
         for (int i = 0; i < n; i++) {
-            int pi = plan.perm[i];
-            for (int p = rowptr[i]; p < rowptr[i + 1]; p++) {
-                int pj = plan.perm[colind[p]];
+            int pi = plan.perm[rowmap ? rowmap[i] : i];
+            for (int p = rowptr_in[i]; p < rowptr_in[i + 1]; p++) {
+                int pj = plan.perm[colind_in[p]];
                 int t = front_of[std::min(pi, pj)];
                 const Front& f = plan.fronts[t];
                 if (!stores(t)) {

@@ -228,7 +228,7 @@ print_options_dist (superlu_dist_options_t * o)
    printf ("**    Equil            : %4d\n", o->Equil);
    printf ("**    ParSymbFact      : %4d  (analysis runs on the host)\n", o->ParSymbFact);
    printf ("**    ColPerm          : %4d  (nested dissection, built in)\n", o->ColPerm);
-   printf ("**    RowPerm          : %4d  (static pivoting, no row permutation)\n", o->RowPerm);
+   printf ("**    RowPerm          : %4d  (static pivoting; LargeDiag row permutation only with NKP_ROWPERM=1)\n", o->RowPerm);
    printf ("**    ReplaceTinyPivot : %4d\n", o->ReplaceTinyPivot);
    printf ("**    IterRefine       : %4d\n", o->IterRefine);
    printf ("**************************************************\n");
@@ -422,7 +422,7 @@ load_coords (int n, int **ci, int **cj, int **ck)
 }
 
 static int
-create_and_factor (compat_state * cs, ScalePermstruct_t * sp, int *info)
+create_and_factor (compat_state * cs, superlu_dist_options_t * options, ScalePermstruct_t * sp, int *info)
 {
    int *ci = NULL, *cj = NULL, *ck = NULL;
    nkp_options o;
@@ -433,7 +433,35 @@ create_and_factor (compat_state * cs, ScalePermstruct_t * sp, int *info)
       o.verbose = 1;
    if (&dbg_lvl != NULL && dbg_lvl)
       printf ("(0) nkp: ordering = %s nested dissection\n", have ? "geometric (index maps of the matrix file)" : "graph");
-   rc = nkp_create (&cs->h, cs->n, cs->rowptr, cs->colind, have ? ci : NULL, have ? cj : NULL, have ? ck : NULL, &o);
+   /* options->RowPerm = LargeDiag is what set_default_options_dist leaves and the reference keeps
+    * (src/solve_ABglobal.c:332-334).  The B200 solver meets the reference's accuracy on this operator family without
+    * a row permutation (it only adds fill here), so the permutation is computed only on request:
+    * NKP_ROWPERM=1 in the environment.  perm_r then reports it, as SuperLU's ScalePermstruct does. */
+   if (options && options->RowPerm == LargeDiag && getenv ("NKP_ROWPERM") && atoi (getenv ("NKP_ROWPERM")) > 0) {
+      int *rowmap = (int *) malloc ((size_t) cs->n * sizeof (int));
+      double *rs = (double *) malloc ((size_t) cs->n * sizeof (double));
+      double *csc = (double *) malloc ((size_t) cs->n * sizeof (double));
+      rc = (rowmap && rs && csc) ? nkp_rowperm_largediag (cs->n, cs->rowptr, cs->colind, cs->val, rowmap, rs, csc) : NKP_ENOMEM;
+      if (rc == 0) {
+         int i, moved = 0;
+         for (i = 0; i < cs->n; i++)
+            moved += rowmap[i] != i;
+         if (&dbg_lvl != NULL && dbg_lvl)
+            printf ("(0) nkp: RowPerm = LargeDiag moves %d of %d rows\n", moved, cs->n);
+         rc = nkp_create_rowperm (&cs->h, cs->n, cs->rowptr, cs->colind, have ? ci : NULL, have ? cj : NULL,
+                                  have ? ck : NULL, &o, rowmap, rs, csc, 0, 1, NULL);
+         if (rc == 0 && sp && sp->perm_r)
+            for (i = 0; i < cs->n; i++)
+               sp->perm_r[i] = rowmap[i];
+      }
+      else
+         fprintf (stderr, "(0) nkp_rowperm_largediag failed with code %d\n", rc);
+      free (rowmap);
+      free (rs);
+      free (csc);
+   }
+   else
+      rc = nkp_create (&cs->h, cs->n, cs->rowptr, cs->colind, have ? ci : NULL, have ? cj : NULL, have ? ck : NULL, &o);
    free (ci);
    free (cj);
    free (ck);
@@ -498,7 +526,7 @@ pdgssvx_ABglobal (superlu_dist_options_t * options, SuperMatrix * A, ScalePermst
             cs->csc_to_crs[p] = q;
          }
       free (next);
-      if (create_and_factor (cs, ScalePermstruct, info))
+      if (create_and_factor (cs, options, ScalePermstruct, info))
          return;
       factored_now = 1;
    }
@@ -588,7 +616,7 @@ pdgssvx (superlu_dist_options_t * options, SuperMatrix * A, ScalePermstruct_t * 
       free (rp);
       free (cid);
       free (vl);
-      if (create_and_factor (cs, ScalePermstruct, info))
+      if (create_and_factor (cs, options, ScalePermstruct, info))
          return;
       factored_now = 1;
       options->SolveInitialized = YES;

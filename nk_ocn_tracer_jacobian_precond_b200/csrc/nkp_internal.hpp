@@ -286,9 +286,11 @@ struct Plan {
 // directory of the on-disk ordering cache; nullptr or "" disables it.  Until this is called the
 // NKP_ANALYSIS_CACHE environment variable decides.
 void set_analysis_cache_dir(const char* dir);
-// coords may be null; otherwise coords[d] (d = 0,1,2) are per-unknown integer coordinates
+// coords may be null; otherwise coords[d] (d = 0,1,2) are per-unknown integer coordinates.
+// rowmap may be null; otherwise row i of the CRS is row rowmap[i] of the matrix that is factored (static row
+// permutation for a large diagonal, rowperm.cpp): Plan::perm then numbers the COLUMNS, row i goes to perm[rowmap[i]].
 int analyse(int n, const int* rowptr, const int* colind, const int* const coords[3],
-            const Options& opt, Plan& plan);
+            const Options& opt, Plan& plan, const int* rowmap = nullptr);
 
 inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
 

@@ -152,6 +152,8 @@ struct nkp_solver {
     double* d_val = nullptr;
     int64_t* d_scatter = nullptr;
     int* d_perm = nullptr;
+    int* d_permr = nullptr;     // row numbering of the permuted system: d_perm, or perm[rowmap[.]] with a static row permutation
+    bool fixed_scale = false;   // d_R / d_C were supplied at creation (nkp_create_rowperm) and are reused by every factorisation
     int* d_bidx = nullptr;
     int* d_rel = nullptr;
     int* d_clo = nullptr;
@@ -284,7 +286,8 @@ void nkp_default_options(nkp_options* o) {
 
 static int create_impl(nkp_solver** out, int n, const int* rowptr, const int* colind, const int* ci,
                        const int* cj, const int* ck, const nkp_options* opt_in, int rank, int nranks,
-                       const void* unique_id, int* d_rowptr_adopt = nullptr, int* d_colind_adopt = nullptr) {
+                       const void* unique_id, int** d_rowptr_adopt = nullptr, int** d_colind_adopt = nullptr,
+                       const int* rowmap = nullptr, const double* row_scale = nullptr, const double* col_scale = nullptr) {
     if (!out || n <= 0 || !rowptr || !colind || rank < 0 || nranks < 1 || rank >= nranks ||
         (nranks > 1 && !unique_id)) {
         g_err = "nkp_create: invalid argument";
@@ -321,6 +324,11 @@ static int create_impl(nkp_solver** out, int n, const int* rowptr, const int* co
     po.nranks = nranks;
     s->rank = rank;
     s->nranks = nranks;
+    if (d_rowptr_adopt && d_colind_adopt) {   // pattern already on the device (nkp_create_be): ours from here on
+        s->d_rowptr = *d_rowptr_adopt;
+        s->d_colind = *d_colind_adopt;
+        *d_rowptr_adopt = *d_colind_adopt = nullptr;
+    }
     if (getenv("NKP_BIG_ENTRIES")) po.big_entries = atoll(getenv("NKP_BIG_ENTRIES"));
     if (getenv("NKP_BIG_ROWS")) po.big_rows = atoi(getenv("NKP_BIG_ROWS"));
     if (getenv("NKP_OUTER")) po.outer = po.top_outer = std::max(1, atoi(getenv("NKP_OUTER")));
@@ -329,13 +337,13 @@ static int create_impl(nkp_solver** out, int n, const int* rowptr, const int* co
     if (getenv("NKP_SPLIT_MAX")) po.split_max = std::max(1, atoi(getenv("NKP_SPLIT_MAX")));
     const int* coords[3] = {ci, cj, ck};
     auto t0 = std::chrono::steady_clock::now();
-    int rc = analyse(n, rowptr, colind, (ci || cj || ck) ? coords : nullptr, po, s->plan);
+    int rc = analyse(n, rowptr, colind, (ci || cj || ck) ? coords : nullptr, po, s->plan, rowmap);
     s->t_analysis = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     if (rc) {
         char b[128];
         snprintf(b, sizeof b, "analysis failed with code %d", rc);
         g_err = b;
-        delete s;
+        nkp_destroy(s);
         return NKP_EANALYSIS;
     }
     Plan& P = s->plan;
@@ -386,16 +394,20 @@ static int create_impl(nkp_solver** out, int n, const int* rowptr, const int* co
         std::vector<int> rp(rowptr, rowptr + n + 1), cidx(colind, colind + s->nnz), ridx((size_t)s->nnz);
         for (int i = 0; i < n; i++)
             for (int p = rowptr[i]; p < rowptr[i + 1]; p++) ridx[p] = i;
-        if (d_rowptr_adopt && d_colind_adopt) {   // already on the device (nkp_create_be)
-            s->d_rowptr = d_rowptr_adopt;
-            s->d_colind = d_colind_adopt;
-        } else {
+        if (!s->d_rowptr) {
             if (upload(&s->d_rowptr, rp)) return NKP_ECUDA;
             if (upload(&s->d_colind, cidx)) return NKP_ECUDA;
         }
         if (upload(&s->d_rowidx, ridx)) return NKP_ECUDA;
         if (upload(&s->d_scatter, P.scatter)) return NKP_ECUDA;
         if (upload(&s->d_perm, P.perm)) return NKP_ECUDA;
+        if (rowmap) {
+            std::vector<int> permr((size_t)n);
+            for (int i = 0; i < n; i++) permr[i] = P.perm[rowmap[i]];
+            if (upload(&s->d_permr, permr)) return NKP_ECUDA;
+        } else {
+            s->d_permr = s->d_perm;
+        }
         if (upload(&s->d_bidx, P.bidx)) return NKP_ECUDA;
         if (upload(&s->d_rel, P.rel)) return NKP_ECUDA;
         if (upload(&s->d_clo, P.child_lo)) return NKP_ECUDA;
@@ -455,6 +467,22 @@ static int create_impl(nkp_solver** out, int n, const int* rowptr, const int* co
         CK(cudaMalloc((void**)&s->d_val, sizeof(double) * (size_t)s->nnz));
         CK(cudaMalloc((void**)&s->d_R, sizeof(double) * n));
         CK(cudaMalloc((void**)&s->d_C, sizeof(double) * n));
+        if (row_scale && col_scale) {
+            // rounded to powers of two like the solver's own equilibration: scaling then adds no rounding error
+            std::vector<double> sc((size_t)n);
+            for (int pass = 0; pass < 2; pass++) {
+                const double* src = pass ? col_scale : row_scale;
+                for (int i = 0; i < n; i++) {
+                    if (!(src[i] > 0) || !std::isfinite(src[i])) {
+                        g_err = "nkp_create_rowperm: scalings must be positive and finite";
+                        return NKP_EINVAL;
+                    }
+                    sc[i] = std::ldexp(1.0, (int)std::lround(std::log2(src[i])));
+                }
+                CK(cudaMemcpy(pass ? s->d_C : s->d_R, sc.data(), sizeof(double) * n, cudaMemcpyHostToDevice));
+            }
+            s->fixed_scale = true;
+        }
         CK(cudaMalloc((void**)&s->d_W, sizeof(double) * (size_t)std::max<int64_t>(P.solve_pool_len, 1) * MAX_NR));
         CK(cudaMalloc((void**)&s->d_y, sizeof(double) * (size_t)n * MAX_NR));
         CK(cudaMalloc((void**)&s->d_r, sizeof(double) * (size_t)n * MAX_NR));
@@ -526,15 +554,10 @@ int nkp_create_be(nkp_solver** out, int n, long long nnz, const void* rowptr_be,
         cudaFree(d_ci);
         return rc;
     }
-    rc = create_impl(out, n, rp.data(), cidx.data(), ci, cj, ck, &o, 0, 1, nullptr, d_rp, d_ci);
-    if (rc) {
-        // create_impl frees adopted arrays through nkp_destroy once they are attached; before that they are still ours
-        // (analysis failure happens before attachment)
-        if (rc == NKP_EANALYSIS || rc == NKP_EINVAL) {
-            cudaFree(d_rp);
-            cudaFree(d_ci);
-        }
-    }
+    rc = create_impl(out, n, rp.data(), cidx.data(), ci, cj, ck, &o, 0, 1, nullptr, &d_rp, &d_ci);
+    // create_impl takes the two arrays over (and nulls our pointers) as soon as its solver object exists
+    if (d_rp) cudaFree(d_rp);
+    if (d_ci) cudaFree(d_ci);
     return rc;
 }
 
@@ -542,6 +565,18 @@ int nkp_create_dist(nkp_solver** out, int n, const int* rowptr, const int* colin
                     const int* cj, const int* ck, const nkp_options* opt_in, int rank, int nranks,
                     const void* unique_id) {
     return create_impl(out, n, rowptr, colind, ci, cj, ck, opt_in, rank, nranks, unique_id);
+}
+
+// static row permutation (+ scalings) chosen by the caller, e.g. with nkp_rowperm_largediag (rowperm.cpp)
+int nkp_create_rowperm(nkp_solver** out, int n, const int* rowptr, const int* colind, const int* ci, const int* cj,
+                       const int* ck, const nkp_options* opt_in, const int* rowmap, const double* row_scale,
+                       const double* col_scale, int rank, int nranks, const void* unique_id) {
+    if (!rowmap || (row_scale == nullptr) != (col_scale == nullptr)) {
+        g_err = "nkp_create_rowperm: rowmap is required; row_scale and col_scale come together or not at all";
+        return NKP_EINVAL;
+    }
+    return create_impl(out, n, rowptr, colind, ci, cj, ck, opt_in, rank, nranks, unique_id, nullptr, nullptr, rowmap,
+                       row_scale, col_scale);
 }
 
 int nkp_comm_unique_id(void* unique_id) {
@@ -698,7 +733,9 @@ static int do_factor(nkp_solver* s) {
     const int nb = P.opt.nb;
     CK(cudaEventRecord(s->ev[0], st));
     // equilibration
-    if (s->opt.equil) {
+    if (s->fixed_scale) {
+        // R and C came with the static row permutation and stay (SamePattern_SameRowPerm)
+    } else if (s->opt.equil) {
         k_row_scale<<<(n + 255) / 256, 256, 0, st>>>(n, s->d_rowptr, s->d_val, s->d_R);
         CK(cudaMemsetAsync(s->d_C, 0, sizeof(double) * n, st));
         k_col_max<<<(unsigned)((nnz + 255) / 256), 256, 0, st>>>(nnz, s->d_rowidx, s->d_colind, s->d_val, s->d_R, s->d_C);
@@ -719,7 +756,7 @@ static int do_factor(nkp_solver* s) {
     s->prof_used = 0;
     prof_mark(s, KC_OTHER);
     // with equilibration every row/column max is in [1,2): threshold relative to ||A|| ~ 1
-    double tiny = std::sqrt(2.220446049250313e-16) * (s->opt.equil ? 1.0 : s->amax);
+    double tiny = std::sqrt(2.220446049250313e-16) * ((s->opt.equil || s->fixed_scale) ? 1.0 : s->amax);
     for (cudaEvent_t e : s->trace_ev) cudaEventDestroy(e);
     s->trace_ev.clear();
     s->trace_name.clear();
@@ -816,7 +853,7 @@ int nkp_factor_device(nkp_solver* s, const double* d_nzval) {
     CK(cudaSetDevice(s->opt.device));
     if (d_nzval != s->d_val)
         CK(cudaMemcpyAsync(s->d_val, d_nzval, sizeof(double) * (size_t)s->nnz, cudaMemcpyDeviceToDevice, s->stream));
-    if (!s->opt.equil && device_amax(s)) return NKP_ECUDA;
+    if (!s->opt.equil && !s->fixed_scale && device_amax(s)) return NKP_ECUDA;
     return do_factor(s);
 }
 
@@ -862,7 +899,7 @@ int nkp_factor_be(nkp_solver* s, const void* nzval_be) {
                                                                       s->d_val, s->nnz);
     s->launches++;
     CK(cudaGetLastError());
-    if (!s->opt.equil && device_amax(s)) return NKP_ECUDA;
+    if (!s->opt.equil && !s->fixed_scale && device_amax(s)) return NKP_ECUDA;
     return do_factor(s);
 }
 
@@ -1084,7 +1121,7 @@ static int solve_chunk(nkp_solver* s, double* dB, int ldb, int nr, double* berr_
     const double safe2 = safe1 / eps;
     // x = 0-th solve
     if (nrp > nr) CK(cudaMemsetAsync(s->d_y, 0, sizeof(double) * (size_t)n * nrp, st));
-    k_permute_in<<<g, 256, 0, st>>>(n, nr, s->d_perm, s->d_R, dB, ldb, s->d_y);
+    k_permute_in<<<g, 256, 0, st>>>(n, nr, s->d_permr, s->d_R, dB, ldb, s->d_y);
     check_finite(s, "the right-hand side", s->d_y, (int64_t)n * nr);
     if (sweeps_nr(s, nrp)) return NKP_ECUDA;
     check_finite(s, "the first sweep pair's result", s->d_y, (int64_t)n * nr);
@@ -1133,7 +1170,7 @@ static int solve_chunk(nkp_solver* s, double* dB, int ldb, int nr, double* berr_
         }
         if (!go || it >= s->opt.refine_max) break;
         it++;
-        k_permute_in<<<g, 256, 0, st>>>(n, nr, s->d_perm, s->d_R, s->d_r, n, s->d_y);
+        k_permute_in<<<g, 256, 0, st>>>(n, nr, s->d_permr, s->d_R, s->d_r, n, s->d_y);
         check_finite(s, "a residual", s->d_y, (int64_t)n * nr);
         if (sweeps_nr(s, nrp)) return NKP_ECUDA;
         check_finite(s, "a correction sweep's result", s->d_y, (int64_t)n * nr);
@@ -1431,7 +1468,7 @@ int nkp_sweeps_device(nkp_solver* s, double* dB, int ldb, int nrhs) {
     const int g = (n + 255) / 256;
     CK(cudaEventRecord(s->ev[2], s->stream));
     if (nrp > nrhs) CK(cudaMemsetAsync(s->d_y, 0, sizeof(double) * (size_t)n * nrp, s->stream));
-    k_permute_in<<<g, 256, 0, s->stream>>>(n, nrhs, s->d_perm, s->d_R, dB, ldb, s->d_y);
+    k_permute_in<<<g, 256, 0, s->stream>>>(n, nrhs, s->d_permr, s->d_R, dB, ldb, s->d_y);
     if (sweeps_nr(s, nrp)) return NKP_ECUDA;
     k_permute_out<<<g, 256, 0, s->stream>>>(n, nrhs, s->d_perm, s->d_C, s->d_y, dB, ldb, 0, 0xffu);
     s->launches += 2;
@@ -1526,6 +1563,7 @@ void nkp_destroy(nkp_solver* s) {
     if (s->cstream) cudaStreamDestroy(s->cstream);
     if (s->ev_p) cudaEventDestroy(s->ev_p);
     if (s->ev_b) cudaEventDestroy(s->ev_b);
+    if (s->d_permr && s->d_permr != s->d_perm) cudaFree(s->d_permr);
     if (s->d_pub) cudaFree(s->d_pub);
     if (s->d_slab) cudaFree(s->d_slab);
     if (s->d_pack) cudaFree(s->d_pack);
@@ -1545,6 +1583,7 @@ void nkp_destroy(nkp_solver* s) {
     for (int i = 0; i < MAX_NR; i++)
         if (s->ev_col[i]) cudaEventDestroy(s->ev_col[i]);
     for (cudaEvent_t e : s->prof_ev) cudaEventDestroy(e);
+    for (cudaEvent_t e : s->trace_ev) cudaEventDestroy(e);
     for (cudaEvent_t e : s->ev_field)
         if (e) cudaEventDestroy(e);
     if (s->stream) cudaStreamDestroy(s->stream);

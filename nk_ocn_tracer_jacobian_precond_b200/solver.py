@@ -65,6 +65,10 @@ def load_library():
     lib.nkp_create_dist.argtypes = [P(vp), C.c_int, P(C.c_int), P(C.c_int), P(C.c_int), P(C.c_int), P(C.c_int),
                                     P(NkpOptions), C.c_int, C.c_int, C.c_char_p]
     lib.nkp_comm_unique_id.argtypes = [C.c_char_p]
+    lib.nkp_rowperm_largediag.argtypes = [C.c_int, P(C.c_int), P(C.c_int), P(C.c_double), P(C.c_int), P(C.c_double),
+                                          P(C.c_double)]
+    lib.nkp_create_rowperm.argtypes = [P(vp), C.c_int, P(C.c_int), P(C.c_int), P(C.c_int), P(C.c_int), P(C.c_int),
+                                       P(NkpOptions), P(C.c_int), P(C.c_double), P(C.c_double), C.c_int, C.c_int, C.c_char_p]
     lib.nkp_create_be.argtypes = [P(vp), C.c_int, C.c_longlong, vp, vp, P(C.c_int), P(C.c_int), P(C.c_int), P(NkpOptions)]
     lib.nkp_crs_finalize_device.argtypes = [C.c_int, vp, vp, vp, C.c_int, P(C.c_longlong), P(C.c_int)]
     lib.nkp_bswap32_device.argtypes = [vp, C.c_longlong]
@@ -125,6 +129,22 @@ def _iptr(a):
     return a.ctypes.data_as(C.POINTER(C.c_int)) if a is not None else None
 
 
+def rowperm_largediag(n, rowptr, colind, nzval):
+    """Static row permutation for a large diagonal (nkp_rowperm_largediag: what pdgssvx does under
+    RowPerm = LargeDiag, MC64 job 5).  Host computation.  Returns (rowmap, row_scale, col_scale)."""
+    rowptr = np.ascontiguousarray(rowptr, dtype=np.int32)
+    colind = np.ascontiguousarray(colind, dtype=np.int32)
+    nzval = np.ascontiguousarray(nzval, dtype=np.float64)
+    rowmap = np.zeros(int(n), dtype=np.int32)
+    R = np.zeros(int(n))
+    Cs = np.zeros(int(n))
+    dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    rc = load_library().nkp_rowperm_largediag(int(n), _iptr(rowptr), _iptr(colind), dp(nzval), _iptr(rowmap), dp(R), dp(Cs))
+    if rc != 0:
+        raise NkpError(f"nkp_rowperm_largediag failed with code {rc} (structurally singular matrix?)")
+    return rowmap, R, Cs
+
+
 def crs_finalize_device(n, d_rowptr, d_colind, d_val, strip_zeros=True):
     """sum_dup_vals + (strip_matrix_zeros) + sort_cols_all_rows (src/matrix.c:3621-3770) on device arrays, in place;
     arguments are device addresses.  Returns (nnz, dup_cnt)."""
@@ -158,8 +178,10 @@ class TracerJacobianSolver:
     src/matrix.c:322-329) enabling the geometric nested dissection.
     """
 
-    def __init__(self, n, rowptr, colind, coords=None, comm=None, file_byte_order=False, **opts):
+    def __init__(self, n, rowptr, colind, coords=None, comm=None, file_byte_order=False, rowperm=None, **opts):
         """comm: None (one GPU) or (rank, nranks, unique_id_bytes) for one-process-per-GPU runs.
+        rowperm: None, or (rowmap, row_scale, col_scale) as returned by rowperm_largediag (the scalings may be None):
+        static row permutation of the factored matrix (nkp_create_rowperm).
         file_byte_order=True: rowptr / colind are the big-endian NC_INT bytes of the matrix file (bytes-like, n + 1 and
         nnz values); they are converted on the device (nkp_create_be)."""
         lib = load_library()
@@ -182,7 +204,18 @@ class TracerJacobianSolver:
         if coords is not None:
             ci, cj, ck = (np.ascontiguousarray(c, dtype=np.int32) if c is not None else None for c in coords)
         self._h = C.c_void_p()
-        if file_byte_order:
+        if rowperm is not None:
+            assert not file_byte_order
+            rowmap, rs, cs = rowperm
+            rowmap = np.ascontiguousarray(rowmap, dtype=np.int32)
+            dp = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.float64).ctypes.data_as(C.POINTER(C.c_double))
+            rs_keep = None if rs is None else np.ascontiguousarray(rs, dtype=np.float64)
+            cs_keep = None if cs is None else np.ascontiguousarray(cs, dtype=np.float64)
+            rank, nranks, uid = comm if comm is not None else (0, 1, None)
+            _check(lib.nkp_create_rowperm(C.byref(self._h), self.n, _iptr(rowptr), _iptr(colind), _iptr(ci), _iptr(cj), _iptr(ck),
+                                          C.byref(o), _iptr(rowmap), dp(rs_keep), dp(cs_keep), int(rank), int(nranks),
+                                          None if uid is None else bytes(uid)), "nkp_create_rowperm")
+        elif file_byte_order:
             _check(lib.nkp_create_be(C.byref(self._h), self.n, self.nnz, C.c_void_p(rp_raw.ctypes.data), C.c_void_p(ci_raw.ctypes.data),
                                      _iptr(ci), _iptr(cj), _iptr(ck), C.byref(o)), "nkp_create_be")
         elif comm is None:

@@ -151,10 +151,13 @@ int nkp_sim_last_order_cached(void) { return g_last_order_cached; }
 // With nranks == 1 this is the plain single-GPU plan.  Returns the solution seen by rank 0.
 // stats_out[0..7]: n_fronts, n_levels, max_front, nnz_lu, heap_len(rank 0), flops, tiny_pivots, analysis seconds
 // part_out (may be null, 4 ints per rank): fronts owned, xfers as src, xfers as dst, local flops / 1e6
-int nkp_sim_run_dist(int n, const int* rowptr, const int* colind, const double* val, const int* ci,
-                     const int* cj, const int* ck, int nb, int leaf, const double* B, int nrhs,
-                     double* X, double* stats_out, int* perm_out, int analysis_only, int nranks,
-                     double* part_out) {
+// rowmap / Rs / Cs (each may be null): static row permutation and row / column scalings of the factored matrix
+// (csrc/rowperm.cpp, nkp_create_rowperm): heap gets Rs[i] a_ij Cs[j] at the position of (rowmap[i], j); the
+// right-hand side enters as Rs[i] b[i] at row rowmap[i], the solution leaves as Cs[j] y[j].
+static int sim_run_impl(int n, const int* rowptr, const int* colind, const double* val, const int* ci,
+                        const int* cj, const int* ck, int nb, int leaf, const double* B, int nrhs,
+                        double* X, double* stats_out, int* perm_out, int analysis_only, int nranks,
+                        double* part_out, const int* rowmap, const double* Rs, const double* Cs) {
     Options opt;
     opt.nb = nb;
     opt.leaf = leaf;
@@ -171,7 +174,7 @@ int nkp_sim_run_dist(int n, const int* rowptr, const int* colind, const double* 
     std::vector<Plan> plans(nranks);
     for (int r = 0; r < nranks; r++) {
         opt.rank = r;
-        int rc = analyse(n, rowptr, colind, (ci || cj || ck) ? coords : nullptr, opt, plans[r]);
+        int rc = analyse(n, rowptr, colind, (ci || cj || ck) ? coords : nullptr, opt, plans[r], rowmap);
         if (rc) return rc;
     }
     Plan& P0 = plans[0];
@@ -206,14 +209,18 @@ int nkp_sim_run_dist(int n, const int* rowptr, const int* colind, const double* 
     }
     if (analysis_only) return 0;
 
+    std::vector<double> sval(val, val + P0.nnz);
+    if (Rs && Cs)
+        for (int i = 0; i < n; i++)
+            for (int p = rowptr[i]; p < rowptr[i + 1]; p++) sval[p] = val[p] * Rs[i] * Cs[colind[p]];
     double amax = 0;
-    for (int64_t p = 0; p < P0.nnz; p++) amax = std::max(amax, std::fabs(val[p]));
+    for (int64_t p = 0; p < P0.nnz; p++) amax = std::max(amax, std::fabs(sval[p]));
     double tiny = std::sqrt(2.220446049250313e-16) * amax;
     std::vector<std::vector<double>> heaps(nranks);
     for (int r = 0; r < nranks; r++) {
         heaps[r].assign((size_t)plans[r].heap_len, 0.0);
         for (int64_t p = 0; p < plans[r].nnz; p++)
-            if (plans[r].scatter[p] >= 0) heaps[r][plans[r].scatter[p]] += val[p];
+            if (plans[r].scatter[p] >= 0) heaps[r][plans[r].scatter[p]] += sval[p];
     }
 
     int nrepl = 0;
@@ -331,7 +338,7 @@ int nkp_sim_run_dist(int n, const int* rowptr, const int* colind, const double* 
             fprintf(stderr, "[sim] rhs %d refine it %d: relres before = %.3e\n", c, it, std::sqrt(rn / bn));
         }
         for (int r = 0; r < nranks; r++)
-            for (int i = 0; i < n; i++) ys[r][P0.perm[i]] = rhs[i];
+            for (int i = 0; i < n; i++) ys[r][P0.perm[rowmap ? rowmap[i] : i]] = (Rs ? Rs[i] : 1.0) * rhs[i];
         for (int l = P0.nlevels - 1; l >= 0; l--) {
             // update vectors of children owned elsewhere
             if (l + 1 < P0.nlevels)
@@ -434,11 +441,27 @@ int nkp_sim_run_dist(int n, const int* rowptr, const int* colind, const double* 
             for (int r = 0; r < nranks; r++)
                 if (r != pr.root) memcpy(ys[r].data() + pr.lo, ys[pr.root].data() + pr.lo, sizeof(double) * (size_t)(pr.hi - pr.lo));
         for (int i = 0; i < n; i++) {
-            xacc[i] += ys[0][P0.perm[i]];
+            xacc[i] += (Cs ? Cs[i] : 1.0) * ys[0][P0.perm[i]];
             X[i + (int64_t)c * n] = xacc[i];
         }
       }
     return 0;
+}
+
+int nkp_sim_run_dist(int n, const int* rowptr, const int* colind, const double* val, const int* ci,
+                     const int* cj, const int* ck, int nb, int leaf, const double* B, int nrhs,
+                     double* X, double* stats_out, int* perm_out, int analysis_only, int nranks,
+                     double* part_out) {
+    return sim_run_impl(n, rowptr, colind, val, ci, cj, ck, nb, leaf, B, nrhs, X, stats_out, perm_out, analysis_only,
+                        nranks, part_out, nullptr, nullptr, nullptr);
+}
+
+int nkp_sim_run_rowperm(int n, const int* rowptr, const int* colind, const double* val, const int* ci,
+                        const int* cj, const int* ck, int nb, int leaf, const double* B, int nrhs,
+                        double* X, double* stats_out, int nranks, const int* rowmap, const double* Rs,
+                        const double* Cs) {
+    return sim_run_impl(n, rowptr, colind, val, ci, cj, ck, nb, leaf, B, nrhs, X, stats_out, nullptr, 0, nranks, nullptr,
+                        rowmap, Rs, Cs);
 }
 
 // Partition as seen by ONE rank (for the world_size-2 gloo test): owner_out[n_fronts],

@@ -237,10 +237,12 @@ def test_full_size_gx3v7_properties():
 DRV = {k: os.path.join(ROOT, "oracle", "_ref", k) for k in ("solve_ABglobal", "solve_ABdist")}
 
 
-@pytest.mark.parametrize("prog,nflag", [("solve_ABglobal", "4,4"), ("solve_ABdist", "1"), ("solve_ABdist", "2,2")])
-def test_reference_driver_cli(tmp_path, golden_matrix, prog, nflag):
+@pytest.mark.parametrize("prog,nflag,rowperm", [("solve_ABglobal", "4,4", 0), ("solve_ABdist", "1", 0), ("solve_ABdist", "2,2", 0),
+                                                 ("solve_ABglobal", "1", 1)])
+def test_reference_driver_cli(tmp_path, golden_matrix, prog, nflag, rowperm):
     """src/solve_ABglobal.c / src/solve_ABdist.c compiled unchanged against include/compat:
-    same command line, same matrix file, tracer fields solved in place, land untouched (KAT-7)."""
+    same command line, same matrix file, tracer fields solved in place, land untouched (KAT-7).
+    rowperm = 1: the shim honours the drivers' RowPerm = LargeDiag (NKP_ROWPERM=1, csrc/rowperm.cpp)."""
     if not os.path.exists(DRV[prog]):
         pytest.skip("reference drivers not built (oracle/_ref)")
     from nk_ocn_tracer_jacobian_precond_b200 import synth
@@ -254,9 +256,10 @@ def test_reference_driver_cli(tmp_path, golden_matrix, prog, nflag):
     tr = tmp_path / "tracers.nc"
     synth.write_tracer_file(str(tr), g, fields)
     out = subprocess.run([DRV[prog], "-D", "1", "-n", nflag, "-v", "T1,T2", str(mat), str(tr)],
-                         capture_output=True, text=True, timeout=300)
+                         capture_output=True, text=True, timeout=300, env=dict(os.environ, NKP_ROWPERM=str(rowperm)))
     assert out.returncode == 0, out.stderr
     assert "info = 0" in out.stdout
+    assert ("RowPerm = LargeDiag moves" in out.stdout) == bool(rowperm)
     i, j, k = c["i"], c["j"], c["k"]
     ocean = np.zeros((10, 24, 20), bool)
     ocean[k, j, i] = True
@@ -620,3 +623,52 @@ def test_device_assembly_is_bit_identical_to_gen_A(golden_matrix, shape, seed):
     xo = oracle_solve.solve(n, ref["rowptr"], ref["colind"], ref["nzval"], b)
     assert np.linalg.norm(x - xo) / np.linalg.norm(xo) <= SOL_TOL
     s.close()
+
+
+def test_largediag_row_permutation(golden_matrix, golden_rhs, reftest_matrix, reftest_rhs):
+    """nkp_create_rowperm: the static row permutation pdgssvx applies under RowPerm = LargeDiag (src/solve_ABglobal.c:332-334).
+    (1) on the operand as it is, the permuted factorisation must give the golden solutions like the default path;
+    (2) with the rows of the operand scrambled (the default path has no usable pivots then: tests/test_rowperm.py shows it
+    on the CPU plan interpreter) the permuted factorisation solves it."""
+    from nk_ocn_tracer_jacobian_precond_b200 import solver
+    c = _golden_case(golden_matrix)
+    n = c["n"]
+    rp_info = solver.rowperm_largediag(n, c["rowptr"], c["colind"], c["nzval"])
+    assert (rp_info[0] != np.arange(n)).sum() > 500   # LargeDiag really moves rows of this operator family
+    s = solver.TracerJacobianSolver(n, c["rowptr"], c["colind"], coords=(c["i"], c["j"], c["k"]), rowperm=rp_info)
+    s.factor(c["nzval"])
+    X = np.asfortranarray(golden_rhs["B"].copy())
+    berr = s.solve(X)
+    rel = np.linalg.norm(X - golden_rhs["X"], axis=0) / np.linalg.norm(golden_rhs["X"], axis=0)
+    assert rel.max() <= SOL_TOL, rel
+    res = np.linalg.norm(_A(c) @ X - golden_rhs["B"], axis=0) / np.linalg.norm(golden_rhs["B"], axis=0)
+    assert res.max() <= RES_TOL
+    assert berr.max() <= 8 * oracle_solve.EPS and s.stats()["tiny_pivots"] == 0
+    # permutation without the scalings (the solver's own equilibration): same answers to the tolerance
+    s2 = solver.TracerJacobianSolver(n, c["rowptr"], c["colind"], coords=(c["i"], c["j"], c["k"]),
+                                     rowperm=(rp_info[0], None, None))
+    s2.factor(c["nzval"])
+    X2 = np.asfortranarray(golden_rhs["B"].copy())
+    s2.solve(X2)
+    assert (np.linalg.norm(X2 - golden_rhs["X"], axis=0) / np.linalg.norm(golden_rhs["X"], axis=0)).max() <= SOL_TOL
+    s.close()
+    s2.close()
+
+    # (2) scrambled rows of the reference-option operand
+    c = _golden_case(reftest_matrix)
+    rng = np.random.default_rng(3)
+    q = rng.permutation(n)
+    As = _A(c)[q, :].tocsr()
+    As.sort_indices()
+    rp, ci, nz = As.indptr.astype(np.int32), As.indices.astype(np.int32), As.data.copy()
+    B = np.asfortranarray(reftest_rhs["B"][q, :])
+    s1 = solver.TracerJacobianSolver(n, rp, ci, coords=(c["i"], c["j"], c["k"]), rowperm=solver.rowperm_largediag(n, rp, ci, nz))
+    s1.factor(nz)
+    X1 = B.copy(order="F")
+    berr = s1.solve(X1)
+    rel1 = np.linalg.norm(X1 - reftest_rhs["X"], axis=0) / np.linalg.norm(reftest_rhs["X"], axis=0)
+    assert rel1.max() <= SOL_TOL, rel1
+    res1 = np.linalg.norm(As @ X1 - B, axis=0) / np.linalg.norm(B, axis=0)
+    assert res1.max() <= RES_TOL and berr.max() <= 8 * oracle_solve.EPS
+    assert s1.stats()["tiny_pivots"] == 0
+    s1.close()
