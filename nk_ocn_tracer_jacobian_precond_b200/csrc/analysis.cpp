@@ -85,7 +85,7 @@ void build_graph(int n, const int* rowptr, const int* colind, Graph& g) {
 }
 
 struct TreeNode {
-    std::vector<int> verts;     // original vertex ids, ascending
+    std::vector<int> verts;     // original vertex ids in elimination order
     std::vector<int> children;
     int parent = -1;
 };
@@ -378,8 +378,9 @@ uint64_t fnv1a(uint64_t h, const void* data, size_t bytes) {
 
 uint64_t ordering_key(int n, const int* rowptr, const int* colind, const int* const* coords, const Options& opt) {
     uint64_t h = 1469598103934665603ull;
-    const int tag[4] = {0x4e4b5031 /* format 1 */, n, opt.leaf, opt.period_i};
+    const int tag[6] = {0x4e4b5032 /* format 2 */, n, opt.leaf, opt.period_i, opt.etree_supernodes, opt.relax_small};
     h = fnv1a(h, tag, sizeof tag);
+    h = fnv1a(h, &opt.relax_frac, sizeof opt.relax_frac);
     h = fnv1a(h, rowptr, sizeof(int) * ((size_t)n + 1));
     h = fnv1a(h, colind, sizeof(int) * (size_t)rowptr[n]);
     for (int d = 0; d < 3; d++) {
@@ -484,6 +485,192 @@ void set_analysis_cache_dir(const char* dir) {
     g_cache_dir = dir ? dir : "";
 }
 
+
+namespace {
+
+// ---- assembly tree from the elimination tree of the dissection ordering ---------------------------------------
+// The dissection tree is a good ORDERING but a poor assembly tree for this operator family: ocean subdomains cut by
+// a coordinate plane are often disconnected (basins behind ridges, land), and a separator treated as one dense front
+// then carries the union of the boundaries of all the pieces it touches -- measured at gx3v7-shape: 2.08x the flops
+// and 1.44x the factor entries that the same ordering needs (independent symbolic factorisation,
+// oracle/plan_sim.cpp::nkp_true_colcounts).  So the fronts are re-derived the textbook way: elimination tree of
+// pattern(A + A^T) in the dissection numbering (Liu), postorder, column counts (Gilbert, Ng & Peyton 1994: skeleton
+// leaves + least common ancestors, O(nnz alpha)), supernodes = maximal paths of the tree whose columns share their
+// structure, relaxed: a path is joined with its parent path while the explicit zeros this stores stay below
+// `relax_frac` of the joined panel (or the joined panel has at most `relax_small` columns).  The result replaces
+// `nodes` (same TreeNode format, postorder, verts in elimination order), so everything downstream -- boundary sets,
+// levels, memory plan, task lists, the multi-GPU mapping, the ordering cache -- is unchanged.
+void supernodes_from_etree(const Graph& g, std::vector<TreeNode>& nodes, std::vector<int>& roots, const Options& opt) {
+    const int n = g.n;
+    // numbering of the dissection tree: nodes in index order (postorder), vertices in stored order
+    std::vector<int> num((size_t)n), inv((size_t)n);
+    {
+        int next = 0;
+        for (const TreeNode& t : nodes)
+            for (int v : t.verts) {
+                num[v] = next;
+                inv[next] = v;
+                next++;
+            }
+    }
+    // elimination tree (path compression over the "virtual ancestor")
+    std::vector<int> parent((size_t)n, -1);
+    {
+        std::vector<int> anc((size_t)n, -1);
+        for (int i = 0; i < n; i++) {
+            const int v = inv[i];
+            for (int64_t q = g.xadj[v]; q < g.xadj[v + 1]; q++) {
+                int k = num[g.adj[q]];
+                while (k != -1 && k < i) {
+                    const int nx = anc[k];
+                    anc[k] = i;
+                    if (nx == -1) parent[k] = i;
+                    k = nx;
+                }
+            }
+        }
+    }
+    // postorder (children in increasing order: the highest-numbered child directly precedes its parent)
+    std::vector<int> post((size_t)n), ipost((size_t)n);
+    {
+        std::vector<int> head((size_t)n, -1), next((size_t)n, -1), stack;
+        std::vector<int> root_list;
+        for (int j = n - 1; j >= 0; j--) {   // reversed, so that the lists come out ascending
+            if (parent[j] < 0) {
+                root_list.push_back(j);
+                continue;
+            }
+            next[j] = head[parent[j]];
+            head[parent[j]] = j;
+        }
+        std::reverse(root_list.begin(), root_list.end());
+        int k = 0;
+        for (int r : root_list) {
+            stack.push_back(r);
+            while (!stack.empty()) {
+                const int v = stack.back();
+                const int c = head[v];
+                if (c == -1) {
+                    stack.pop_back();
+                    post[k] = v;
+                    ipost[v] = k;
+                    k++;
+                } else {
+                    head[v] = next[c];
+                    stack.push_back(c);
+                }
+            }
+        }
+    }
+    // final numbering fin = ipost o num; etree in it (a postordered tree: every subtree is a contiguous range)
+    std::vector<int> fin((size_t)n), finv((size_t)n), par((size_t)n, -1);
+    for (int v = 0; v < n; v++) {
+        fin[v] = ipost[num[v]];
+        finv[fin[v]] = v;
+    }
+    for (int j = 0; j < n; j++)
+        if (parent[j] >= 0) par[ipost[j]] = ipost[parent[j]];
+    // column counts (diagonal included)
+    std::vector<int64_t> cc((size_t)n, 0);
+    std::vector<int> first((size_t)n, -1);   // first (lowest) descendant: the subtree of j is the range [first[j], j]
+    {
+        std::vector<int> maxfirst((size_t)n, -1), prevleaf((size_t)n, -1), anc((size_t)n);
+        for (int k = 0; k < n; k++) {
+            cc[k] = first[k] == -1 ? 1 : 0;   // leaf of the tree
+            for (int j = k; j != -1 && first[j] == -1; j = par[j]) first[j] = k;
+        }
+        for (int i = 0; i < n; i++) anc[i] = i;
+        for (int j = 0; j < n; j++) {
+            if (par[j] != -1) cc[par[j]]--;
+            const int v = finv[j];
+            for (int64_t q = g.xadj[v]; q < g.xadj[v + 1]; q++) {
+                const int i = fin[g.adj[q]];
+                if (i <= j || first[j] <= maxfirst[i]) continue;   // j is not a leaf of the row subtree of i
+                maxfirst[i] = first[j];
+                const int jprev = prevleaf[i];
+                prevleaf[i] = j;
+                cc[j]++;
+                if (jprev != -1) {   // subsequent leaf: the overlap with the previous one ends at their common ancestor
+                    int q2 = jprev;
+                    while (q2 != anc[q2]) q2 = anc[q2];
+                    for (int s2 = jprev; s2 != q2;) {
+                        const int sp = anc[s2];
+                        anc[s2] = q2;
+                        s2 = sp;
+                    }
+                    cc[q2]--;
+                }
+            }
+            if (par[j] != -1) anc[j] = par[j];
+        }
+        for (int j = 0; j < n; j++)
+            if (par[j] != -1) cc[par[j]] += cc[j];
+    }
+    // supernodes: left to right; the supernode that ends at column f - 1 is joined with the one starting at f when it
+    // hangs under f and the padding is acceptable.  zeros[] = explicit zeros already accepted inside a supernode.
+    struct SN {
+        int first, s;
+        int64_t r, zeros;
+    };
+    std::vector<SN> sn;
+    // Whole subtrees of at most `leaf` columns become ONE front, as the leaves of the dissection were: inside them the
+    // tree is a thicket of short paths (dozens of levels of tiny supernodes) whose exact structure saves a percent of
+    // the flops and costs the sweeps a launch pair per level.  sub_root[f] = root of the maximal such subtree that
+    // starts at column f.
+    std::vector<int> sub_root((size_t)n, -1);
+    for (int j = 0; j < n; j++) {
+        const int size = j - first[j] + 1;
+        if (size > opt.leaf || size < 2) continue;
+        if (par[j] != -1 && par[j] - first[par[j]] + 1 <= opt.leaf) continue;   // not maximal
+        sub_root[first[j]] = j;
+    }
+    for (int j = 0; j < n; j++) {
+        SN cur{j, 1, cc[j] - 1, 0};
+        if (sub_root[j] >= 0) {
+            const int root = sub_root[j];
+            const int64_t sz = root - j + 1;
+            int64_t have = 0;
+            for (int c = j; c <= root; c++) have += cc[c];
+            cur = SN{j, (int)sz, cc[root] - 1, sz * (sz + 1) / 2 + sz * (cc[root] - 1) - have};
+            j = root;
+        }
+        while (!sn.empty()) {
+            const SN& pr = sn.back();
+            if (par[pr.first + pr.s - 1] != cur.first) break;
+            // joined: pr.s + cur.s pivots with boundary cur.r; the columns of pr get cur.s + cur.r - pr.r rows they lack
+            const int64_t z = pr.zeros + cur.zeros + (int64_t)pr.s * (cur.s + cur.r - pr.r);
+            const int64_t sj = (int64_t)pr.s + cur.s;
+            const int64_t tot = sj * (sj + 1) / 2 + sj * cur.r;
+            if (!(sj <= opt.relax_small || (double)z <= opt.relax_frac * (double)tot)) break;
+            cur.first = pr.first;
+            cur.s = (int)sj;
+            cur.zeros = z;
+            sn.pop_back();
+        }
+        sn.push_back(cur);   // the next column may still join it
+    }
+    // (a column arrives as a supernode of its own; every time it extends the supernode to its left, the supernode
+    //  before that one is looked at again -- the accepted zeros are cumulative, so the bound holds for the result)
+    const int ns = (int)sn.size();
+    std::vector<int> sn_of((size_t)n);
+    for (int q = 0; q < ns; q++)
+        for (int a = 0; a < sn[q].s; a++) sn_of[sn[q].first + a] = q;
+    std::vector<TreeNode> out((size_t)ns);
+    roots.clear();
+    for (int q = 0; q < ns; q++) {
+        out[q].verts.resize((size_t)sn[q].s);
+        for (int a = 0; a < sn[q].s; a++) out[q].verts[a] = finv[sn[q].first + a];
+        const int p = par[sn[q].first + sn[q].s - 1];
+        out[q].parent = p < 0 ? -1 : sn_of[p];
+        if (p < 0) roots.push_back(q);
+    }
+    for (int q = 0; q < ns; q++)
+        if (out[q].parent >= 0) out[out[q].parent].children.push_back(q);
+    nodes.swap(out);
+}
+
+}  // namespace
+
 int analyse(int n, const int* rowptr_in, const int* colind_in, const int* const coords[3],
             const Options& opt, Plan& plan, const int* rowmap) {
     plan = Plan();
@@ -530,6 +717,7 @@ int analyse(int n, const int* rowptr_in, const int* colind_in, const int* const 
         roots.clear();        // a rejected cache file may have left partial data behind
         ds.nodes.clear();
         ds.run(roots);
+        if (opt.etree_supernodes) supernodes_from_etree(g, ds.nodes, roots, opt);
         if (!cdir.empty()) save_ordering(cache_path(cdir, key), key, n, ds.nodes, roots);
     }
     std::vector<TreeNode>& nodes = ds.nodes;

@@ -216,6 +216,10 @@ struct Options {
     int outer = 8;         // inner panels per outer block (wide Schur updates use K = outer*nb)
     int top_outer = 8;     // the same for the distributed top fronts (multi-GPU): width of a distribution block / nb
     int leaf = 96;         // stop dissecting below this many unknowns
+    int etree_supernodes = 1;   // fronts = relaxed supernodes of the elimination tree of the dissection ordering (0: the dissection
+                                // nodes themselves, one dense front per separator / leaf -- the round-1 assembly tree)
+    double relax_frac = 0.10;   // ... a supernode is joined with its parent while the explicit zeros stay below this share
+    int relax_small = 32;       // ... or the joined supernode has at most this many columns
     int tm = 128, tn = 64; // GEMM tile (must match the kernel)
     int trsm_rows = 128;   // rows per TRSM CTA
     int add_tile = 32;     // extend-add tile
@@ -225,7 +229,7 @@ struct Options {
     int big_rows = 768;             // ... and so do tall fronts (few pivots, long boundary): one warp would crawl
     int rank = 0, nranks = 1;       // multi-GPU: this process' rank (one GPU per rank)
     double split_tol = 0.03;        // multi-GPU: accepted flop imbalance (max / mean - 1) of the two halves of a rank range
-    int split_max = 8;              // ... and the largest number of candidate subtrees the splitting may produce per range
+    int split_max = 16;             // ... and the largest number of candidate subtrees the splitting may produce per range
 };
 
 struct Plan {

@@ -335,6 +335,9 @@ static int create_impl(nkp_solver** out, int n, const int* rowptr, const int* co
     if (getenv("NKP_TOP_OUTER")) po.top_outer = std::max(1, atoi(getenv("NKP_TOP_OUTER")));
     if (getenv("NKP_SPLIT_TOL")) po.split_tol = atof(getenv("NKP_SPLIT_TOL"));
     if (getenv("NKP_SPLIT_MAX")) po.split_max = std::max(1, atoi(getenv("NKP_SPLIT_MAX")));
+    if (getenv("NKP_SUPERNODES")) po.etree_supernodes = atoi(getenv("NKP_SUPERNODES"));
+    if (getenv("NKP_RELAX_FRAC")) po.relax_frac = atof(getenv("NKP_RELAX_FRAC"));
+    if (getenv("NKP_RELAX_SMALL")) po.relax_small = atoi(getenv("NKP_RELAX_SMALL"));
     const int* coords[3] = {ci, cj, ck};
     auto t0 = std::chrono::steady_clock::now();
     int rc = analyse(n, rowptr, colind, (ci || cj || ck) ? coords : nullptr, po, s->plan, rowmap);

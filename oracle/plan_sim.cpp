@@ -140,6 +140,13 @@ void sim_invert_diag(double* H, const DiagTask& t) {
 
 static int g_last_order_cached = 0;
 
+// assembly-tree options from the environment (the same variables csrc/solver.cu reads)
+static void tree_env(Options& opt) {
+    if (getenv("NKP_SUPERNODES")) opt.etree_supernodes = atoi(getenv("NKP_SUPERNODES"));
+    if (getenv("NKP_RELAX_FRAC")) opt.relax_frac = atof(getenv("NKP_RELAX_FRAC"));
+    if (getenv("NKP_RELAX_SMALL")) opt.relax_small = atoi(getenv("NKP_RELAX_SMALL"));
+}
+
 extern "C" {
 
 // ordering cache of the analysis (csrc/analysis.cpp): directory, and whether the last analysis used it
@@ -166,6 +173,7 @@ static int sim_run_impl(int n, const int* rowptr, const int* colind, const doubl
     if (getenv("NKP_TOP_OUTER")) opt.top_outer = atoi(getenv("NKP_TOP_OUTER"));
     if (getenv("NKP_SPLIT_TOL")) opt.split_tol = atof(getenv("NKP_SPLIT_TOL"));
     if (getenv("NKP_SPLIT_MAX")) opt.split_max = atoi(getenv("NKP_SPLIT_MAX"));
+    tree_env(opt);
     if (getenv("NKP_SIM_TM")) opt.tm = atoi(getenv("NKP_SIM_TM"));
     if (getenv("NKP_SIM_TN")) opt.tn = atoi(getenv("NKP_SIM_TN"));
     opt.verbose = getenv("NKP_SIM_VERBOSE") ? atoi(getenv("NKP_SIM_VERBOSE")) : 0;
@@ -472,6 +480,7 @@ int nkp_sim_partition(int n, const int* rowptr, const int* colind, const int* ci
     Options opt;
     opt.nb = nb;
     opt.leaf = leaf;
+    tree_env(opt);
     if (opt.tn > nb) opt.tn = nb;
     opt.rank = rank;
     opt.nranks = nranks;
@@ -517,6 +526,7 @@ int nkp_sim_check_plan(int n, const int* rowptr, const int* colind, const int* c
     Options opt;
     opt.nb = nb;
     opt.leaf = leaf;
+    tree_env(opt);
     if (opt.tn > nb) opt.tn = nb;
     opt.nranks = nranks;
     const int* coords[3] = {ci, cj, ck};
@@ -593,6 +603,75 @@ int nkp_sim_check_plan(int n, const int* rowptr, const int* colind, const int* c
                 next_panel[it.front] = it.idx - 1;
             }
         }
+    }
+    return 0;
+}
+
+// the fronts of the single-GPU plan: out[4 t .. 4 t + 3] = first pivot, pivots, boundary size, level; returns their number
+int nkp_sim_fronts(int n, const int* rowptr, const int* colind, const int* ci, const int* cj, const int* ck, int nb,
+                   int leaf, int* out, int cap, int* perm_out) {
+    Options opt;
+    opt.nb = nb;
+    opt.leaf = leaf;
+    tree_env(opt);
+    if (opt.tn > nb) opt.tn = nb;
+    const int* coords[3] = {ci, cj, ck};
+    Plan P;
+    if (analyse(n, rowptr, colind, (ci || cj || ck) ? coords : nullptr, opt, P)) return -1;
+    const int nf = (int)P.fronts.size();
+    for (int t = 0; t < nf && t < cap; t++) {
+        out[4 * t] = P.fronts[t].first;
+        out[4 * t + 1] = P.fronts[t].s;
+        out[4 * t + 2] = P.fronts[t].r;
+        out[4 * t + 3] = P.fronts[t].level;
+    }
+    if (perm_out) memcpy(perm_out, P.perm.data(), sizeof(int) * n);
+    return nf;
+}
+
+// INDEPENDENT symbolic factorisation (shares nothing with csrc/analysis.cpp but the permutation it is given):
+// below-diagonal column counts of the Cholesky factor of pattern(A + A^T) in the numbering perm[old] = new --
+// elimination tree by path compression (Liu), then one row-subtree traversal per row, which visits every nonzero
+// of L exactly once.  O(nnz(L)) time, O(n + nnz(A)) memory.  From the counts c_j: nnz(L + U) = 2 sum c_j + n and
+// the LU flops of a structurally symmetric elimination, sum (2 c_j^2 + c_j) -- the minimum any method pays for
+// this ordering; the plan's dense fronts pay for padding on top (tests/test_oracle_and_plan.py).
+int nkp_true_colcounts(int n, const int* rowptr, const int* colind, const int* perm, long long* counts) {
+    std::vector<int64_t> lp((size_t)n + 1, 0);
+    for (int i = 0; i < n; i++)
+        for (int p = rowptr[i]; p < rowptr[i + 1]; p++) {
+            const int a = perm[i], b = perm[colind[p]];
+            if (a != b) lp[std::max(a, b) + 1]++;
+        }
+    for (int i = 0; i < n; i++) lp[i + 1] += lp[i];
+    std::vector<int> lo((size_t)lp[n]);   // for every row (new numbering): its neighbours with a smaller number
+    {
+        std::vector<int64_t> pos(lp.begin(), lp.end() - 1);
+        for (int i = 0; i < n; i++)
+            for (int p = rowptr[i]; p < rowptr[i + 1]; p++) {
+                const int a = perm[i], b = perm[colind[p]];
+                if (a != b) lo[pos[std::max(a, b)]++] = std::min(a, b);
+            }
+    }
+    std::vector<int> parent((size_t)n, -1), anc((size_t)n, -1);
+    for (int i = 0; i < n; i++)
+        for (int64_t p = lp[i]; p < lp[i + 1]; p++) {
+            int k = lo[p];
+            while (k != -1 && k < i) {
+                const int next = anc[k];
+                anc[k] = i;
+                if (next == -1) parent[k] = i;
+                k = next;
+            }
+        }
+    std::vector<int> mark((size_t)n, -1);
+    for (int i = 0; i < n; i++) counts[i] = 0;
+    for (int i = 0; i < n; i++) {
+        mark[i] = i;
+        for (int64_t p = lp[i]; p < lp[i + 1]; p++)
+            for (int k = lo[p]; k != -1 && mark[k] != i; k = parent[k]) {
+                mark[k] = i;
+                counts[k]++;
+            }
     }
     return 0;
 }
