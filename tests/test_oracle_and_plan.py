@@ -314,3 +314,31 @@ def test_plan_flops_against_the_minimum_of_its_ordering(sim_lib, shape, monkeypa
         ratios[mode] = (stats[5] / true_flops, stats[3] / true_nnz)
     assert ratios["1"][0] <= 1.7 and ratios["1"][1] <= 1.6, ratios   # measured 1.52 / 1.42 and 1.30 / 1.30 with leaf = 16; 1.07 / 1.15 at gx3v7-shape with the default leaf
     assert ratios["0"][0] >= 1.5 * ratios["1"][0], ratios
+
+
+def test_degenerate_trees_through_the_plan_interpreter(sim_lib):
+    """Shapes of elimination tree the ocean operand does not produce but a caller's matrix may: forests (diagonal and
+    block-diagonal matrices), a star (arrow matrix: every leaf column is its own front), a path (tridiagonal), 1 x 1."""
+    rng = np.random.default_rng(0)
+    n = 300
+    arrow = sp.lil_matrix((n, n))
+    arrow.setdiag(4.0)
+    arrow[n - 1, :] = 1.0
+    arrow[:, n - 1] = 1.0
+    arrow[n - 1, n - 1] = 400.0
+    cases = {
+        "diagonal": sp.diags(rng.uniform(1, 2, 10)),
+        "1x1": sp.diags([3.0]),
+        "block diagonal": sp.block_diag([sp.random(7, 7, 0.5, random_state=k) + 10 * sp.eye(7) for k in range(5)] + [2 * sp.eye(3)]),
+        "arrow": arrow,
+        "path": sp.diags([-np.ones(999), 4 * np.ones(1000), -np.ones(999)], [-1, 0, 1]),
+    }
+    for name, A in cases.items():
+        A = sp.csr_matrix(A)
+        A.sort_indices()
+        m = A.shape[0]
+        xs = rng.standard_normal((m, 2))
+        X, stats, perm = run_sim(sim_lib, m, A.indptr.astype(np.int32), A.indices.astype(np.int32), A.data.astype(np.float64),
+                                 None, A @ xs)
+        assert sorted(perm.tolist()) == list(range(m)), name
+        assert np.abs(X - xs).max() <= 1e-12, name
