@@ -97,7 +97,7 @@ void nkp_default_options(nkp_options* opt);
 /* On-disk cache of the pattern-dependent ordering (the expensive part of the analysis), keyed by a hash
  * of (rowptr, colind, coordinates, ordering options).  The reference repeats the whole analysis in every
  * process (src/solve_ABglobal.c:350-353); with a cache directory set, nkp_create stores the nested-
- * dissection tree there and later processes -- e.g. the next Newton iteration's solver run -- read it
+ * dissection ordering and its assembly tree there and later processes -- e.g. the next Newton iteration's solver run -- read it
  * back.  Process-wide; dir = NULL or "" disables it.  Without this call the environment variable
  * NKP_ANALYSIS_CACHE is consulted.  A missing, stale or damaged file only means "recompute". */
 int nkp_set_analysis_cache(const char* dir);

@@ -13,8 +13,10 @@
 //      handles the periodic i direction of src/matrix.c:795-798 and the +-2 reach of
 //      upwind3 without special cases).  Without coordinates a BFS level-structure
 //      dissection is used.
-//   3. assembly tree = dissection tree (separators/leaves are the supernodes),
-//      postorder numbering, symbolic front structures
+//   3. assembly tree = relaxed supernodes of the elimination tree of that ordering
+//      (supernodes_from_etree below: etree, postorder, column counts, path supernodes;
+//      NKP_SUPERNODES=0 keeps the dissection nodes themselves as the fronts),
+//      symbolic front structures by a bottom-up merge
 //   4. memory plan (factor arena + two ping-pong pools of update matrices)
 //   5. static task lists for every kernel launch of the numeric phase and solves
 //
@@ -359,7 +361,7 @@ struct Dissector {
 // The nested dissection is the expensive, purely pattern-dependent part of the analysis (about two
 // thirds of it at gx1v6-shape).  The reference refactors from scratch on every process start
 // (src/solve_ABglobal.c:350-353); with a cache directory set (nkp_set_analysis_cache or the
-// NKP_ANALYSIS_CACHE environment variable) the dissection tree is stored under a key derived from
+// NKP_ANALYSIS_CACHE environment variable) the ordering and its assembly tree are stored under a key derived from
 // the pattern, the coordinates and the ordering options, and later processes read it back.
 // File: magic, key, n, nf, nroots, node sizes[nf], node parents[nf], roots[nroots], iperm[n]
 // (= the vertices of the nodes in node order).  Any mismatch or short read means "recompute".

@@ -267,7 +267,7 @@ struct Plan {
     int64_t nnz_lu = 0;        // stored factor entries incl. diagonal
     int max_front = 0;
     double t_order = 0, t_symbolic = 0, t_plan = 0;
-    bool order_cached = false;     // the dissection tree came from the on-disk cache
+    bool order_cached = false;     // ordering + assembly tree came from the on-disk cache
     // multi-GPU partition (identical on every rank)
     int rank = 0, nranks = 1;
     std::vector<int> owner;          // per front
