@@ -608,8 +608,15 @@ int nkp_sim_check_plan(int n, const int* rowptr, const int* colind, const int* c
 }
 
 // the fronts of the single-GPU plan: out[4 t .. 4 t + 3] = first pivot, pivots, boundary size, level; returns their number
+// (parent_out, may be null: index of the parent front, -1 for roots)
+int nkp_sim_fronts2(int n, const int* rowptr, const int* colind, const int* ci, const int* cj, const int* ck, int nb,
+                    int leaf, int* out, int cap, int* perm_out, int* parent_out);
 int nkp_sim_fronts(int n, const int* rowptr, const int* colind, const int* ci, const int* cj, const int* ck, int nb,
                    int leaf, int* out, int cap, int* perm_out) {
+    return nkp_sim_fronts2(n, rowptr, colind, ci, cj, ck, nb, leaf, out, cap, perm_out, nullptr);
+}
+int nkp_sim_fronts2(int n, const int* rowptr, const int* colind, const int* ci, const int* cj, const int* ck, int nb,
+                    int leaf, int* out, int cap, int* perm_out, int* parent_out) {
     Options opt;
     opt.nb = nb;
     opt.leaf = leaf;
@@ -624,6 +631,7 @@ int nkp_sim_fronts(int n, const int* rowptr, const int* colind, const int* ci, c
         out[4 * t + 1] = P.fronts[t].s;
         out[4 * t + 2] = P.fronts[t].r;
         out[4 * t + 3] = P.fronts[t].level;
+        if (parent_out) parent_out[t] = P.fronts[t].parent;
     }
     if (perm_out) memcpy(perm_out, P.perm.data(), sizeof(int) * n);
     return nf;
