@@ -672,3 +672,21 @@ def test_largediag_row_permutation(golden_matrix, golden_rhs, reftest_matrix, re
     assert res1.max() <= RES_TOL and berr.max() <= 8 * oracle_solve.EPS
     assert s1.stats()["tiny_pivots"] == 0
     s1.close()
+
+
+def test_dissection_node_fronts_remain_available(golden_matrix, golden_rhs, monkeypatch):
+    """NKP_SUPERNODES=0 (one dense front per dissection node, the assembly tree of round 1) is kept for A/B runs
+    (scripts/tree_ab.py); it must keep giving the golden solutions, with more flops than the default tree."""
+    c = _golden_case(golden_matrix)
+    flops = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("NKP_SUPERNODES", mode)
+        s = _solver(c)
+        s.factor(c["nzval"])
+        X = np.asfortranarray(golden_rhs["B"].copy())
+        s.solve(X)
+        rel = np.linalg.norm(X - golden_rhs["X"], axis=0) / np.linalg.norm(golden_rhs["X"], axis=0)
+        assert rel.max() <= SOL_TOL, (mode, rel)
+        flops[mode] = s.stats()["factor_flops"]
+        s.close()
+    assert flops["1"] < flops["0"]

@@ -342,3 +342,18 @@ def test_degenerate_trees_through_the_plan_interpreter(sim_lib):
                                  None, A @ xs)
         assert sorted(perm.tolist()) == list(range(m)), name
         assert np.abs(X - xs).max() <= 1e-12, name
+
+
+@pytest.mark.parametrize("nranks", [1, 4])
+def test_dissection_node_fronts_remain_available(sim_lib, golden_matrix, golden_rhs, monkeypatch, nranks):
+    """NKP_SUPERNODES=0: one dense front per dissection node (the assembly tree of round 1), kept for A/B runs."""
+    monkeypatch.setenv("NKP_SUPERNODES", "0")
+    monkeypatch.setenv("NKP_SIM_RANKS", str(nranks))
+    m = golden_matrix
+    coords = (m["tracer_state_ind_to_i"], m["tracer_state_ind_to_j"], m["tracer_state_ind_to_k"])
+    X, stats, _ = run_sim(sim_lib, m["n"], m["rowptr"], m["colind"], m["nzval_row_wise"], coords, golden_rhs["B"])
+    rel = np.linalg.norm(X - golden_rhs["X"], axis=0) / np.linalg.norm(golden_rhs["X"], axis=0)
+    assert rel.max() <= 1e-8 and stats[6] == 0
+    monkeypatch.setenv("NKP_SUPERNODES", "1")
+    _, stats_new, _ = run_sim(sim_lib, m["n"], m["rowptr"], m["colind"], m["nzval_row_wise"], coords, golden_rhs["B"])
+    assert stats_new[5] < stats[5]      # the elimination-tree supernodes need fewer flops
