@@ -357,3 +357,27 @@ def test_dissection_node_fronts_remain_available(sim_lib, golden_matrix, golden_
     monkeypatch.setenv("NKP_SUPERNODES", "1")
     _, stats_new, _ = run_sim(sim_lib, m["n"], m["rowptr"], m["colind"], m["nzval_row_wise"], coords, golden_rhs["B"])
     assert stats_new[5] < stats[5]      # the elimination-tree supernodes need fewer flops
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_random_patterns_through_analysis_and_interpreter(sim_lib, seed, monkeypatch):
+    """Arbitrary sparsity (not the stencil family): random unsymmetric / partly symmetric patterns without coordinates,
+    random panel width, leaf size, rank count and supernode relaxation -- ordering, elimination tree, supernodes, plan
+    and the lockstep interpreter must solve every one of them (diagonally dominant, so static pivoting is safe)."""
+    from test_rowperm import sim_rowperm
+    rng = np.random.default_rng(seed)
+    for trial in range(20):
+        n = int(rng.integers(2, 400))
+        A = sp.random(n, n, density=rng.choice([0.002, 0.01, 0.03, 0.1]), random_state=rng, format="csr")
+        if rng.random() < 0.5:
+            A = A + A.T * rng.random()
+        A = sp.csr_matrix(A + sp.diags(np.asarray(abs(A).sum(axis=1)).ravel() + 1.0))
+        A.sort_indices()
+        xs = rng.standard_normal((n, 2))
+        monkeypatch.setenv("NKP_RELAX_FRAC", str(rng.choice([0.0, 0.1, 0.3])))
+        monkeypatch.setenv("NKP_RELAX_SMALL", str(int(rng.choice([0, 8, 32]))))
+        rc, X, _ = sim_rowperm(sim_lib, n, A.indptr.astype(np.int32), A.indices.astype(np.int32), A.data.astype(np.float64),
+                               None, A @ xs, nranks=int(rng.choice([1, 2, 3, 5])), nb=int(rng.choice([8, 16, 64])),
+                               leaf=int(rng.choice([4, 16, 48, 96])))
+        assert rc == 0, (seed, trial, rc)
+        assert np.abs(X - xs).max() <= 1e-9, (seed, trial)
