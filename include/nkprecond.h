@@ -41,7 +41,8 @@ typedef struct nkp_solver nkp_solver;
 /* Options; zero-initialise then call nkp_default_options. */
 typedef struct nkp_options {
     int nb;              /* pivot block width (<= 64)                                    */
-    int leaf;            /* nested dissection stops below this many unknowns             */
+    int leaf;            /* nested dissection stops below this many unknowns; subtrees of */
+                         /* the elimination tree up to this size stay one front          */
     int equil;           /* 1: row/column equilibration (SuperLU Equil=YES)              */
     int refine_max;      /* max refinement steps (SuperLU IterRefine=SLU_DOUBLE, ITMAX)  */
     int device;          /* CUDA device ordinal                                          */
